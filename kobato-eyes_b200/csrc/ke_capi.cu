@@ -1,0 +1,154 @@
+// ke_capi.cu — context lifetime, error reporting, host-side Pillow coefficient tables.
+#include <cmath>
+#include <cstring>
+
+#include "ke_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void ke_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int ke_abi_version(void) { return KE_ABI_VERSION; }
+extern "C" const char* ke_last_error(void) { return g_err; }
+
+extern "C" int ke_ctx_create(int device, ke_ctx** out) {
+    KE_REQUIRE(out != nullptr, "ke_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        ke_set_error("ke_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return KE_E_CUDA;
+    }
+    KE_REQUIRE(device >= 0 && device < count, "ke_ctx_create: device %d out of range [0,%d)", device, count);
+    KeDeviceGuard guard(device);
+    cudaDeviceProp prop;
+    KE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        ke_set_error("ke_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                     prop.minor);
+        return KE_E_UNSUPPORTED;
+    }
+    ke_ctx* ctx = new (std::nothrow) ke_ctx();
+    if (!ctx) return KE_E_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    for (auto& s : ctx->copy_stream) KE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev) KE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    *out = ctx;
+    return KE_OK;
+}
+
+extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
+    if (!ctx) return;
+    KeDeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    ke_tables_free(ctx->tables);
+    for (auto p : ctx->d_scratch) cudaFree(p);
+    for (auto p : ctx->h_pinned) cudaFreeHost(p);
+    for (auto s : ctx->copy_stream)
+        if (s) cudaStreamDestroy(s);
+    for (auto ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    delete ctx;
+}
+
+extern "C" int ke_ctx_device(const ke_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" int ke_ctx_sm_count(const ke_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
+extern "C" int64_t ke_ctx_launch_count(const ke_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int ke_ctx_scratch(ke_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->d_scratch_bytes[slot] < bytes) {
+        if (ctx->d_scratch[slot]) KE_CUDA(cudaFree(ctx->d_scratch[slot]));
+        ctx->d_scratch[slot] = nullptr;
+        ctx->d_scratch_bytes[slot] = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        KE_CUDA(cudaMalloc(&ctx->d_scratch[slot], want));
+        ctx->d_scratch_bytes[slot] = want;
+    }
+    *out = ctx->d_scratch[slot];
+    return KE_OK;
+}
+
+int ke_ctx_pinned(ke_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->h_pinned_bytes[slot] < bytes) {
+        if (ctx->h_pinned[slot]) KE_CUDA(cudaFreeHost(ctx->h_pinned[slot]));
+        ctx->h_pinned[slot] = nullptr;
+        ctx->h_pinned_bytes[slot] = 0;
+        KE_CUDA(cudaMallocHost(&ctx->h_pinned[slot], bytes));
+        ctx->h_pinned_bytes[slot] = bytes;
+    }
+    *out = ctx->h_pinned[slot];
+    return KE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pillow 8bpc LANCZOS tables.  Double precision with libm sin on the HOST: the device's sin may
+// differ by an ulp and flip a quantised tap, and tables depend on (in,out) only.
+
+namespace {
+constexpr int kPrecisionBits = 32 - 8 - 2;
+constexpr double kLanczosSupport = 3.0;
+
+inline double sinc_pi(double x) {
+    if (x == 0.0) return 1.0;
+    const double px = x * M_PI;
+    return std::sin(px) / px;
+}
+inline double lanczos3(double x) { return (x >= -3.0 && x < 3.0) ? sinc_pi(x) * sinc_pi(x / 3.0) : 0.0; }
+
+struct Geometry {
+    double scale, filterscale, support;
+    int ksize;
+};
+inline Geometry geometry(int in_size, int out_size) {
+    Geometry g;
+    // Pillow keeps the box edges as C floats: (double)(in1 - in0) / outSize
+    g.scale = (double)((float)in_size - 0.0f) / (double)out_size;
+    g.filterscale = g.scale < 1.0 ? 1.0 : g.scale;
+    g.support = kLanczosSupport * g.filterscale;
+    g.ksize = (int)std::ceil(g.support) * 2 + 1;
+    return g;
+}
+}  // namespace
+
+extern "C" int ke_resample_ksize(int in_size, int out_size) {
+    if (in_size <= 0 || out_size <= 0) return KE_E_INVALID;
+    return geometry(in_size, out_size).ksize;
+}
+
+extern "C" int ke_resample_table(int in_size, int out_size, int32_t* kk, int32_t* bounds, int ksize) {
+    KE_REQUIRE(in_size > 0 && out_size > 0 && kk && bounds, "ke_resample_table: bad arguments");
+    const Geometry g = geometry(in_size, out_size);
+    KE_REQUIRE(ksize == g.ksize, "ke_resample_table: ksize %d != %d", ksize, g.ksize);
+    std::vector<double> w((size_t)g.ksize);
+    const double inv_fs = 1.0 / g.filterscale;
+    for (int o = 0; o < out_size; ++o) {
+        const double center = (o + 0.5) * g.scale;
+        int first = (int)(center - g.support + 0.5);
+        if (first < 0) first = 0;
+        int last = (int)(center + g.support + 0.5);
+        if (last > in_size) last = in_size;
+        const int count = last - first;
+        double total = 0.0;
+        for (int t = 0; t < count; ++t) {
+            w[t] = lanczos3((t + first - center + 0.5) * inv_fs);
+            total += w[t];
+        }
+        int32_t* row = kk + (size_t)o * g.ksize;
+        for (int t = 0; t < g.ksize; ++t) {
+            double v = 0.0;
+            if (t < count) v = (total != 0.0 ? w[t] / total : w[t]) * (double)(1 << kPrecisionBits);
+            row[t] = v < 0 ? (int32_t)(v - 0.5) : (int32_t)(v + 0.5);
+        }
+        bounds[2 * o] = first;
+        bounds[2 * o + 1] = count;
+    }
+    return KE_OK;
+}

@@ -1,0 +1,64 @@
+// ke_common.cuh — context, error plumbing and small device helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "kobato_b200.h"
+
+void ke_set_error(const char* fmt, ...);
+
+#define KE_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            ke_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return KE_E_CUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define KE_REQUIRE(cond, ...)        \
+    do {                             \
+        if (!(cond)) {               \
+            ke_set_error(__VA_ARGS__); \
+            return KE_E_INVALID;     \
+        }                            \
+    } while (0)
+
+// Device-resident Pillow coefficient tables, cached per image geometry (ke_phash.cu).
+struct KeTableCache;
+void ke_tables_free(KeTableCache* cache);
+
+struct ke_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int64_t launches = 0;
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // growable device / pinned scratch owned by the context
+    void* d_scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t d_scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* h_pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t h_pinned_bytes[4] = {0, 0, 0, 0};
+    KeTableCache* tables = nullptr;
+};
+
+int ke_ctx_scratch(ke_ctx* ctx, int slot, size_t bytes, void** out);
+int ke_ctx_pinned(ke_ctx* ctx, int slot, size_t bytes, void** out);
+
+struct KeDeviceGuard {
+    int prev = -1;
+    explicit KeDeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~KeDeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};

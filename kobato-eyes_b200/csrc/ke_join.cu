@@ -1,0 +1,327 @@
+// ke_join.cu — K2: all-pairs 64-bit Hamming threshold join (XOR + POPC), sm_100a.
+//
+// Replaces the candidate search of DuplicateScanner.build_clusters (reference
+// src/dup/scanner.py:227-290, distance = src/sig/phash.py:60-63).
+//
+// Layout / schedule
+//   * hashes: uint64[n] in HBM; 8 MB (1 M) .. 80 MB (10 M) -> L2 resident (126 MB), so the kernel
+//     is integer-issue bound, not memory bound.
+//   * The N x N upper triangle is cut into square tiles of TILE = 256*RPT hashes.  Tiles are
+//     enumerated linearly (row-major over c >= r) and dealt round-robin:
+//         tile t  ->  GPU  (t % part_count),  then CTA ((t / part_count) % gridDim.x)
+//     A persistent grid of sm_count * CTAS_PER_SM CTAs walks its tiles.
+//   * Per tile: each thread keeps RPT row hashes in registers (2*RPT b32), the CTA stages the
+//     TILE column hashes in shared memory once, and every thread streams them as warp-broadcast
+//     LDS.64 (all lanes read the same address: one wavefront).
+//   * Per pair (fast path): 2 LOP3 (xor) + 2 POPC + 1 IADD3 (pl + ph - (T+1)) + 1/2 LOP3 (OR of
+//     sign bits).  A check of the accumulated sign every CB columns x RPT rows enters the rare
+//     slow path, which re-evaluates those pairs with bounds, i<j, the optional band predicate,
+//     and appends (i, j, d) through one global atomic per hit.
+//   * Bounding pipe: POPC (2 per pair).  Algorithmic work per pair = 6 integer instructions.
+#include "ke_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kColBatch = 4;  // columns per fast-path check
+
+struct JoinArgs {
+    const uint64_t* hashes;
+    const uint64_t* band_allow;  // nullable
+    long long n;
+    int threshold;
+    unsigned flags;
+    int band_bits;
+    int band_count;
+    int part_index;
+    int part_count;
+    long long tiles_per_dim;
+    long long tile_total;  // tiles_per_dim*(tiles_per_dim+1)/2
+    uint32_t* out_i;
+    uint32_t* out_j;
+    uint8_t* out_d;
+    long long capacity;
+    unsigned long long* count;
+};
+
+__device__ __forceinline__ void tile_coords(long long t, long long nt, long long& r, long long& c) {
+    // row r owns tiles [r*nt - r(r-1)/2, ...) of length nt - r
+    double disc = (2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t;
+    long long rr = (long long)(((2.0 * nt + 1.0) - sqrt(disc)) * 0.5);
+    if (rr < 0) rr = 0;
+    if (rr >= nt) rr = nt - 1;
+    while (rr > 0 && rr * nt - rr * (rr - 1) / 2 > t) --rr;
+    while ((rr + 1) * nt - (rr + 1) * rr / 2 <= t) ++rr;
+    r = rr;
+    c = rr + (t - (rr * nt - rr * (rr - 1) / 2));
+}
+
+__device__ __forceinline__ bool band_match(uint64_t x, const JoinArgs& a, uint64_t allow) {
+    const uint64_t mask = a.band_bits >= 64 ? ~0ull : ((1ull << a.band_bits) - 1ull);
+    for (int b = 0; b < a.band_count; ++b) {
+        if ((((x >> (b * a.band_bits)) & mask) == 0ull) && ((allow >> b) & 1ull)) return true;
+    }
+    return false;
+}
+
+__device__ __noinline__ void emit_hits(const JoinArgs& a, const uint64_t* rows, long long row0, const uint64_t* cols,
+                                       long long col0, int jbase, int rpt) {
+    // Re-evaluate rpt x kColBatch pairs of this thread with every filter.
+    for (int k = 0; k < rpt; ++k) {
+        const long long i = row0 + threadIdx.x + (long long)k * kThreads;
+        if (i >= a.n) continue;
+        for (int jj = 0; jj < kColBatch; ++jj) {
+            const long long j = col0 + jbase + jj;
+            if (j >= a.n || j <= i) continue;
+            const uint64_t x = rows[k] ^ cols[jbase + jj];
+            const int d = __popcll(x);
+            if (d > a.threshold) continue;
+            if (a.flags & KE_JOIN_REQUIRE_BAND) {
+                const uint64_t allow = a.band_allow ? (a.band_allow[i] & a.band_allow[j]) : ~0ull;
+                if (!band_match(x, a, allow)) continue;
+            }
+            const unsigned long long slot = atomicAdd(a.count, 1ull);
+            if ((long long)slot < a.capacity) {
+                a.out_i[slot] = (uint32_t)i;
+                a.out_j[slot] = (uint32_t)j;
+                a.out_d[slot] = (uint8_t)d;
+            }
+        }
+    }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(kThreads) ke_join_kernel(const JoinArgs a) {
+    constexpr int TILE = kThreads * RPT;
+    __shared__ __align__(16) uint64_t cols[TILE];
+    const int neg_t1 = -(a.threshold + 1);
+
+    for (long long local = blockIdx.x;; local += gridDim.x) {
+        const long long t = local * a.part_count + a.part_index;
+        if (t >= a.tile_total) break;
+        long long tr, tc;
+        tile_coords(t, a.tiles_per_dim, tr, tc);
+        const long long row0 = tr * TILE, col0 = tc * TILE;
+
+        __syncthreads();  // previous tile's readers are done with cols[]
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const long long j = col0 + threadIdx.x + (long long)k * kThreads;
+            cols[threadIdx.x + k * kThreads] = j < a.n ? __ldg(a.hashes + j) : ~0ull;  // pad: distance 64 from row pad 0
+        }
+        uint32_t al[RPT], ah[RPT];
+        uint64_t rows[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const long long i = row0 + threadIdx.x + (long long)k * kThreads;
+            rows[k] = i < a.n ? __ldg(a.hashes + i) : 0ull;
+            al[k] = (uint32_t)rows[k];
+            ah[k] = (uint32_t)(rows[k] >> 32);
+        }
+        __syncthreads();
+
+        const long long col_valid = a.n - col0 < TILE ? a.n - col0 : TILE;
+        const int jend = (int)((col_valid + kColBatch - 1) / kColBatch) * kColBatch;
+#pragma unroll 1
+        for (int j = 0; j < jend; j += kColBatch) {
+            int acc = 0;
+#pragma unroll
+            for (int jj = 0; jj < kColBatch; ++jj) {
+                const uint2 b = *reinterpret_cast<const uint2*>(&cols[j + jj]);
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    // sign bit of (popc_lo + popc_hi - (T+1)) is set iff the pair is within T
+                    acc |= __popc(al[k] ^ b.x) + __popc(ah[k] ^ b.y) + neg_t1;
+                }
+            }
+            if (acc < 0) emit_hits(a, rows, row0, cols, col0, j, RPT);
+        }
+    }
+}
+
+template <int RPT>
+int launch_join(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream) {
+    constexpr int TILE = kThreads * RPT;
+    a.tiles_per_dim = (a.n + TILE - 1) / TILE;
+    a.tile_total = a.tiles_per_dim * (a.tiles_per_dim + 1) / 2;
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_join_kernel<RPT>, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long long mine = (a.tile_total - a.part_index + a.part_count - 1) / a.part_count;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > mine) grid = mine;
+    if (grid < 1) return KE_OK;
+    ke_join_kernel<RPT><<<(unsigned)grid, kThreads, 0, stream>>>(a);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
+int pick_rpt(const ke_ctx* ctx, long long n, int part_count) {
+    // Largest tile that still leaves every CTA >= 8 tiles (tail balance), smallest otherwise.
+    const int opts[3] = {8, 4, 2};
+    for (int rpt : opts) {
+        long long tile = (long long)kThreads * rpt;
+        long long nt = (n + tile - 1) / tile;
+        long long tiles = nt * (nt + 1) / 2 / part_count;
+        if (tiles >= (long long)ctx->sm_count * 4 * 8) return rpt;
+    }
+    return 2;
+}
+
+}  // namespace
+
+extern "C" int64_t ke_hamming_join_pairs(int64_t n, int part_index, int part_count) {
+    // Pairs are attributed to parts by tile; for reporting, an even split of the triangle.
+    if (n < 2 || part_count <= 0 || part_index < 0 || part_index >= part_count) return 0;
+    const int64_t total = n * (n - 1) / 2;
+    return total / part_count + (part_index < total % part_count ? 1 : 0);
+}
+
+extern "C" int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n, int threshold, uint32_t flags,
+                               int band_bits, int band_count, const uint64_t* d_band_allow, int part_index,
+                               int part_count, uint32_t* d_out_i, uint32_t* d_out_j, uint8_t* d_out_dist,
+                               int64_t capacity, unsigned long long* d_count, void* stream) {
+    KE_REQUIRE(ctx != nullptr, "ke_hamming_join: ctx is NULL");
+    KE_REQUIRE(n >= 0 && n <= 0xFFFFFFFFll, "ke_hamming_join: n=%lld out of range", (long long)n);
+    KE_REQUIRE(threshold >= 0 && threshold <= 64, "hamming_threshold must be in [0, 64]");
+    KE_REQUIRE(part_count >= 1 && part_index >= 0 && part_index < part_count, "ke_hamming_join: bad partition %d/%d",
+               part_index, part_count);
+    KE_REQUIRE(capacity >= 0 && d_count != nullptr, "ke_hamming_join: bad output arguments");
+    KE_REQUIRE(capacity == 0 || (d_out_i && d_out_j && d_out_dist), "ke_hamming_join: NULL output buffers");
+    if (flags & KE_JOIN_REQUIRE_BAND) {
+        KE_REQUIRE(band_bits > 0, "band_bits must be positive");
+        KE_REQUIRE(band_count > 0, "band_count must be positive");
+        KE_REQUIRE((long long)band_bits * band_count <= 64, "band config too large");
+    }
+    KeDeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    KE_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
+    if (n < 2) return KE_OK;
+    KE_REQUIRE(d_hashes != nullptr, "ke_hamming_join: d_hashes is NULL");
+    JoinArgs a;
+    a.hashes = d_hashes;
+    a.band_allow = (flags & KE_JOIN_REQUIRE_BAND) ? d_band_allow : nullptr;
+    a.n = n;
+    a.threshold = threshold;
+    a.flags = flags;
+    a.band_bits = band_bits;
+    a.band_count = band_count;
+    a.part_index = part_index;
+    a.part_count = part_count;
+    a.out_i = d_out_i;
+    a.out_j = d_out_j;
+    a.out_d = d_out_dist;
+    a.capacity = capacity;
+    a.count = d_count;
+    switch (pick_rpt(ctx, n, part_count)) {
+        case 8: return launch_join<8>(ctx, a, s);
+        case 4: return launch_join<4>(ctx, a, s);
+        default: return launch_join<2>(ctx, a, s);
+    }
+}
+
+extern "C" int ke_hamming_join_host(ke_ctx* ctx, const uint64_t* h_hashes, int64_t n, int threshold, uint32_t flags,
+                                    int band_bits, int band_count, const uint64_t* h_band_allow, int part_index,
+                                    int part_count, uint32_t* h_out_i, uint32_t* h_out_j, uint8_t* h_out_dist,
+                                    int64_t capacity, int64_t* out_count) {
+    KE_REQUIRE(ctx != nullptr && out_count != nullptr, "ke_hamming_join_host: NULL argument");
+    KE_REQUIRE(n >= 0 && capacity >= 0, "ke_hamming_join_host: negative size");
+    KE_REQUIRE(n == 0 || h_hashes != nullptr, "ke_hamming_join_host: h_hashes is NULL");
+    *out_count = 0;
+    KeDeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->copy_stream[0];
+    void *d_h = nullptr, *d_allow = nullptr, *d_i = nullptr, *d_j = nullptr, *d_d = nullptr, *d_cnt = nullptr;
+    int rc;
+    if ((rc = ke_ctx_scratch(ctx, 0, (size_t)n * 8 + 8, &d_h))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 1, (size_t)capacity * 4 + 8, &d_i))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 2, (size_t)capacity * 4 + 8, &d_j))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 3, (size_t)capacity + 8, &d_d))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 4, 64, &d_cnt))) return rc;
+    if (n) KE_CUDA(cudaMemcpyAsync(d_h, h_hashes, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (h_band_allow && (flags & KE_JOIN_REQUIRE_BAND) && n) {
+        if ((rc = ke_ctx_scratch(ctx, 5, (size_t)n * 8 + 8, &d_allow))) return rc;
+        KE_CUDA(cudaMemcpyAsync(d_allow, h_band_allow, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    }
+    rc = ke_hamming_join(ctx, (const uint64_t*)d_h, n, threshold, flags, band_bits, band_count,
+                         (const uint64_t*)d_allow, part_index, part_count, (uint32_t*)d_i, (uint32_t*)d_j,
+                         (uint8_t*)d_d, capacity, (unsigned long long*)d_cnt, s);
+    if (rc) return rc;
+    unsigned long long cnt = 0;
+    KE_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    KE_CUDA(cudaStreamSynchronize(s));
+    *out_count = (int64_t)cnt;
+    const size_t take = (size_t)((int64_t)cnt < capacity ? (int64_t)cnt : capacity);
+    if (take) {
+        KE_CUDA(cudaMemcpyAsync(h_out_i, d_i, take * 4, cudaMemcpyDeviceToHost, s));
+        KE_CUDA(cudaMemcpyAsync(h_out_j, d_j, take * 4, cudaMemcpyDeviceToHost, s));
+        KE_CUDA(cudaMemcpyAsync(h_out_dist, d_d, take, cudaMemcpyDeviceToHost, s));
+        KE_CUDA(cudaStreamSynchronize(s));
+    }
+    if ((int64_t)cnt > capacity) {
+        ke_set_error("ke_hamming_join_host: %llu pairs qualify but capacity is %lld", cnt, (long long)capacity);
+        return KE_E_CAPACITY;
+    }
+    return KE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// POPC issue-rate microbenchmark: 8 independent popc chains per thread, enough warps to
+// saturate the pipe.  Reports thread-level POPC per SM clock per SM.
+
+__global__ void __launch_bounds__(256) ke_popc_bench_kernel(int iters, uint32_t seed, uint32_t* sink,
+                                                            long long* clocks) {
+    uint32_t x0 = seed + threadIdx.x, x1 = x0 * 3u, x2 = x0 * 5u, x3 = x0 * 7u, x4 = x0 * 11u, x5 = x0 * 13u,
+             x6 = x0 * 17u, x7 = x0 * 19u;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __popc(x0) + seed;
+            x1 = __popc(x1) + seed;
+            x2 = __popc(x2) + seed;
+            x3 = __popc(x3) + seed;
+            x4 = __popc(x4) + seed;
+            x5 = __popc(x5) + seed;
+            x6 = __popc(x6) + seed;
+            x7 = __popc(x7) + seed;
+        }
+    }
+    const long long t1 = clock64();
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+}
+
+extern "C" int ke_microbench_popc(ke_ctx* ctx, int iters, double* popc_per_clk_per_sm, double* sm_clock_mhz) {
+    KE_REQUIRE(ctx && iters > 0 && popc_per_clk_per_sm, "ke_microbench_popc: bad arguments");
+    KeDeviceGuard guard(ctx->device);
+    const int ctas_per_sm = 4, threads = 256;
+    const int grid = ctx->sm_count * ctas_per_sm;
+    void *d_sink = nullptr, *d_clk = nullptr;
+    int rc;
+    if ((rc = ke_ctx_scratch(ctx, 6, (size_t)grid * threads * 4, &d_sink))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 7, (size_t)grid * 8, &d_clk))) return rc;
+    cudaEvent_t e0, e1;
+    KE_CUDA(cudaEventCreate(&e0));
+    KE_CUDA(cudaEventCreate(&e1));
+    ke_popc_bench_kernel<<<grid, threads>>>(iters / 8 + 1, 12345u, (uint32_t*)d_sink, (long long*)d_clk);  // warm
+    KE_CUDA(cudaEventRecord(e0));
+    ke_popc_bench_kernel<<<grid, threads>>>(iters, 12345u, (uint32_t*)d_sink, (long long*)d_clk);
+    KE_CUDA(cudaEventRecord(e1));
+    KE_CUDA(cudaEventSynchronize(e1));
+    ctx->launches += 2;
+    float ms = 0.f;
+    KE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> clk((size_t)grid);
+    KE_CUDA(cudaMemcpy(clk.data(), d_clk, (size_t)grid * 8, cudaMemcpyDeviceToHost));
+    long long worst = 0;
+    for (long long c : clk) worst = c > worst ? c : worst;
+    const double popc_per_sm = (double)iters * 64.0 * threads * ctas_per_sm;
+    *popc_per_clk_per_sm = popc_per_sm / (double)worst;
+    if (sm_clock_mhz) *sm_clock_mhz = (double)worst / (ms * 1e-3) / 1e6;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return KE_OK;
+}

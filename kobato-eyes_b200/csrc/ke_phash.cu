@@ -1,0 +1,683 @@
+// ke_phash.cu — K1: batched pHash + dHash of decoded uint8 images, sm_100a.
+//
+// Replaces sig.phash.phash / dhash (reference src/sig/phash.py:21-57): convert("L") ->
+// resize(LANCZOS) to 32x32 and 9x8 (Pillow's fixed-point arithmetic, byte-identical) -> DCT-II of
+// the 32x32 plane (FP64 on CUDA cores; tensor cores deliberately unused: a bit must not flip at
+// the threshold) -> 8x8 low block compared with the mean of its 63 AC terms -> 64-bit hash;
+// dHash = left<right compares on the 8x9 plane.
+//
+// One persistent CTA (256 threads) walks images; per image it streams row chunks:
+//   1. raw rows HBM -> shared memory with one 1-D TMA bulk copy (cp.async.bulk + mbarrier;
+//      16-byte aligned superset of the chunk), issued one chunk ahead of the compute;
+//   2. luma: L = (R*19595 + G*38470 + B*7471 + 0x8000) >> 16 with dp4a on the packed bytes
+//      -> uint8 luma rows in shared memory (odd word pitch: lane=row reads are conflict free);
+//   3. horizontal Lanczos taps for both targets (32 and 9 outputs per row).  Taps are 22-bit
+//      fixed point split into three byte planes so that 4 pixels x 1 plane = one dp4a:
+//      sum = D0 + 256*D1 + 65536*D2 (mod 2^32, exact because the true sum fits in int32).
+//      Lanes map to rows, so the tap words are warp-uniform (shared-memory broadcast);
+//   4. (2^21 + sum) >> 22, clip to uint8 -> the chunk's rows of the [H,32] and [H,9] planes;
+//   5. vertical taps are accumulated on the fly into per-thread registers (each thread owns 4
+//      of the 32x32 outputs; 72 threads own the 8x9 outputs), so no [H,32] plane is ever stored.
+// After the last chunk: vertical rounding, FP64 DCT (8x32 * 32x32 * 32x8), warp-shuffle mean
+// of the AC terms, ballot -> hash bits (first element = MSB).
+//
+// Algorithmic HBM bytes per image: h*w*c read + 16 written.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "ke_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kOutW = 32, kOutH = 32, kDW = 9, kDH = 8;
+constexpr int kOuts = kOutW + kDW;  // 41 horizontal outputs per row
+constexpr int kPrec = 22;
+
+// ------------------------------------------------------------------ host-side table cache
+
+struct HTable {           // horizontal pass, one per input width
+    uint4* d_coef = nullptr;   // packed byte-plane tap words, outputs back to back
+    int4* d_items = nullptr;   // work items {out, word_begin, word_count, 0}
+    int* d_meta = nullptr;     // [kOuts] first pixel word, [kOuts] offset into d_coef
+    int n_items = 0;
+    int coef_words = 0;
+};
+struct VTable {           // vertical pass, one per input height
+    int* d_kk32 = nullptr;
+    int* d_b32 = nullptr;
+    int* d_kk8 = nullptr;
+    int* d_b8 = nullptr;
+    int ks32 = 0, ks8 = 0;
+};
+
+}  // namespace
+
+struct KeTableCache {
+    std::map<int, HTable> h;
+    std::map<int, VTable> v;
+};
+
+void ke_tables_free(KeTableCache* cache) {
+    if (!cache) return;
+    for (auto& kv : cache->h) {
+        cudaFree(kv.second.d_coef);
+        cudaFree(kv.second.d_items);
+        cudaFree(kv.second.d_meta);
+    }
+    for (auto& kv : cache->v) {
+        cudaFree(kv.second.d_kk32);
+        cudaFree(kv.second.d_b32);
+        cudaFree(kv.second.d_kk8);
+        cudaFree(kv.second.d_b8);
+    }
+    delete cache;
+}
+
+namespace {
+
+template <typename T>
+int upload(const std::vector<T>& v, T** d) {
+    KE_CUDA(cudaMalloc((void**)d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) KE_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return KE_OK;
+}
+
+int get_htable(ke_ctx* ctx, int w, const HTable** out) {
+    if (!ctx->tables) ctx->tables = new KeTableCache();
+    auto it = ctx->tables->h.find(w);
+    if (it != ctx->tables->h.end()) {
+        *out = &it->second;
+        return KE_OK;
+    }
+    std::vector<uint4> coef;
+    std::vector<int> meta(2 * kOuts);
+    std::vector<int> nwords(kOuts);
+    const int outs[2] = {kOutW, kDW};
+    int o_base = 0;
+    for (int tbl = 0; tbl < 2; ++tbl) {
+        const int ow = outs[tbl];
+        const int ks = ke_resample_ksize(w, ow);
+        std::vector<int32_t> kk((size_t)ks * ow), bd(2 * (size_t)ow);
+        int rc = ke_resample_table(w, ow, kk.data(), bd.data(), ks);
+        if (rc) return rc;
+        for (int o = 0; o < ow; ++o) {
+            const int first = bd[2 * o], count = bd[2 * o + 1];
+            const int w0 = first / 4, lead = first % 4;
+            const int nw = (lead + count + 3) / 4;
+            meta[o_base + o] = w0;
+            meta[kOuts + o_base + o] = (int)coef.size();
+            nwords[o_base + o] = nw;
+            for (int t = 0; t < nw; ++t) {
+                uint32_t plane[3] = {0, 0, 0};
+                for (int b = 0; b < 4; ++b) {
+                    const int tap = 4 * t + b - lead;
+                    const int32_t k = (tap >= 0 && tap < count) ? kk[(size_t)o * ks + tap] : 0;
+                    // k = b0 + 256*b1 + 65536*b2 with b0,b1 unsigned bytes and b2 a signed byte
+                    const uint32_t u = (uint32_t)k;
+                    const int32_t top = k >> 16;  // arithmetic: floor(k / 65536)
+                    if (top < -128 || top > 127) {
+                        ke_set_error("resample tap %d does not fit 24 bits (w=%d -> %d)", k, w, ow);
+                        return KE_E_UNSUPPORTED;
+                    }
+                    plane[0] |= (u & 0xFFu) << (8 * b);
+                    plane[1] |= ((u >> 8) & 0xFFu) << (8 * b);
+                    plane[2] |= ((uint32_t)top & 0xFFu) << (8 * b);
+                }
+                coef.push_back(make_uint4(plane[0], plane[1], plane[2], 0u));
+            }
+        }
+        o_base += ow;
+    }
+    // Work items: split every output's word range into pieces no longer than the longest
+    // 32-wide output so the 8 warps get pieces of similar cost.
+    int piece = 1;
+    for (int o = 0; o < kOutW; ++o) piece = std::max(piece, nwords[o]);
+    std::vector<int4> items;
+    for (int o = 0; o < kOuts; ++o) {
+        const int parts = (nwords[o] + piece - 1) / piece;
+        for (int p = 0; p < parts; ++p) {
+            const int b = (int)((long long)nwords[o] * p / parts), e = (int)((long long)nwords[o] * (p + 1) / parts);
+            if (e > b) items.push_back(make_int4(o, b, e - b, 0));
+        }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return a.z > b.z; });
+    HTable t;
+    t.n_items = (int)items.size();
+    t.coef_words = (int)coef.size();
+    int rc;
+    if ((rc = upload(coef, &t.d_coef))) return rc;
+    if ((rc = upload(items, &t.d_items))) return rc;
+    if ((rc = upload(meta, &t.d_meta))) return rc;
+    auto ins = ctx->tables->h.emplace(w, t);
+    *out = &ins.first->second;
+    return KE_OK;
+}
+
+int get_vtable(ke_ctx* ctx, int h, const VTable** out) {
+    if (!ctx->tables) ctx->tables = new KeTableCache();
+    auto it = ctx->tables->v.find(h);
+    if (it != ctx->tables->v.end()) {
+        *out = &it->second;
+        return KE_OK;
+    }
+    VTable t;
+    t.ks32 = ke_resample_ksize(h, kOutH);
+    t.ks8 = ke_resample_ksize(h, kDH);
+    std::vector<int32_t> kk32((size_t)t.ks32 * kOutH), b32(2 * kOutH), kk8((size_t)t.ks8 * kDH), b8(2 * kDH);
+    int rc;
+    if ((rc = ke_resample_table(h, kOutH, kk32.data(), b32.data(), t.ks32))) return rc;
+    if ((rc = ke_resample_table(h, kDH, kk8.data(), b8.data(), t.ks8))) return rc;
+    if ((rc = upload(kk32, &t.d_kk32))) return rc;
+    if ((rc = upload(b32, &t.d_b32))) return rc;
+    if ((rc = upload(kk8, &t.d_kk8))) return rc;
+    if ((rc = upload(b8, &t.d_b8))) return rc;
+    auto ins = ctx->tables->v.emplace(h, t);
+    *out = &ins.first->second;
+    return KE_OK;
+}
+
+// ------------------------------------------------------------------ device helpers
+
+__constant__ double c_dct[8 * 32];  // orthonormal DCT-II rows 0..7 (what cv2.dct applies)
+
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint8_t clip8(int32_t v) {
+    v >>= kPrec;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+struct PhashArgs {
+    const uint8_t* img;
+    long long n;
+    int h, w, c;
+    long long img_stride, row_stride;
+    long long total_bytes;  // bytes addressable from img (bounds the aligned superset copies)
+    int rows_per_chunk;     // power of two <= 32
+    int pitch_words;        // odd
+    int raw_bytes;          // shared-memory bytes reserved for a raw chunk
+    int use_bulk;           // rows contiguous: chunk = one contiguous byte range
+    // tables
+    const uint4* coef;
+    const int4* items;
+    const int* meta;
+    int n_items, coef_words;
+    const int* kk32;
+    const int* b32;
+    const int* kk8;
+    const int* b8;
+    int ks32, ks8;
+    // outputs
+    uint64_t* phash;
+    uint64_t* dhash;
+    float* min_margin;
+    uint8_t* plane32;
+    uint8_t* plane98;
+};
+
+struct SmemLayout {
+    int coef, raw, luma, acc, hrow, x32, x98, tmat, ymat, meta, bar, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int coef_words, int raw_bytes, int rows, int pitch_words) {
+    SmemLayout L;
+    int off = 0;
+    auto take = [&](int bytes, int align) {
+        off = (off + align - 1) / align * align;
+        int at = off;
+        off += bytes;
+        return at;
+    };
+    L.raw = take(raw_bytes, 128);
+    L.coef = take(coef_words * 16, 16);
+    L.luma = take(rows * pitch_words * 4, 16);
+    L.acc = take(rows * kOuts * 4, 16);
+    L.hrow = take(rows * kOuts, 16);
+    L.x32 = take(1024, 16);
+    L.x98 = take(80, 16);
+    L.tmat = take(8 * 32 * 8, 16);
+    L.ymat = take(64 * 8, 16);
+    L.meta = take(2 * kOuts * 4, 16);
+    L.bar = take(8, 8);
+    L.total = off;
+    return L;
+}
+
+// ------------------------------------------------------------------ the kernel
+
+template <int C>
+__device__ __forceinline__ void luma_chunk(const uint8_t* __restrict__ raw, uint32_t* __restrict__ luma, int rows, int w,
+                                           int pitch_words, bool aligned) {
+    // Pillow rgb2l, split into low/high coefficient bytes for dp4a:
+    // 19595 = 0x4C8B, 38470 = 0x9646, 7471 = 0x1D2F.
+    constexpr uint32_t LO = 0x002F468Bu, HI = 0x001D964Cu;  // bytes (R,G,B,0) little endian
+    const int wq = w >> 2;  // full 4-pixel groups per row
+    if (C == 1) {
+        uint8_t* lb = reinterpret_cast<uint8_t*>(luma);
+        for (int idx = threadIdx.x; idx < rows * w; idx += kThreads) {
+            const int r = idx / w, x = idx - r * w;
+            lb[r * pitch_words * 4 + x] = raw[(size_t)r * w + x];
+        }
+        return;
+    }
+    if (aligned && C == 3) {
+        for (int idx = threadIdx.x; idx < rows * wq; idx += kThreads) {
+            const int r = idx / wq, q = idx - r * wq;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)r * w * 3) + q * 3;
+            const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+            // pixel byte positions inside the 12-byte group: p0=0..2, p1=3..5, p2=6..8, p3=9..11
+            uint32_t l0 = dp4a_uu(w0, LO, 0x8000u), h0 = dp4a_uu(w0, HI, 0u);
+            uint32_t l1 = dp4a_uu(w0, LO << 24, 0x8000u), h1 = dp4a_uu(w0, HI << 24, 0u);
+            l1 = dp4a_uu(w1, LO >> 8, l1), h1 = dp4a_uu(w1, HI >> 8, h1);
+            uint32_t l2 = dp4a_uu(w1, LO << 16, 0x8000u), h2 = dp4a_uu(w1, HI << 16, 0u);
+            l2 = dp4a_uu(w2, LO >> 16, l2), h2 = dp4a_uu(w2, HI >> 16, h2);
+            uint32_t l3 = dp4a_uu(w2, LO << 8, 0x8000u), h3 = dp4a_uu(w2, HI << 8, 0u);
+            const uint32_t s0 = l0 + (h0 << 8), s1 = l1 + (h1 << 8), s2 = l2 + (h2 << 8), s3 = l3 + (h3 << 8);
+            // L = byte 2 of each sum (sums < 2^24)
+            const uint32_t lo2 = __byte_perm(s0, s1, 0x0062), hi2 = __byte_perm(s2, s3, 0x0062);
+            luma[r * pitch_words + q] = __byte_perm(lo2, hi2, 0x5410);
+        }
+    } else if (aligned && C == 4) {
+        for (int idx = threadIdx.x; idx < rows * wq; idx += kThreads) {
+            const int r = idx / wq, q = idx - r * wq;
+            const uint4 px = *reinterpret_cast<const uint4*>(raw + (size_t)r * w * 4 + (size_t)q * 16);
+            const uint32_t s0 = dp4a_uu(px.x, LO, 0x8000u) + (dp4a_uu(px.x, HI, 0u) << 8);
+            const uint32_t s1 = dp4a_uu(px.y, LO, 0x8000u) + (dp4a_uu(px.y, HI, 0u) << 8);
+            const uint32_t s2 = dp4a_uu(px.z, LO, 0x8000u) + (dp4a_uu(px.z, HI, 0u) << 8);
+            const uint32_t s3 = dp4a_uu(px.w, LO, 0x8000u) + (dp4a_uu(px.w, HI, 0u) << 8);
+            const uint32_t lo2 = __byte_perm(s0, s1, 0x0062), hi2 = __byte_perm(s2, s3, 0x0062);
+            luma[r * pitch_words + q] = __byte_perm(lo2, hi2, 0x5410);
+        }
+    }
+    // generic bytes: everything when unaligned, else only the w % 4 tail pixels of each row
+    const int x_begin = aligned ? (wq << 2) : 0;
+    const int tail = w - x_begin;
+    if (tail > 0) {
+        uint8_t* lb = reinterpret_cast<uint8_t*>(luma);
+        for (int idx = threadIdx.x; idx < rows * tail; idx += kThreads) {
+            const int r = idx / tail, x = x_begin + (idx - r * tail);
+            const uint8_t* p = raw + ((size_t)r * w + x) * C;
+            lb[r * pitch_words * 4 + x] = (uint8_t)((p[0] * 19595u + p[1] * 38470u + p[2] * 7471u + 0x8000u) >> 16);
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) ke_phash_kernel(const PhashArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const SmemLayout L = smem_layout(a.coef_words, a.raw_bytes, a.rows_per_chunk, a.pitch_words);
+    uint8_t* s_raw = smem + L.raw;
+    uint4* s_coef = reinterpret_cast<uint4*>(smem + L.coef);
+    uint32_t* s_luma = reinterpret_cast<uint32_t*>(smem + L.luma);
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
+    uint8_t* s_hrow = smem + L.hrow;
+    uint8_t* s_x32 = smem + L.x32;
+    uint8_t* s_x98 = smem + L.x98;
+    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
+    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
+    int* s_meta = reinterpret_cast<int*>(smem + L.meta);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int RC = a.rows_per_chunk;
+    const int nparts = 32 / RC;
+    const int row_l = lane & (RC - 1), part = lane / RC;
+    const int n_chunks = (a.h + RC - 1) / RC;
+    const long long row_bytes = (long long)a.w * C;
+
+    for (int i = tid; i < a.coef_words; i += kThreads) s_coef[i] = a.coef[i];
+    for (int i = tid; i < 2 * kOuts; i += kThreads) s_meta[i] = a.meta[i];
+    for (int i = tid; i < RC * kOuts; i += kThreads) s_acc[i] = 1u << (kPrec - 1);
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    // Issue (or perform) the load of chunk `ck` of image `im`; returns the byte offset of the
+    // chunk's first row inside s_raw.
+    auto chunk_geometry = [&](long long im, int ck, long long& g_begin, int& bytes, int& lead) {
+        const long long start = im * a.img_stride + (long long)ck * RC * a.row_stride;
+        const int rows = min(RC, a.h - ck * RC);
+        const long long end = start + (long long)rows * row_bytes;
+        // 16-byte aligned superset relative to the (16-byte aligned) base pointer
+        const long long a0 = start & ~15ll;
+        long long a1 = (end + 15ll) & ~15ll;
+        if (a1 > a.total_bytes) a1 = a.total_bytes;  // never read past the caller's buffer
+        g_begin = a0;
+        bytes = (int)(a1 - a0);
+        lead = (int)(start - a0);
+    };
+    auto issue_load = [&](long long im, int ck) {
+        long long g0;
+        int bytes, lead;
+        chunk_geometry(im, ck, g0, bytes, lead);
+        if (a.use_bulk && (bytes & 15) == 0) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(s_bar, (uint32_t)bytes);
+                bulk_g2s(s_raw, a.img + g0, (uint32_t)bytes, s_bar);
+            }
+        } else {
+            // generic path (strided rows or an unaligned tail): plain loads, then arrive
+            const int rows = min(RC, a.h - ck * RC);
+            const long long start = im * a.img_stride + (long long)ck * RC * a.row_stride;
+            for (long long idx = tid; idx < rows * row_bytes; idx += kThreads) {
+                const long long r = idx / row_bytes, x = idx - r * row_bytes;
+                s_raw[lead + idx] = a.img[start + r * a.row_stride + x];
+            }
+            __syncthreads();
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(s_bar)) : "memory");
+        }
+        return lead;
+    };
+
+    long long im = blockIdx.x;
+    int lead = 0;
+    if (im < a.n) lead = issue_load(im, 0);
+
+    for (; im < a.n; im += gridDim.x) {
+        int32_t vacc[4], dacc = 1 << (kPrec - 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vacc[q] = 1 << (kPrec - 1);
+        const int vx = tid & 31, vg = tid >> 5;
+
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            const int r0 = ck * RC;
+            const int rows = min(RC, a.h - r0);
+            mbar_wait(s_bar, parity);
+            parity ^= 1u;
+            // vector fast path needs word (RGB) / 16-byte (RGBA) aligned rows in shared memory
+            const bool aligned = C == 3 ? (((lead & 3) == 0) && ((row_bytes & 3) == 0))
+                                        : (C == 4 ? (((lead & 15) == 0) && ((a.w & 3) == 0)) : false);
+            luma_chunk<C>(s_raw + lead, s_luma, rows, a.w, a.pitch_words, aligned);
+            __syncthreads();  // luma complete, s_raw free
+
+            // prefetch the next chunk (of this or the next image) behind the horizontal pass
+            {
+                long long nim = im;
+                int nck = ck + 1;
+                if (nck == n_chunks) {
+                    nim = im + gridDim.x;
+                    nck = 0;
+                }
+                if (nim < a.n) lead = issue_load(nim, nck);
+            }
+
+            // ---- horizontal taps: lane -> (row, part); items dealt round-robin to warps
+            for (int it = warp; it < a.n_items; it += kWarps) {
+                const int4 item = a.items[it];
+                const int o = item.x;
+                const uint4* cf = s_coef + s_meta[kOuts + o] + item.y;
+                const uint32_t* px = s_luma + row_l * a.pitch_words + s_meta[o] + item.y;
+                uint32_t d0 = 0, d1 = 0;
+                int32_t d2 = 0;
+#pragma unroll 4
+                for (int t = part; t < item.z; t += nparts) {
+                    const uint4 cw = cf[t];
+                    const uint32_t p = px[t];
+                    d0 = dp4a_uu(p, cw.x, d0);
+                    d1 = dp4a_uu(p, cw.y, d1);
+                    d2 = dp4a_us(p, cw.z, d2);
+                }
+                if (row_l < rows) atomicAdd(&s_acc[row_l * kOuts + o], d0 + (d1 << 8) + ((uint32_t)d2 << 16));
+            }
+            __syncthreads();
+
+            // ---- round, clip, reset accumulators
+            for (int i = tid; i < rows * kOuts; i += kThreads) {
+                s_hrow[i] = clip8((int32_t)s_acc[i]);
+                s_acc[i] = 1u << (kPrec - 1);
+            }
+            __syncthreads();
+
+            // ---- vertical taps, streamed: each thread owns outputs (yy = vg*4+q, x = vx)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int yy = vg * 4 + q;
+                const int ymin = __ldg(a.b32 + 2 * yy), ylen = __ldg(a.b32 + 2 * yy + 1);
+                const int lo = max(ymin, r0), hi = min(ymin + ylen, r0 + rows);
+                const int* kk = a.kk32 + yy * a.ks32 - ymin;
+                for (int y = lo; y < hi; ++y) vacc[q] += (int32_t)s_hrow[(y - r0) * kOuts + vx] * __ldg(kk + y);
+            }
+            if (tid < kDW * kDH) {
+                const int yy = tid / kDW, x = tid - yy * kDW;
+                const int ymin = __ldg(a.b8 + 2 * yy), ylen = __ldg(a.b8 + 2 * yy + 1);
+                const int lo = max(ymin, r0), hi = min(ymin + ylen, r0 + rows);
+                const int* kk = a.kk8 + yy * a.ks8 - ymin;
+                for (int y = lo; y < hi; ++y) dacc += (int32_t)s_hrow[(y - r0) * kOuts + kOutW + x] * __ldg(kk + y);
+            }
+            // s_hrow is rewritten only after the next chunk's two barriers
+        }
+
+        // ---- planes
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_x32[(vg * 4 + q) * 32 + vx] = clip8(vacc[q]);
+        if (tid < kDW * kDH) s_x98[tid] = clip8(dacc);
+        __syncthreads();
+        if (a.plane32)
+            for (int i = tid; i < 1024; i += kThreads) a.plane32[im * 1024 + i] = s_x32[i];
+        if (a.plane98 && tid < kDW * kDH) a.plane98[im * 72 + tid] = s_x98[tid];
+
+        // ---- DCT low block: T = C(8x32) * X(32x32);  Y = T * C^T (8x8)
+        {
+            const int k = tid >> 5, x = tid & 31;
+            double s = 0.0;
+#pragma unroll 8
+            for (int nn = 0; nn < 32; ++nn) s = fma(c_dct[k * 32 + nn], (double)s_x32[nn * 32 + x], s);
+            s_t[k * 32 + x] = s;
+        }
+        __syncthreads();
+        if (tid < 64) {
+            const int k = tid >> 3, l = tid & 7;
+            double s = 0.0;
+#pragma unroll 8
+            for (int nn = 0; nn < 32; ++nn) s = fma(s_t[k * 32 + nn], c_dct[l * 32 + nn], s);
+            s_y[tid] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const double y0 = s_y[lane], y1 = s_y[lane + 32];
+            double sum = (lane == 0 ? 0.0 : y0) + y1;  // DC is compared but not averaged
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            const double mean = sum / 63.0;
+            const uint32_t bhi = __ballot_sync(0xffffffffu, y0 > mean), blo = __ballot_sync(0xffffffffu, y1 > mean);
+            double mg = fmin(fabs(y0 - mean), fabs(y1 - mean));
+#pragma unroll
+            for (int off = 16; off; off >>= 1) mg = fmin(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+            // dHash: bit (r*8+c) = plane[r][c+1] > plane[r][c], first = MSB
+            const int r_a = lane >> 3, c_a = lane & 7;
+            const uint32_t dhi = __ballot_sync(0xffffffffu, s_x98[r_a * 9 + c_a + 1] > s_x98[r_a * 9 + c_a]);
+            const uint32_t dlo =
+                __ballot_sync(0xffffffffu, s_x98[(r_a + 4) * 9 + c_a + 1] > s_x98[(r_a + 4) * 9 + c_a]);
+            if (lane == 0) {
+                a.phash[im] = ((uint64_t)__brev(bhi) << 32) | (uint64_t)__brev(blo);
+                a.dhash[im] = ((uint64_t)__brev(dhi) << 32) | (uint64_t)__brev(dlo);
+                if (a.min_margin) a.min_margin[im] = (float)mg;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int g_dct_uploaded_device = -1;
+
+int ensure_dct(ke_ctx* ctx) {
+    if (g_dct_uploaded_device == ctx->device) return KE_OK;
+    double c[8 * 32];
+    for (int k = 0; k < 8; ++k)
+        for (int n = 0; n < 32; ++n)
+            c[k * 32 + n] = (k == 0 ? std::sqrt(1.0 / 32.0) : std::sqrt(2.0 / 32.0)) * std::cos(M_PI * (2 * n + 1) * k / 64.0);
+    KE_CUDA(cudaMemcpyToSymbol(c_dct, c, sizeof(c)));
+    g_dct_uploaded_device = ctx->device;
+    return KE_OK;
+}
+
+template <int C>
+int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
+    // rows per chunk: as many (power of two, <= 32) as keep the CTA's shared memory <= ~110 KB
+    // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
+    const long long row_bytes = (long long)a.w * C;
+    a.pitch_words = ((a.w + 3) / 4) | 1;
+    int rc_rows = 32;
+    SmemLayout L;
+    for (;;) {
+        a.rows_per_chunk = rc_rows;
+        a.raw_bytes = (int)(((long long)rc_rows * row_bytes + 15 + 16 + 15) / 16 * 16);
+        L = smem_layout(a.coef_words, a.raw_bytes, rc_rows, a.pitch_words);
+        const int budget = rc_rows > 1 ? 112 * 1024 : 227 * 1024;
+        if (L.total <= budget || rc_rows == 1) break;
+        rc_rows >>= 1;
+    }
+    if (L.total > 227 * 1024) {
+        // retry preferring one CTA per SM with more rows
+        ke_set_error("ke_phash_batch: image rows of %lld bytes do not fit shared memory", row_bytes);
+        return KE_E_UNSUPPORTED;
+    }
+    KE_CUDA(cudaFuncSetAttribute(ke_phash_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_kernel<C>, kThreads, L.total));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.n) grid = a.n;
+    ke_phash_kernel<C><<<(unsigned)grid, kThreads, L.total, s>>>(a);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
+}  // namespace
+
+extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int w, int c, int64_t img_stride,
+                              int64_t row_stride, uint64_t* d_phash, uint64_t* d_dhash, float* d_min_margin,
+                              uint8_t* d_plane32, uint8_t* d_plane9x8, void* stream) {
+    KE_REQUIRE(ctx != nullptr, "ke_phash_batch: ctx is NULL");
+    KE_REQUIRE(n >= 0, "ke_phash_batch: n < 0");
+    if (n == 0) return KE_OK;
+    KE_REQUIRE(d_img && d_phash && d_dhash, "ke_phash_batch: NULL buffer");
+    KE_REQUIRE(h > 0 && w > 0, "ke_phash_batch: empty image %dx%d", w, h);
+    KE_REQUIRE(c == 1 || c == 3 || c == 4, "ke_phash_batch: channels must be 1, 3 or 4 (got %d)", c);
+    KE_REQUIRE(row_stride >= (int64_t)w * c && img_stride >= (int64_t)(h - 1) * row_stride + (int64_t)w * c,
+               "ke_phash_batch: strides smaller than the image");
+    KeDeviceGuard guard(ctx->device);
+    int rc;
+    if ((rc = ensure_dct(ctx))) return rc;
+    const HTable* ht;
+    const VTable* vt;
+    if ((rc = get_htable(ctx, w, &ht))) return rc;
+    if ((rc = get_vtable(ctx, h, &vt))) return rc;
+    PhashArgs a;
+    a.img = d_img;
+    a.n = n;
+    a.h = h;
+    a.w = w;
+    a.c = c;
+    a.img_stride = img_stride;
+    a.row_stride = row_stride;
+    a.total_bytes = (n - 1) * img_stride + (int64_t)(h - 1) * row_stride + (int64_t)w * c;
+    a.use_bulk = (row_stride == (int64_t)w * c) && ((reinterpret_cast<uintptr_t>(d_img) & 15) == 0);
+    a.coef = ht->d_coef;
+    a.items = ht->d_items;
+    a.meta = ht->d_meta;
+    a.n_items = ht->n_items;
+    a.coef_words = ht->coef_words;
+    a.kk32 = vt->d_kk32;
+    a.b32 = vt->d_b32;
+    a.kk8 = vt->d_kk8;
+    a.b8 = vt->d_b8;
+    a.ks32 = vt->ks32;
+    a.ks8 = vt->ks8;
+    a.phash = d_phash;
+    a.dhash = d_dhash;
+    a.min_margin = d_min_margin;
+    a.plane32 = d_plane32;
+    a.plane98 = d_plane9x8;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (c) {
+        case 1: return launch_phash<1>(ctx, a, s);
+        case 3: return launch_phash<3>(ctx, a, s);
+        default: return launch_phash<4>(ctx, a, s);
+    }
+}
+
+extern "C" int ke_phash_batch_host(ke_ctx* ctx, const uint8_t* h_img, int64_t n, int h, int w, int c,
+                                   uint64_t* h_phash, uint64_t* h_dhash, float* h_min_margin) {
+    KE_REQUIRE(ctx != nullptr, "ke_phash_batch_host: ctx is NULL");
+    KE_REQUIRE(n >= 0, "ke_phash_batch_host: n < 0");
+    if (n == 0) return KE_OK;
+    KE_REQUIRE(h_img && h_phash && h_dhash, "ke_phash_batch_host: NULL buffer");
+    KE_REQUIRE(h > 0 && w > 0 && (c == 1 || c == 3 || c == 4), "ke_phash_batch_host: bad geometry %dx%dx%d", w, h, c);
+    KeDeviceGuard guard(ctx->device);
+    const int64_t img_bytes = (int64_t)h * w * c;
+    const int64_t img_stride = (img_bytes + 15) / 16 * 16;  // keep every image 16-byte aligned on the device
+    int64_t per_chunk = (256ll << 20) / img_stride;
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > n) per_chunk = n;
+    void *d_buf[2], *d_ph = nullptr, *d_dh = nullptr, *d_mm = nullptr;
+    int rc;
+    for (int b = 0; b < 2; ++b)
+        if ((rc = ke_ctx_scratch(ctx, b, (size_t)(per_chunk * img_stride) + 64, &d_buf[b]))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 2, (size_t)n * 8, &d_ph))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 3, (size_t)n * 8, &d_dh))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 4, (size_t)n * 4, &d_mm))) return rc;
+    int k = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += per_chunk, ++k) {
+        const int b = k & 1;
+        const int64_t cnt = std::min<int64_t>(per_chunk, n - i0);
+        cudaStream_t s = ctx->copy_stream[b];
+        if (img_stride == img_bytes) {
+            KE_CUDA(cudaMemcpyAsync(d_buf[b], h_img + i0 * img_bytes, (size_t)(cnt * img_bytes), cudaMemcpyHostToDevice, s));
+        } else {
+            KE_CUDA(cudaMemcpy2DAsync(d_buf[b], (size_t)img_stride, h_img + i0 * img_bytes, (size_t)img_bytes,
+                                      (size_t)img_bytes, (size_t)cnt, cudaMemcpyHostToDevice, s));
+        }
+        rc = ke_phash_batch(ctx, (const uint8_t*)d_buf[b], cnt, h, w, c, img_stride, (int64_t)w * c,
+                            (uint64_t*)d_ph + i0, (uint64_t*)d_dh + i0, (float*)d_mm + i0, nullptr, nullptr, s);
+        if (rc) return rc;
+    }
+    for (auto s : ctx->copy_stream) KE_CUDA(cudaStreamSynchronize(s));
+    KE_CUDA(cudaMemcpy(h_phash, d_ph, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    KE_CUDA(cudaMemcpy(h_dhash, d_dh, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (h_min_margin) KE_CUDA(cudaMemcpy(h_min_margin, d_mm, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return KE_OK;
+}

@@ -1,0 +1,344 @@
+// ke_ssim.cu — K3: batched SSIM on candidate pairs, sm_100a.
+//
+// Replaces skimage.metrics.structural_similarity(a, b, data_range=1.0) as called by
+// dup.refine._compute_ssim (reference src/dup/refine.py:44-52): 7x7 UNIFORM window, sample
+// covariance (x49/48), K1=.01, K2=.03, 3-pixel border cropped, mean of the SSIM map.
+//
+// Arithmetic: the five window sums (u, v, u^2, v^2, uv over 49 pixels) are EXACT integers
+// (they fit int32), the variance/covariance numerators 49*Suu - Su^2 ... are exact integers too,
+// so there is no cancellation error; only the final ratio is FP32 and the mean FP64.
+// With N=49 and pixel scale 255 everything is kept multiplied by 49^2*255^2 (means) or
+// 48*49*255^2 (covariances):
+//     S = (2*Su*Sv + c1) (2*(49*Suv - Su*Sv) + c2) / ((Su^2 + Sv^2 + c1) (49*(Suu+Svv) - Su^2 - Sv^2 + c2))
+//     c1 = 1e-4 * 49^2 * 255^2,  c2 = 9e-4 * 48*49 * 255^2.
+//
+// Schedule: a work unit is (pair, block of 256 output columns).  Thread = output column.
+// Rows stream through shared memory in strips (one 1-D TMA bulk copy per image per strip when
+// the plane is contiguous, double buffered).  Per row a thread forms the horizontal 7-sums of its
+// window straight from the packed bytes with dp4a (4+3 bytes, no sliding dependency), then keeps
+// the vertical 7-row running sums in registers with a 7-deep register ring: no inter-thread
+// exchange at all.
+//
+// Algorithmic HBM bytes per pair: 2*h*w*c read + 8 written.
+#include "ke_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kStripRows = 28;        // multiple of 7 (ring unroll)
+constexpr int kBlockCols = kThreads;  // output columns per unit
+constexpr int kWin = 7;
+
+struct SsimArgs {
+    const uint8_t* bank;
+    int h, w, c;
+    long long img_stride, row_stride;
+    const long long* ia;
+    const long long* ib;
+    long long n_pairs;
+    int n_cblocks;
+    int pitch;     // shared-memory row pitch in bytes (multiple of 4)
+    int use_bulk;  // contiguous 'L' planes, one column block: bulk copies straight into the strip
+    double inv_count;
+    double* out;
+};
+
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct HSum {
+    uint32_t s;  // Su | Sv << 16 (each <= 7*255)
+    uint32_t uu, vv, uv;
+};
+
+// Horizontal 7-sums of the window starting at byte `k` (0..3) of word w0.
+__device__ __forceinline__ HSum hsum7(const uint32_t* __restrict__ ru, const uint32_t* __restrict__ rv, uint32_t sel) {
+    const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2];
+    const uint32_t v0 = rv[0], v1 = rv[1], v2 = rv[2];
+    const uint32_t ua = __byte_perm(u0, u1, sel), ub = __byte_perm(u1, u2, sel);
+    const uint32_t va = __byte_perm(v0, v1, sel), vb = __byte_perm(v1, v2, sel);
+    const uint32_t ubm = ub & 0x00FFFFFFu, vbm = vb & 0x00FFFFFFu;
+    HSum r;
+    const uint32_t su = dp4a_uu(ua, 0x01010101u, dp4a_uu(ub, 0x00010101u, 0u));
+    const uint32_t sv = dp4a_uu(va, 0x01010101u, dp4a_uu(vb, 0x00010101u, 0u));
+    r.s = su + (sv << 16);
+    r.uu = dp4a_uu(ua, ua, dp4a_uu(ub, ubm, 0u));
+    r.vv = dp4a_uu(va, va, dp4a_uu(vb, vbm, 0u));
+    r.uv = dp4a_uu(ua, va, dp4a_uu(ub, vbm, 0u));
+    return r;
+}
+
+__device__ __forceinline__ float ssim_point(uint32_t s, uint32_t suu, uint32_t svv, uint32_t suv) {
+    constexpr float C1 = 1e-4f * 49.0f * 49.0f * 255.0f * 255.0f;
+    constexpr float C2 = 9e-4f * 48.0f * 49.0f * 255.0f * 255.0f;
+    const int a = (int)(s & 0xFFFFu), b = (int)(s >> 16);
+    const int p = a * b;
+    const int q = a * a + b * b;
+    const int vxy = 49 * (int)suv - p;
+    const int vs = 49 * (int)(suu + svv) - q;
+    const float num = fmaf(2.0f, (float)p, C1) * fmaf(2.0f, (float)vxy, C2);
+    const float den = ((float)q + C1) * ((float)vs + C2);
+    return __fdividef(num, den);
+}
+
+template <int C>
+__device__ __forceinline__ uint8_t luma_of(const uint8_t* p) {
+    if (C == 1) return p[0];
+    return (uint8_t)((p[0] * 19595u + p[1] * 38470u + p[2] * 7471u + 0x8000u) >> 16);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [buf 0: u strip | v strip][buf 1: u strip | v strip][2 mbarriers]
+    const int strip_bytes = (kStripRows * a.pitch + 16 + 127) / 128 * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * strip_bytes);
+    __shared__ double s_red[kThreads / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity[2] = {0u, 0u};
+    const int n_strips = (a.h + kStripRows - 1) / kStripRows;
+    const long long n_units = a.n_pairs * a.n_cblocks;
+
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long pair = unit / a.n_cblocks;
+        const int cb = (int)(unit - pair * a.n_cblocks);
+        const int col0 = cb * kBlockCols;                       // first output column of this unit
+        const int out_cols = min(kBlockCols, (a.w - 6) - col0);  // valid output columns
+        const int in_cols = out_cols + 6;
+        const uint8_t* img_u = a.bank + a.ia[pair] * a.img_stride;
+        const uint8_t* img_v = a.bank + a.ib[pair] * a.img_stride;
+
+        auto load_strip = [&](int s) {
+            const int buf = s & 1;
+            const int r0 = s * kStripRows;
+            const int rows = min(kStripRows, a.h - r0);
+            uint8_t* du = smem + (2 * buf) * strip_bytes;
+            uint8_t* dv = smem + (2 * buf + 1) * strip_bytes;
+            if (a.use_bulk) {
+                if (tid == 0) {
+                    const uint32_t bytes = (uint32_t)(rows * a.w);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&bars[buf], 2u * bytes);
+                    bulk_g2s(du, img_u + (long long)r0 * a.row_stride, bytes, &bars[buf]);
+                    bulk_g2s(dv, img_v + (long long)r0 * a.row_stride, bytes, &bars[buf]);
+                }
+            } else {
+                for (int idx = tid; idx < rows * in_cols; idx += kThreads) {
+                    const int r = idx / in_cols, x = idx - r * in_cols;
+                    const long long g = (long long)(r0 + r) * a.row_stride + (long long)(col0 + x) * C;
+                    du[r * a.pitch + x] = luma_of<C>(img_u + g);
+                    dv[r * a.pitch + x] = luma_of<C>(img_v + g);
+                }
+                __syncthreads();
+                if (tid == 0) mbar_arrive(&bars[buf]);
+            }
+        };
+
+        HSum ring[kWin];
+#pragma unroll
+        for (int i = 0; i < kWin; ++i) ring[i] = HSum{0u, 0u, 0u, 0u};
+        uint32_t acc_s = 0, acc_uu = 0, acc_vv = 0, acc_uv = 0;
+        double total = 0.0;
+        const bool active = tid < out_cols;
+        const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(tid & 3);
+        const int word = tid >> 2;
+
+        __syncthreads();  // every thread is done with the previous unit's buffers
+        load_strip(0);
+        for (int s = 0; s < n_strips; ++s) {
+            const int buf = s & 1;
+            if (s + 1 < n_strips) load_strip(s + 1);  // buffer (s+1)&1 was released by the barrier below
+            mbar_wait(&bars[buf], parity[buf]);
+            parity[buf] ^= 1u;
+            const int r0 = s * kStripRows;
+            const int rows = min(kStripRows, a.h - r0);
+            const uint32_t* su = reinterpret_cast<const uint32_t*>(smem + (2 * buf) * strip_bytes) + word;
+            const uint32_t* sv = reinterpret_cast<const uint32_t*>(smem + (2 * buf + 1) * strip_bytes) + word;
+            const int pw = a.pitch >> 2;
+            float part = 0.f;
+            if (active) {
+                for (int rb = 0; rb < rows; rb += kWin) {
+#pragma unroll
+                    for (int k = 0; k < kWin; ++k) {
+                        const int r = rb + k;  // (r0 + r) % 7 == k because strips are multiples of 7
+                        if (r < rows) {
+                            const HSum hs = hsum7(su + r * pw, sv + r * pw, sel);
+                            acc_s += hs.s;
+                            acc_uu += hs.uu;
+                            acc_vv += hs.vv;
+                            acc_uv += hs.uv;
+                            if (r0 + r >= kWin - 1) part += ssim_point(acc_s, acc_uu, acc_vv, acc_uv);
+                            // slot (k+1)%7 holds row (r0+r-6): it leaves the window
+                            const HSum old = ring[(k + 1) % kWin];
+                            acc_s -= old.s;
+                            acc_uu -= old.uu;
+                            acc_vv -= old.vv;
+                            acc_uv -= old.uv;
+                            ring[k] = hs;
+                        }
+                    }
+                }
+            }
+            total += (double)part;
+            __syncthreads();  // strip buffer `buf` may be refilled
+        }
+
+        // block reduction of the per-column sums
+#pragma unroll
+        for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+        if (lane == 0) s_red[warp] = total;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kThreads / 32; ++i) t += s_red[i];
+            if (a.n_cblocks == 1) a.out[pair] = t * a.inv_count;
+            else atomicAdd(&a.out[pair], t * a.inv_count);
+        }
+    }
+}
+
+template <int C>
+int launch_ssim(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
+    const int strip_bytes = (kStripRows * a.pitch + 16 + 127) / 128 * 128;
+    const int smem = 4 * strip_bytes + 16;
+    KE_CUDA(cudaFuncSetAttribute(ke_ssim_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_ssim_kernel<C>, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long units = a.n_pairs * a.n_cblocks;
+    if (grid > units) grid = units;
+    ke_ssim_kernel<C><<<(unsigned)grid, kThreads, smem, s>>>(a);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
+}  // namespace
+
+extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride,
+                             int64_t row_stride, const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs,
+                             double* d_ssim, void* stream) {
+    KE_REQUIRE(ctx != nullptr, "ke_ssim_batch: ctx is NULL");
+    KE_REQUIRE(n_pairs >= 0, "ke_ssim_batch: n_pairs < 0");
+    if (n_pairs == 0) return KE_OK;
+    KE_REQUIRE(d_bank && d_ia && d_ib && d_ssim, "ke_ssim_batch: NULL buffer");
+    KE_REQUIRE(c == 1 || c == 3 || c == 4, "ke_ssim_batch: channels must be 1, 3 or 4 (got %d)", c);
+    if (h < kWin || w < kWin) {
+        ke_set_error("win_size exceeds image extent (%dx%d < 7)", w, h);
+        return KE_E_UNSUPPORTED;
+    }
+    KE_REQUIRE(row_stride >= (int64_t)w * c && img_stride >= (int64_t)(h - 1) * row_stride + (int64_t)w * c,
+               "ke_ssim_batch: strides smaller than the image");
+    KeDeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    SsimArgs a;
+    a.bank = d_bank;
+    a.h = h;
+    a.w = w;
+    a.c = c;
+    a.img_stride = img_stride;
+    a.row_stride = row_stride;
+    a.ia = (const long long*)d_ia;
+    a.ib = (const long long*)d_ib;
+    a.n_pairs = n_pairs;
+    a.n_cblocks = ((w - 6) + kBlockCols - 1) / kBlockCols;
+    a.use_bulk = (c == 1 && a.n_cblocks == 1 && (w % 16) == 0 && row_stride == w && (img_stride % 16) == 0 &&
+                  (reinterpret_cast<uintptr_t>(d_bank) & 15) == 0);
+    a.pitch = a.use_bulk ? w : ((std::min(w, kBlockCols + 6) + 3) / 4 * 4 + 4);
+    a.inv_count = 1.0 / ((double)(h - 6) * (double)(w - 6));
+    a.out = d_ssim;
+    if (a.n_cblocks > 1) KE_CUDA(cudaMemsetAsync(d_ssim, 0, (size_t)n_pairs * sizeof(double), s));
+    switch (c) {
+        case 1: return launch_ssim<1>(ctx, a, s);
+        case 3: return launch_ssim<3>(ctx, a, s);
+        default: return launch_ssim<4>(ctx, a, s);
+    }
+}
+
+extern "C" int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w,
+                                  double* h_ssim) {
+    KE_REQUIRE(ctx != nullptr, "ke_ssim_pairs_host: ctx is NULL");
+    KE_REQUIRE(n_pairs >= 0, "ke_ssim_pairs_host: n_pairs < 0");
+    if (n_pairs == 0) return KE_OK;
+    KE_REQUIRE(h_a && h_b && h_ssim, "ke_ssim_pairs_host: NULL buffer");
+    if (h < kWin || w < kWin) {
+        ke_set_error("win_size exceeds image extent (%dx%d < 7)", w, h);
+        return KE_E_UNSUPPORTED;
+    }
+    KeDeviceGuard guard(ctx->device);
+    const int64_t plane = (int64_t)h * w;
+    const int64_t stride = (plane + 15) / 16 * 16;
+    int64_t per_chunk = (128ll << 20) / (2 * stride);
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > n_pairs) per_chunk = n_pairs;
+    // device bank per chunk: [a planes | b planes], pair p -> (p, per_chunk + p)
+    void *d_bank[2], *d_idx = nullptr, *d_out = nullptr;
+    int rc;
+    for (int b = 0; b < 2; ++b)
+        if ((rc = ke_ctx_scratch(ctx, b, (size_t)(2 * per_chunk * stride) + 64, &d_bank[b]))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 2, (size_t)per_chunk * 16, &d_idx))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 3, (size_t)n_pairs * 8, &d_out))) return rc;
+    std::vector<long long> idx((size_t)per_chunk * 2);
+    for (int64_t p = 0; p < per_chunk; ++p) {
+        idx[(size_t)p] = p;
+        idx[(size_t)(per_chunk + p)] = per_chunk + p;
+    }
+    KE_CUDA(cudaMemcpy(d_idx, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice));
+    int k = 0;
+    for (int64_t p0 = 0; p0 < n_pairs; p0 += per_chunk, ++k) {
+        const int b = k & 1;
+        const int64_t cnt = std::min<int64_t>(per_chunk, n_pairs - p0);
+        cudaStream_t s = ctx->copy_stream[b];
+        uint8_t* da = (uint8_t*)d_bank[b];
+        uint8_t* db = da + per_chunk * stride;
+        KE_CUDA(cudaMemcpy2DAsync(da, (size_t)stride, h_a + p0 * plane, (size_t)plane, (size_t)plane, (size_t)cnt,
+                                  cudaMemcpyHostToDevice, s));
+        KE_CUDA(cudaMemcpy2DAsync(db, (size_t)stride, h_b + p0 * plane, (size_t)plane, (size_t)plane, (size_t)cnt,
+                                  cudaMemcpyHostToDevice, s));
+        rc = ke_ssim_batch(ctx, da, h, w, 1, stride, w, (const int64_t*)d_idx, (const int64_t*)d_idx + per_chunk, cnt,
+                           (double*)d_out + p0, s);
+        if (rc) return rc;
+    }
+    for (auto s : ctx->copy_stream) KE_CUDA(cudaStreamSynchronize(s));
+    KE_CUDA(cudaMemcpy(h_ssim, d_out, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost));
+    return KE_OK;
+}

@@ -1,0 +1,255 @@
+"""Array-level entry points over the C ABI (include/kobato_b200.h).
+
+Inputs may be CUDA ``torch`` tensors (zero-copy: only ``data_ptr()`` and the current stream are
+handed to the library) or host ``numpy`` arrays (the library's ``*_host`` entry points move the
+data through pinned staging).  No path computes on the CPU; if the CUDA library or device is
+missing these functions raise ``KobatoNativeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+U64 = (1 << 64) - 1
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _is_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr(device_index: int) -> int:
+    torch = _torch()
+    return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def _np_ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+# ----------------------------------------------------------------------------- K1
+
+
+def phash_dhash_batch(images, *, want_margin: bool = False, want_planes: bool = False):
+    """pHash and dHash of a batch of decoded images (reference src/sig/phash.py:33-57).
+
+    images: uint8 ``[n,h,w]`` ('L') or ``[n,h,w,c]`` with c in {1,3,4}; CUDA tensor or numpy array.
+    Returns ``(phash, dhash)`` as **signed** int64 (the reference's ``_to_signed`` wrap, ready for
+    SQLite), plus ``margin`` (float32, min |coef-mean|) and ``(plane32, plane9x8)`` on request.
+    CUDA tensors in -> CUDA tensors out; numpy in -> numpy out.
+    """
+    lib = nat.load()
+    if _is_tensor(images):
+        torch = _torch()
+        if not images.is_cuda or images.dtype != torch.uint8:
+            raise ValueError("phash_dhash_batch wants a CUDA uint8 tensor (or a numpy array)")
+        x = images if images.dim() == 4 else images.unsqueeze(-1)
+        if x.dim() != 4:
+            raise ValueError("images must be [n,h,w] or [n,h,w,c]")
+        n, h, w, c = x.shape
+        if x.stride(3) != 1 or x.stride(2) != c:
+            x = x.contiguous()
+        dev = x.device.index
+        ctx = nat.context(dev)
+        ph = torch.empty(n, dtype=torch.int64, device=x.device)
+        dh = torch.empty(n, dtype=torch.int64, device=x.device)
+        mg = torch.empty(n, dtype=torch.float32, device=x.device) if want_margin else None
+        p32 = torch.empty((n, 32, 32), dtype=torch.uint8, device=x.device) if want_planes else None
+        p98 = torch.empty((n, 8, 9), dtype=torch.uint8, device=x.device) if want_planes else None
+        if n:
+            with ctx.lock:
+                nat.check(lib.ke_phash_batch(ctx.handle, x.data_ptr(), n, h, w, c, x.stride(0), x.stride(1),
+                                             ph.data_ptr(), dh.data_ptr(), mg.data_ptr() if want_margin else None,
+                                             p32.data_ptr() if want_planes else None,
+                                             p98.data_ptr() if want_planes else None, _stream_ptr(dev)),
+                          "ke_phash_batch")
+        out = [ph, dh]
+    else:
+        x = np.ascontiguousarray(images, dtype=np.uint8)
+        if x.ndim == 3:
+            x = x[..., None]
+        if x.ndim != 4:
+            raise ValueError("images must be [n,h,w] or [n,h,w,c]")
+        n, h, w, c = x.shape
+        if want_planes:
+            raise ValueError("planes are only returned for device tensors")
+        ctx = nat.context()
+        ph = np.empty(n, np.int64)
+        dh = np.empty(n, np.int64)
+        mg = np.empty(n, np.float32) if want_margin else None
+        if n:
+            with ctx.lock:
+                nat.check(lib.ke_phash_batch_host(ctx.handle, _np_ptr(x), n, h, w, c, _np_ptr(ph), _np_ptr(dh),
+                                                  _np_ptr(mg) if want_margin else None), "ke_phash_batch_host")
+        out = [ph, dh]
+        p32 = p98 = None
+    if want_margin:
+        out.append(mg)
+    if want_planes:
+        out.append((p32, p98))
+    return tuple(out)
+
+
+# ----------------------------------------------------------------------------- K2
+
+
+def hamming_join(hashes, threshold: int, *, require_band: bool = False, band_bits: int = 16, band_count: int = 4,
+                 band_allow=None, part_index: int = 0, part_count: int = 1, capacity: int | None = None):
+    """All pairs i<j with popcount(h[i]^h[j]) <= threshold (reference src/dup/scanner.py:262-290).
+
+    hashes: int64/uint64 table, CUDA tensor or numpy array.  Returns ``(i, j, dist)`` numpy arrays
+    (uint32, uint32, uint8) sorted by (i, j).  The output buffer grows and the join re-runs when
+    more pairs qualify than ``capacity`` (nothing is truncated)."""
+    lib = nat.load()
+    flags = nat.KE_JOIN_REQUIRE_BAND if require_band else 0
+    if _is_tensor(hashes):
+        torch = _torch()
+        if not hashes.is_cuda or hashes.dtype not in (torch.int64, torch.uint64):
+            raise ValueError("hamming_join wants a CUDA int64/uint64 tensor (or a numpy array)")
+        h = hashes.contiguous().view(-1)
+        n = h.numel()
+        dev = h.device.index
+        ctx = nat.context(dev)
+        allow = None
+        if band_allow is not None:
+            allow = band_allow.contiguous() if _is_tensor(band_allow) else \
+                torch.from_numpy(np.ascontiguousarray(band_allow, np.uint64).view(np.int64)).to(h.device)
+        cap = int(capacity) if capacity is not None else max(1 << 16, 4 * n)
+        while True:
+            oi = torch.empty(cap, dtype=torch.int32, device=h.device)
+            oj = torch.empty(cap, dtype=torch.int32, device=h.device)
+            od = torch.empty(cap, dtype=torch.uint8, device=h.device)
+            cnt = torch.zeros(1, dtype=torch.int64, device=h.device)
+            with ctx.lock:
+                nat.check(lib.ke_hamming_join(ctx.handle, h.data_ptr(), n, int(threshold), flags, band_bits, band_count,
+                                              allow.data_ptr() if allow is not None else None, part_index, part_count,
+                                              oi.data_ptr(), oj.data_ptr(), od.data_ptr(), cap, cnt.data_ptr(),
+                                              _stream_ptr(dev)), "ke_hamming_join")
+            total = int(cnt.item())
+            if total <= cap:
+                break
+            cap = total
+        ii = oi[:total].cpu().numpy().view(np.uint32)
+        jj = oj[:total].cpu().numpy().view(np.uint32)
+        dd = od[:total].cpu().numpy()
+    else:
+        h = np.ascontiguousarray(hashes).reshape(-1)
+        if h.dtype not in (np.int64, np.uint64):
+            raise ValueError("hashes must be int64 or uint64")
+        n = h.shape[0]
+        ctx = nat.context()
+        allow = np.ascontiguousarray(band_allow, np.uint64) if band_allow is not None else None
+        cap = int(capacity) if capacity is not None else max(1 << 16, 4 * n)
+        while True:
+            ii = np.empty(cap, np.uint32)
+            jj = np.empty(cap, np.uint32)
+            dd = np.empty(cap, np.uint8)
+            total = C.c_int64(0)
+            with ctx.lock:
+                st = lib.ke_hamming_join_host(ctx.handle, _np_ptr(h), n, int(threshold), flags, band_bits, band_count,
+                                              _np_ptr(allow) if allow is not None else None, part_index, part_count,
+                                              _np_ptr(ii), _np_ptr(jj), _np_ptr(dd), cap, C.byref(total))
+            if st == nat.KE_E_CAPACITY:
+                cap = int(total.value)
+                continue
+            nat.check(st, "ke_hamming_join_host")
+            break
+        ii, jj, dd = ii[: total.value], jj[: total.value], dd[: total.value]
+    order = np.lexsort((jj, ii))
+    return ii[order], jj[order], dd[order]
+
+
+# ----------------------------------------------------------------------------- K3
+
+
+def ssim_batch(bank, ia, ib):
+    """SSIM of pairs (bank[ia[p]], bank[ib[p]]) — reference src/dup/refine.py:52 semantics.
+
+    bank: CUDA uint8 tensor ``[m,h,w]`` ('L' planes) or ``[m,h,w,c]`` (RGB/RGBA, Pillow luma applied
+    on the fly); ia/ib: index sequences.  Returns a float64 CUDA tensor ``[n_pairs]``."""
+    torch = _torch()
+    lib = nat.load()
+    if not (_is_tensor(bank) and bank.is_cuda and bank.dtype == torch.uint8):
+        raise ValueError("ssim_batch wants a CUDA uint8 bank tensor")
+    x = bank if bank.dim() == 4 else bank.unsqueeze(-1)
+    m, h, w, c = x.shape
+    if x.stride(3) != 1 or x.stride(2) != c:
+        x = x.contiguous()
+    dev = x.device.index
+    ia_t = torch.as_tensor(ia, dtype=torch.int64).to(x.device).contiguous()
+    ib_t = torch.as_tensor(ib, dtype=torch.int64).to(x.device).contiguous()
+    if ia_t.shape != ib_t.shape or ia_t.dim() != 1:
+        raise ValueError("ia and ib must be 1-D and of equal length")
+    n = ia_t.numel()
+    if n and (int(torch.max(torch.maximum(ia_t, ib_t))) >= m or int(torch.min(torch.minimum(ia_t, ib_t))) < 0):
+        raise ValueError("pair index out of range")
+    out = torch.empty(n, dtype=torch.float64, device=x.device)
+    if n:
+        ctx = nat.context(dev)
+        with ctx.lock:
+            st = lib.ke_ssim_batch(ctx.handle, x.data_ptr(), h, w, c, x.stride(0), x.stride(1), ia_t.data_ptr(),
+                                   ib_t.data_ptr(), n, out.data_ptr(), _stream_ptr(dev))
+        if st == nat.KE_E_UNSUPPORTED:
+            raise ValueError(nat.last_error())  # the reference (skimage) raises ValueError here
+        nat.check(st, "ke_ssim_batch")
+    return out
+
+
+def ssim_pairs(a, b) -> np.ndarray:
+    """SSIM of host 'L' planes: a, b uint8 ``[n,h,w]`` (or ``[h,w]``) -> float64 ``[n]``."""
+    lib = nat.load()
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    if a.shape != b.shape:
+        raise ValueError("Input images must have the same dimensions.")
+    if a.ndim == 2:
+        a, b = a[None], b[None]
+    n, h, w = a.shape
+    out = np.empty(n, np.float64)
+    if n:
+        ctx = nat.context()
+        with ctx.lock:
+            st = lib.ke_ssim_pairs_host(ctx.handle, _np_ptr(a), _np_ptr(b), n, h, w, _np_ptr(out))
+        if st == nat.KE_E_UNSUPPORTED:
+            raise ValueError(nat.last_error())
+        nat.check(st, "ke_ssim_pairs_host")
+    return out
+
+
+# ----------------------------------------------------------------------------- helpers
+
+
+def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n_set: int = 1 << 30,
+                        seed: int | None = None, planted: float = 0.05, device=None, out=None):
+    """CUDA twin of ``synth.synth_image`` (identical bytes) -> uint8 CUDA tensor [count,h,w,c]."""
+    from . import synth
+
+    torch = _torch()
+    lib = nat.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if out is None:
+        out = torch.empty((count, h, w, c), dtype=torch.uint8, device=dev)
+    ctx = nat.context(dev.index)
+    with ctx.lock:
+        nat.check(lib.ke_synth_images(ctx.handle, out.data_ptr(), start, count, h, w, c, n_set,
+                                      (synth.SEED if seed is None else seed) & U64, int(round(planted * 1000)),
+                                      _stream_ptr(dev.index)), "ke_synth_images")
+    return out if c > 1 else out[..., 0]
+
+
+def popc_rate(iters: int = 4096, device: int | None = None):
+    """(POPC thread-instructions per SM clock per SM, SM clock MHz) — K2's roofline denominator."""
+    lib = nat.load()
+    ctx = nat.context(device)
+    rate, mhz = C.c_double(), C.c_double()
+    with ctx.lock:
+        nat.check(lib.ke_microbench_popc(ctx.handle, iters, C.byref(rate), C.byref(mhz)), "ke_microbench_popc")
+    return rate.value, mhz.value

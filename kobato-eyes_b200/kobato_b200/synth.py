@@ -39,7 +39,7 @@ def synth_hashes(n: int, seed: int = SEED, planted: float = 0.05, max_flips: int
     n = int(n)
     idx = np.arange(n, dtype=np.uint64)
     h = _mix(seed, idx, 0)
-    n_base = n - int(n * planted)
+    n_base = n - (n * int(round(planted * 1000))) // 1000
     if n_base < 1 or n_base == n:
         return h
     t = idx[n_base:]
@@ -79,7 +79,7 @@ def _lerp_grid(seed: int, src: int, ch: int, g: int, h: int, w: int, salt: int) 
 
 def image_source(i: int, n_set: int, seed: int = SEED, planted: float = 0.05):
     """(source index, variant) of image i: variant 0 = original, 1 gain, 2 re-noised, 3 shifted."""
-    n_base = n_set - int(n_set * planted)
+    n_base = n_set - (n_set * int(round(planted * 1000))) // 1000
     if i < n_base or n_base < 1:
         return i, 0
     src = int(_mix(seed ^ 0x5EED, i, 1) % np.uint64(n_base))
