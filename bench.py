@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — duplicate-scan throughput on B200 (BASELINE.json configs[1], "C2").
+
+A *step* is one pass of the hot path over one batch of synthetic decoded images:
+    pHash+dHash (K1) -> all-pairs Hamming join, T=8, reference band predicate (K2) -> SSIM
+    verification of the candidate pairs at ssim>=0.9 (K3) -> cluster assembly (host, rank 0).
+Workload at N=1: 70 000 synthetic 512x512 RGB images (55 GB, resident in HBM; >> L2).  With N>1
+every rank holds its own 70 000-image shard (weak scaling); hashes are all-gathered (NCCL) and the
+join's triangle tiles and the SSIM pairs are split across ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                       # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM, `e2e` = the same
+scan from pinned HOST images (H2D copies, result read-back and host cluster assembly inside the
+timed region).  See DESIGN.md §Measurement for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "kobato-eyes_b200"))
+sys.path.insert(0, str(ROOT))
+
+METRIC = ("dup-scan images/s (pHash+dHash -> all-pairs Hamming T=8 -> SSIM verify), with per-kernel "
+          "pHash images/s, Hamming pairs/s, SSIM pairs/s")
+H = W = 512
+C = 3
+IMG_BYTES = H * W * C
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+
+
+def run_reference(args) -> dict:
+    """The reference's CPU path on the box's host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    from oracle.ref_workers import CpuReference
+
+    cores = os.cpu_count() or 1
+    ref = CpuReference(H, W, C, unique=args.ref_unique, cores=cores)
+    try:
+        for _ in range(args.warmup):
+            ref.step(args.ref_sample)
+        t0 = time.perf_counter()
+        stats = [ref.step(args.ref_sample) for _ in range(args.steps)]
+        total = time.perf_counter() - t0
+    finally:
+        ref.close()
+    imgs = args.ref_sample * args.steps
+    value = imgs / total
+    hash_rate = imgs / sum(s["hash_s"] for s in stats)
+    ssim_pairs = sum(s["ssim_pairs"] for s in stats)
+    ssim_s = sum(s["ssim_s"] for s in stats)
+    sample = (f"{args.ref_sample} images/step cycling {args.ref_unique} unique synthetic 512x512 RGB images "
+              f"(hash: process pool x{cores}; scan: single process over {stats[-1]['scan_files']} files; "
+              f"SSIM on <=256 candidate pairs, pool x{cores})")
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 DCT/SSIM", "data": "synthetic",
+        "config": {"workload": "C2 sample: pHash+dHash + LSH Hamming scan (T=8) + SSIM verify on CPU", "h": H, "w": W,
+                   "c": C, "images_per_step": args.ref_sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                         "phash_images_per_s": hash_rate,
+                         "ssim_pairs_per_s": (ssim_pairs / ssim_s) if ssim_s > 0 and ssim_pairs else None},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def cpu_baseline_subprocess(args) -> dict | None:
+    """Run the reference arm in a fresh process (no CUDA context is forked) on a bounded sample."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--ref-sample", str(args.ref_sample), "--ref-unique", str(args.ref_unique)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as exc:  # pragma: no cover
+        return {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA arm
+
+
+def run_cuda(args) -> dict:
+    import numpy as np
+    import torch
+
+    from kobato_b200 import _native as nat
+    from kobato_b200 import ops, pipeline, synth
+    from kobato_b200 import dist as kdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = nat.context(local)
+    hbm_peak, sm_max_mhz, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- synthetic shard, generated on the GPU (each rank its own 70k-image set) -------------
+    n = args.images
+    bank = torch.empty((n, H, W, C), dtype=torch.uint8, device=dev)
+    seed = synth.SEED + 7919 * rank
+    for lo in range(0, n, 8192):
+        cnt = min(8192, n - lo)
+        ops.synth_images_device(lo, cnt, H, W, C, n_set=n, seed=seed, out=bank[lo:lo + cnt])
+    torch.cuda.synchronize(dev)
+
+    # ---- device-resident steps (`value`) ------------------------------------------------------
+    for _ in range(args.warmup):
+        pipeline.scan(bank, threshold=8, ssim_threshold=0.9)
+    barrier()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {}
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            out = pipeline.scan(bank, threshold=8, ssim_threshold=0.9)
+            for k, v in out.stage_ms.items():
+                stage[k] = stage.get(k, 0.0) + v
+        e1.record()
+        barrier()
+    launches = ctx.launches - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * n * args.steps / (ms_total * 1e-3)
+    counts = out.counts
+
+    # ---- per-kernel timings (CUDA events around single launches, inputs >> L2 or L2-flushed) ---
+    def timed(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sum(ts) / len(ts)
+
+    k1_ms = stage["phash"] / args.steps  # live, inside the timed region: one launch per step
+    k1_bytes = n * (IMG_BYTES + 16)
+    k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+    roof_k1 = {"kernel": "ke_phash_kernel<3>", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+               "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+               "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+               "images_per_s": n / (k1_ms * 1e-3)}
+
+    # K2 at config C3: 1 M synthetic hashes, T=8, tiles split over the ranks (strong scaling)
+    popc_rate, popc_mhz = ops.popc_rate(4096, local)
+    hashes = torch.from_numpy(synth.synth_hashes(args.join_n).view(np.int64)).to(dev)
+    lib = nat.load()
+    cap = 1 << 22
+    oi = torch.empty(cap, dtype=torch.int32, device=dev)
+    oj = torch.empty(cap, dtype=torch.int32, device=dev)
+    od = torch.empty(cap, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def run_join():
+        nat.check(lib.ke_hamming_join(ctx.handle, hashes.data_ptr(), args.join_n, 8, 0, 16, 4, None, rank, world,
+                                      oi.data_ptr(), oj.data_ptr(), od.data_ptr(), cap, cnt.data_ptr(),
+                                      int(torch.cuda.current_stream(dev).cuda_stream)), "ke_hamming_join")
+
+    run_join()
+    barrier()
+    k2_ms_local = timed(run_join)
+    k2 = torch.tensor([k2_ms_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(k2, op=torch.distributed.ReduceOp.MAX)
+    k2_ms = float(k2.item())
+    pairs_total = args.join_n * (args.join_n - 1) // 2
+    k2_rate = pairs_total / (k2_ms * 1e-3)
+    # integer roofline: 2 POPC per pair on the measured POPC issue rate at the max SM clock
+    k2_peak = world * ctx.sm_count * popc_rate * sm_max_mhz * 1e6 / 2.0
+    roof_k2 = {"kernel": "ke_join_kernel<8>", "bound": "int-alu (POPC pipe)", "achieved": k2_rate, "peak": k2_peak,
+               "unit": "pairs/s", "frac": k2_rate / k2_peak, "n_hashes": args.join_n, "threshold": 8,
+               "hits": int(cnt.item()), "ms": k2_ms,
+               "popc_per_clk_per_sm_measured": popc_rate, "sm_clock_mhz_in_microbench": popc_mhz,
+               "peak_source": "measured POPC issue rate x sm_count x clocks.max.sm / 2 POPC per pair"}
+
+    # K3 at config C4's shape: 256x256 'L' crops, bank >> L2, pairs sharded by index
+    m_bank = args.ssim_bank
+    crops = torch.empty((m_bank, 256, 256, 1), dtype=torch.uint8, device=dev)
+    for lo in range(0, m_bank, 16384):
+        c_ = min(16384, m_bank - lo)
+        ops.synth_images_device(lo, c_, 256, 256, 1, n_set=m_bank, seed=seed + 1, planted=0.5, out=crops[lo:lo + c_])
+    g = torch.Generator(device="cpu").manual_seed(synth.SEED + 2 + rank)
+    n_pairs = args.ssim_pairs // world
+    ia = torch.randint(0, m_bank, (n_pairs,), generator=g).to(dev)
+    ib = torch.randint(0, m_bank, (n_pairs,), generator=g).to(dev)
+    bank_l = crops[..., 0]
+    ops.ssim_batch(bank_l, ia[:1024], ib[:1024])
+    barrier()
+    k3_ms_local = timed(lambda: ops.ssim_batch(bank_l, ia, ib))
+    k3 = torch.tensor([k3_ms_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(k3, op=torch.distributed.ReduceOp.MAX)
+    k3_ms = float(k3.item())
+    k3_bytes = n_pairs * (2 * 256 * 256 + 8)
+    k3_gbs = k3_bytes / (k3_ms_local * 1e-3) / 1e9
+    roof_k3 = {"kernel": "ke_ssim_kernel<1>", "bound": "hbm", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s",
+               "frac": k3_gbs / hbm_peak, "pairs_per_s": world * n_pairs / (k3_ms * 1e-3), "shape": "256x256 L",
+               "pairs": world * n_pairs, "bank_images": m_bank, "ms": k3_ms, "peak_source": peak_src}
+    del crops, bank_l, ia, ib, hashes
+
+    # ---- end to end from pinned host memory ---------------------------------------------------
+    import psutil
+
+    avail = psutil.virtual_memory().available
+    budget = int(avail * 0.30 / max(1, min(world, torch.cuda.device_count())))
+    n_e2e = max(1024, min(n, budget // IMG_BYTES))
+    host = torch.empty((n_e2e, H, W, C), dtype=torch.uint8, pin_memory=True)
+    for lo in range(0, n_e2e, 4096):
+        hi = min(n_e2e, lo + 4096)
+        host[lo:hi].copy_(bank[lo:hi])
+    torch.cuda.synchronize(dev)
+    dev_bank = bank[:n_e2e]
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_warm = max(1, min(args.warmup, 2))
+    for _ in range(e2e_warm):
+        pipeline.scan(dev_bank, host_images=host, threshold=8, ssim_threshold=0.9, n_local=n_e2e)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        eo = pipeline.scan(dev_bank, host_images=host, threshold=8, ssim_threshold=0.9, n_local=n_e2e)
+    t1.record()
+    barrier()
+    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * n_e2e * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(eo.bytes_h2d),
+           "d2h_bytes_per_step": int(eo.bytes_d2h), "images_per_step_per_gpu": int(n_e2e), "steps": e2e_steps,
+           "api": "kobato_b200.pipeline.scan(host_images=pinned uint8 [n,512,512,3]) -> hashes, candidates, SSIM, clusters"}
+
+    result = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 fixed point; f64 DCT; int32+f32 SSIM", "data": "synthetic",
+        "config": {"workload": "C2: 70k synthetic 512x512 RGB images per GPU: batched pHash+dHash + all-pairs Hamming "
+                               "(T=8, band predicate) + SSIM verify (>=0.9)", "images_per_gpu": n, "h": H, "w": W, "c": C,
+                   "hamming_threshold": 8, "ssim_threshold": 0.9, "l2": "inputs (55 GB/GPU) exceed L2; no flush needed",
+                   "parallelism": f"image shards x{world}; join tiles t%{world}; SSIM pairs by owner"},
+        "counts": counts,
+        "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+        "roofline": roof_k1, "roofline_join": roof_k2, "roofline_ssim": roof_k3,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        del host
+        result["cpu_baseline"] = cpu_baseline_subprocess(args)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return result if rank == 0 else {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--images", type=int, default=70000, help="images per GPU (C2: 70000)")
+    ap.add_argument("--join-n", type=int, default=1_000_000, help="hash count for the K2 roofline run (C3)")
+    ap.add_argument("--ssim-bank", type=int, default=65536, help="256x256 crops in the K3 roofline bank")
+    ap.add_argument("--ssim-pairs", type=int, default=1_000_000, help="pairs in the K3 roofline run")
+    ap.add_argument("--ref-sample", type=int, default=4096, help="images per reference-arm step")
+    ap.add_argument("--ref-unique", type=int, default=256, help="unique synthetic images behind the reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        print(f"bench.py: warmup {args.warmup} < 3 — numbers from this run are not valid bench values", file=sys.stderr)
+
+    if args.impl == "reference":
+        res = run_reference(args)
+    else:
+        if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+            # convenience: re-launch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29533", *sys.argv]
+            raise SystemExit(subprocess.call(cmd))
+        res = run_cuda(args)
+    if res:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -115,9 +115,10 @@ int64_t ke_hamming_join_pairs(int64_t n, int part_index, int part_count);
 int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride, int64_t row_stride,
                   const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs, double* d_ssim, void* stream);
 
-/* Host buffers: pair p compares h_a + p*h*w with h_b + p*h*w ('L' planes), chunked through
- * pinned staging.  Behind the drop-in dup.refine._compute_ssim / refine_pairs_batch. */
-int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w,
+/* Host buffers: pair p compares h_a + p*h*w*c with h_b + p*h*w*c (c = 1: 'L' planes), copied in
+ * chunks overlapped with the kernel.  Behind the drop-in dup.refine._compute_ssim /
+ * refine_pairs_batch. */
+int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w, int c,
                        double* h_ssim);
 
 /* ---------------------------------------------------------------------------------------

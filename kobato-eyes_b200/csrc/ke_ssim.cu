@@ -295,17 +295,18 @@ extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, i
 }
 
 extern "C" int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w,
-                                  double* h_ssim) {
+                                  int c, double* h_ssim) {
     KE_REQUIRE(ctx != nullptr, "ke_ssim_pairs_host: ctx is NULL");
     KE_REQUIRE(n_pairs >= 0, "ke_ssim_pairs_host: n_pairs < 0");
     if (n_pairs == 0) return KE_OK;
     KE_REQUIRE(h_a && h_b && h_ssim, "ke_ssim_pairs_host: NULL buffer");
+    KE_REQUIRE(c == 1 || c == 3 || c == 4, "ke_ssim_pairs_host: channels must be 1, 3 or 4 (got %d)", c);
     if (h < kWin || w < kWin) {
         ke_set_error("win_size exceeds image extent (%dx%d < 7)", w, h);
         return KE_E_UNSUPPORTED;
     }
     KeDeviceGuard guard(ctx->device);
-    const int64_t plane = (int64_t)h * w;
+    const int64_t plane = (int64_t)h * w * c;
     const int64_t stride = (plane + 15) / 16 * 16;
     int64_t per_chunk = (128ll << 20) / (2 * stride);
     if (per_chunk < 1) per_chunk = 1;
@@ -334,7 +335,7 @@ extern "C" int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t
                                   cudaMemcpyHostToDevice, s));
         KE_CUDA(cudaMemcpy2DAsync(db, (size_t)stride, h_b + p0 * plane, (size_t)plane, (size_t)plane, (size_t)cnt,
                                   cudaMemcpyHostToDevice, s));
-        rc = ke_ssim_batch(ctx, da, h, w, 1, stride, w, (const int64_t*)d_idx, (const int64_t*)d_idx + per_chunk, cnt,
+        rc = ke_ssim_batch(ctx, da, h, w, c, stride, (int64_t)w * c, (const int64_t*)d_idx, (const int64_t*)d_idx + per_chunk, cnt,
                            (double*)d_out + p0, s);
         if (rc) return rc;
     }

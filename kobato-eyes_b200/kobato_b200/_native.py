@@ -57,7 +57,8 @@ _SIGNATURES = {
     "ke_hamming_join_pairs": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "ke_ssim_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "ke_ssim_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "ke_ssim_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p]),
     "ke_synth_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
                                   C.c_uint64, C.c_int, C.c_void_p]),
     "ke_microbench_popc": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -1,0 +1,116 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, ``torch.distributed`` for plumbing.
+
+Partitioning:
+  * pHash/dHash — images are independent: each rank hashes its own shard, no collective;
+  * Hamming join — every rank needs the whole (tiny) hash table: ONE ``all_gather`` of the
+    per-rank hash shards (or a ``broadcast`` from rank 0) over NCCL/NVLink, then the N x N triangle's
+    tiles are dealt round-robin to ranks (``part_index=rank, part_count=world``) with no further
+    exchange; per-rank candidate lists are gathered to rank 0 on the host;
+  * SSIM — pairs are independent: sharded by contiguous pair index, no collective.
+
+Everything here also runs on the ``gloo`` backend with CPU tensors (the join itself is injected),
+which is how the world_size-2 CPU tests exercise the sharding logic.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def world() -> tuple[int, int]:
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, size: int) -> tuple[int, int]:
+    """Contiguous [lo, hi) share of n items for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(int(n), size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_hashes(local):
+    """Concatenate per-rank int64 hash shards (possibly of different lengths) on every rank."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    if size == 1:
+        return local
+    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(size)]
+    dist.all_gather(counts, torch.tensor([local.numel()], dtype=torch.int64, device=local.device))
+    counts = [int(c.item()) for c in counts]
+    cap = max(counts)
+    padded = torch.zeros(cap, dtype=torch.int64, device=local.device)
+    padded[: local.numel()] = local
+    parts = [torch.empty(cap, dtype=torch.int64, device=local.device) for _ in range(size)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
+def broadcast_table(table, src: int = 0):
+    """Rank `src` holds the table (int64 tensor); every rank returns its own copy."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    if size == 1:
+        return table
+    dev = table.device if table is not None else torch.device("cuda", torch.cuda.current_device())
+    n = torch.tensor([table.numel() if rank == src else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src)
+    buf = table if rank == src else torch.empty(int(n.item()), dtype=torch.int64, device=dev)
+    dist.broadcast(buf, src)
+    return buf
+
+
+def gather_candidates(i: np.ndarray, j: np.ndarray, d: np.ndarray, dst: int = 0):
+    """Per-rank candidate lists -> one (i, j, d) sorted by (i, j) on rank `dst` (None elsewhere)."""
+    dist = _dist()
+    rank, size = world()
+    if size == 1:
+        return i, j, d
+    payload = (np.ascontiguousarray(i), np.ascontiguousarray(j), np.ascontiguousarray(d))
+    gathered = [None] * size if rank == dst else None
+    dist.gather_object(payload, gathered, dst=dst)
+    if rank != dst:
+        return None
+    ii = np.concatenate([g[0] for g in gathered])
+    jj = np.concatenate([g[1] for g in gathered])
+    dd = np.concatenate([g[2] for g in gathered])
+    order = np.lexsort((jj, ii))
+    return ii[order], jj[order], dd[order]
+
+
+def distributed_join(table, threshold: int, *, require_band: bool = False, band_bits: int = 16, band_count: int = 4,
+                     band_allow=None, join: Callable | None = None, dst: int = 0):
+    """Tile-split Hamming join of a table every rank already holds.  Returns the merged candidate
+    list on rank `dst` and None on the others.  `join` defaults to the CUDA kernel."""
+    rank, size = world()
+    if join is None:
+        from . import ops
+
+        join = ops.hamming_join
+    i, j, d = join(table, threshold, require_band=require_band, band_bits=band_bits, band_count=band_count,
+                   band_allow=band_allow, part_index=rank, part_count=size)
+    return gather_candidates(i, j, d, dst)
+
+
+def sharded_ssim(bank, ia, ib, *, ssim: Callable | None = None):
+    """Each rank scores its contiguous share of the pair list; returns (lo, hi, scores[lo:hi])."""
+    rank, size = world()
+    lo, hi = shard_range(len(ia), rank, size)
+    if ssim is None:
+        from . import ops
+
+        ssim = ops.ssim_batch
+    return lo, hi, ssim(bank, ia[lo:hi], ib[lo:hi])

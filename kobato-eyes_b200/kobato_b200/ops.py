@@ -204,7 +204,8 @@ def ssim_batch(bank, ia, ib):
 
 
 def ssim_pairs(a, b) -> np.ndarray:
-    """SSIM of host 'L' planes: a, b uint8 ``[n,h,w]`` (or ``[h,w]``) -> float64 ``[n]``."""
+    """SSIM of host images: a, b uint8 ``[n,h,w]`` 'L' planes (or one ``[h,w]`` pair) or
+    ``[n,h,w,c]`` RGB(A) (Pillow luma applied on the GPU) -> float64 ``[n]``."""
     lib = nat.load()
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
@@ -212,12 +213,14 @@ def ssim_pairs(a, b) -> np.ndarray:
         raise ValueError("Input images must have the same dimensions.")
     if a.ndim == 2:
         a, b = a[None], b[None]
-    n, h, w = a.shape
+    if a.ndim == 3:
+        a, b = a[..., None], b[..., None]
+    n, h, w, c = a.shape
     out = np.empty(n, np.float64)
     if n:
         ctx = nat.context()
         with ctx.lock:
-            st = lib.ke_ssim_pairs_host(ctx.handle, _np_ptr(a), _np_ptr(b), n, h, w, _np_ptr(out))
+            st = lib.ke_ssim_pairs_host(ctx.handle, _np_ptr(a), _np_ptr(b), n, h, w, c, _np_ptr(out))
         if st == nat.KE_E_UNSUPPORTED:
             raise ValueError(nat.last_error())
         nat.check(st, "ke_ssim_pairs_host")

@@ -1,0 +1,201 @@
+"""The whole duplicate scan on decoded images: pHash+dHash -> all-pairs Hamming join -> SSIM
+verification -> clusters.  This is the call behind bench.py's step and its end-to-end number.
+
+Per rank (one process per GPU):
+    K1  hashes its own image shard (no collective)
+    --  all_gather of the hash shards (NCCL; the only exchange the path needs)
+    K2  joins its share of the triangle's tiles over the full table
+    --  candidate lists gathered to rank 0 on the host, pair list broadcast back
+    K3  verifies the pairs whose first image it owns (images of the rare cross-shard pairs are
+        sent peer to peer)
+    --  rank 0 unions the accepted pairs into clusters (host, a few thousand pairs)
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import dist as kdist
+from . import ops
+
+
+@dataclass
+class ScanOutput:
+    phash: object = None          # int64 CUDA tensor, local shard
+    dhash: object = None
+    cand_i: np.ndarray | None = None   # rank 0: merged candidates (global indices), sorted
+    cand_j: np.ndarray | None = None
+    cand_d: np.ndarray | None = None
+    ssim: np.ndarray | None = None     # rank 0: score per candidate
+    accepted: np.ndarray | None = None  # rank 0: bool per candidate
+    clusters: list | None = None       # rank 0: [(representative, [members])]
+    stage_ms: dict = field(default_factory=dict)   # device time of this rank's kernels
+    counts: dict = field(default_factory=dict)
+    bytes_h2d: int = 0
+    bytes_d2h: int = 0
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _components(i, j, keep):
+    parent: dict[int, int] = {}
+
+    def find(x):
+        parent.setdefault(x, x)
+        r = x
+        while parent[r] != r:
+            r = parent[r]
+        while parent[x] != r:
+            parent[x], x = r, parent[x]
+        return r
+
+    for a, b in zip(i[keep].tolist(), j[keep].tolist()):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    comps: dict[int, list[int]] = {}
+    for x in parent:
+        comps.setdefault(find(x), []).append(x)
+    return sorted((min(m), sorted(m)) for m in comps.values())
+
+
+class Timer:
+    """CUDA-event stage timer on the current stream."""
+
+    def __init__(self):
+        self.marks = []
+
+    def mark(self, name):
+        torch = _torch()
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.marks.append((name, ev))
+
+    def result(self):
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 0.9, require_band: bool = True,
+         chunk_images: int = 2048, n_local: int | None = None) -> ScanOutput:
+    """Run the duplicate scan over this rank's shard.
+
+    bank: CUDA uint8 [n,h,w,c] holding (or receiving) the rank's decoded images.
+    host_images: optional pinned CPU uint8 tensor of the same shape; when given, the images are
+        copied host->device in chunks overlapped with K1 (the end-to-end path) and every result is
+        read back to the host; when None the bank is taken as already resident.
+    """
+    torch = _torch()
+    rank, size = kdist.world()
+    out = ScanOutput()
+    n, h, w, c = bank.shape
+    dev = bank.device
+    tm = Timer()
+    ph = torch.empty(n, dtype=torch.int64, device=dev)
+    dh = torch.empty(n, dtype=torch.int64, device=dev)
+
+    # ---- K1 ---------------------------------------------------------------------------------
+    tm.mark("start")
+    if host_images is None:
+        p, d = ops.phash_dhash_batch(bank)
+        ph.copy_(p)
+        dh.copy_(d)
+    else:
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)
+        for lo in range(0, n, chunk_images):
+            hi = min(n, lo + chunk_images)
+            with torch.cuda.stream(copy_stream):
+                bank[lo:hi].copy_(host_images[lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            main.wait_event(ready)
+            p, d = ops.phash_dhash_batch(bank[lo:hi])
+            ph[lo:hi].copy_(p)
+            dh[lo:hi].copy_(d)
+        out.bytes_h2d += n * h * w * c
+    tm.mark("phash")
+    out.phash, out.dhash = ph, dh
+
+    # ---- exchange + K2 ----------------------------------------------------------------------
+    table = kdist.all_gather_hashes(ph)
+    tm.mark("exchange")
+    total = table.numel()
+    cap = max(1 << 16, 2 * total)
+    lib_i, lib_j, lib_d = ops.hamming_join(table, threshold, require_band=require_band, part_index=rank,
+                                           part_count=size, capacity=cap)
+    tm.mark("join")
+    out.bytes_d2h += lib_i.nbytes + lib_j.nbytes + lib_d.nbytes
+    merged = kdist.gather_candidates(lib_i, lib_j, lib_d)
+    if size > 1:
+        box = [merged]
+        kdist._dist().broadcast_object_list(box, src=0)
+        merged = box[0]
+    ci, cj, cd = merged
+    out.counts.update(images_local=int(n), images_total=int(total), candidates=int(len(ci)))
+
+    # ---- K3 ---------------------------------------------------------------------------------
+    n_loc = int(n_local if n_local is not None else n)
+    own_i = ci.astype(np.int64) // n_loc
+    own_j = cj.astype(np.int64) // n_loc
+    mine = np.flatnonzero((own_i == rank) & (own_j == rank))
+    scores = np.full(len(ci), np.nan, np.float64)
+    tm.mark("pre_ssim")
+    if len(mine):
+        s = ops.ssim_batch(bank, ci[mine].astype(np.int64) - rank * n_loc, cj[mine].astype(np.int64) - rank * n_loc)
+        tm.mark("ssim")
+        scores[mine] = s.cpu().numpy()
+        out.bytes_d2h += 8 * len(mine)
+    else:
+        tm.mark("ssim")
+    cross = np.flatnonzero(own_i != own_j)
+    if size > 1 and len(cross):
+        dist = kdist._dist()
+        tmp = torch.empty((2 * len(cross), h, w, c), dtype=torch.uint8, device=dev)
+        for k, q in enumerate(cross.tolist()):
+            a, b = int(own_i[q]), int(own_j[q])  # rank a scores the pair, rank b ships image j
+            if rank == a:
+                tmp[2 * k].copy_(bank[int(ci[q]) - a * n_loc])
+                dist.recv(tmp[2 * k + 1], src=b)
+            elif rank == b:
+                dist.send(bank[int(cj[q]) - b * n_loc].contiguous(), dst=a)
+        sel = [k for k, q in enumerate(cross.tolist()) if int(own_i[q]) == rank]
+        if sel:
+            s = ops.ssim_batch(tmp, [2 * k for k in sel], [2 * k + 1 for k in sel]).cpu().numpy()
+            scores[cross[sel]] = s
+    if size > 1:
+        box = [None] * size if rank == 0 else None
+        kdist._dist().gather_object(scores, box, dst=0)
+        if rank == 0:
+            scores = np.full(len(ci), np.nan, np.float64)
+            for part in box:  # every pair was scored by exactly one rank
+                got = ~np.isnan(part)
+                scores[got] = part[got]
+    tm.mark("post")
+
+    # ---- host assembly (rank 0) ---------------------------------------------------------------
+    if rank == 0:
+        t0 = time.perf_counter()
+        keep = scores >= ssim_threshold
+        out.cand_i, out.cand_j, out.cand_d, out.ssim, out.accepted = ci, cj, cd, scores, keep
+        out.clusters = _components(ci.astype(np.int64), cj.astype(np.int64), keep)
+        out.counts.update(accepted=int(np.count_nonzero(keep)), clusters=len(out.clusters))
+        out.stage_ms["host_assembly"] = (time.perf_counter() - t0) * 1e3
+    if host_images is not None:
+        # the hashes go back to the host too (they are what the reference stores in SQLite)
+        out.phash_host = ph.cpu().numpy()
+        out.dhash_host = dh.cpu().numpy()
+        out.bytes_d2h += 16 * n
+    torch.cuda.synchronize(dev)
+    out.stage_ms.update(tm.result())
+    out.counts["ssim_pairs_local"] = int(len(mine))
+    return out

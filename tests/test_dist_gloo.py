@@ -1,0 +1,101 @@
+"""world_size-2 `gloo` tests (CPU) of the multi-GPU sharding logic in kobato_b200.dist: hash
+all-gather, tile-split join with per-rank candidate lists gathered to rank 0, SSIM pair shards.
+The CUDA kernels are replaced by the oracle through the functions' injection seams."""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _worker(rank: int, size: int, init_file: str, out_dir: str):
+    for p in (str(ROOT), str(ROOT / "kobato-eyes_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from kobato_b200 import dist as kdist
+    from kobato_b200 import synth
+
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=size)
+    try:
+        assert kdist.world() == (rank, size)
+        # ---- hash shards of unequal length -> the same full table everywhere
+        full = synth.synth_hashes(3001, seed=5, planted=0.2)
+        lo, hi = kdist.shard_range(len(full), rank, size)
+        local = torch.from_numpy(full[lo:hi].view(np.int64))
+        table = kdist.all_gather_hashes(local)
+        assert np.array_equal(table.numpy().view(np.uint64), full)
+        # ---- broadcast from rank 0
+        t0 = torch.from_numpy(full.view(np.int64).copy()) if rank == 0 else torch.empty(0, dtype=torch.int64)
+        got = kdist.broadcast_table(t0, src=0)
+        assert np.array_equal(got.numpy().view(np.uint64), full)
+
+        # ---- join split by part_index/part_count, gathered on rank 0
+        def cpu_join(tbl, threshold, *, require_band, band_bits, band_count, band_allow, part_index, part_count):
+            h = tbl.numpy().view(np.uint64)
+            i, j, d = oracle.hamming_join(h, threshold, require_band=require_band, band_bits=band_bits,
+                                          band_count=band_count)
+            mine = (i.astype(np.int64) // 256 + j.astype(np.int64) // 256) % part_count == part_index  # "tiles"
+            return i[mine], j[mine], d[mine]
+
+        merged = kdist.distributed_join(table, 8, require_band=True, join=cpu_join)
+        if rank == 0:
+            wi, wj, wd = oracle.hamming_join(full, 8, require_band=True)
+            assert np.array_equal(merged[0], wi) and np.array_equal(merged[1], wj) and np.array_equal(merged[2], wd)
+            assert len(wi) > 50
+        else:
+            assert merged is None
+
+        # ---- SSIM pairs sharded by contiguous index
+        bank = synth.synth_images(0, 12, 24, 31, 1, n_set=12, planted=0.5)
+        ia = np.arange(11)
+        ib = np.arange(11) + 1
+
+        def cpu_ssim(bk, a, b_):
+            return oracle.ssim_batch(bk, a, b_, exact=True)
+
+        lo, hi, s = kdist.sharded_ssim(bank, ia, ib, ssim=cpu_ssim)
+        assert (lo, hi) == kdist.shard_range(11, rank, size) and len(s) == hi - lo
+        np.save(os.path.join(out_dir, f"ssim_{rank}.npy"), np.asarray(s))
+        np.save(os.path.join(out_dir, f"range_{rank}.npy"), np.array([lo, hi]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_covers_everything_once():
+    sys.path.insert(0, str(ROOT / "kobato-eyes_b200"))
+    from kobato_b200 import dist as kdist
+
+    for n in (0, 1, 7, 70000, 70001):
+        for size in (1, 2, 3, 8):
+            parts = [kdist.shard_range(n, r, size) for r in range(size)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    import oracle
+    from kobato_b200 import synth
+
+    oracle.build()
+    with tempfile.TemporaryDirectory() as tmp:
+        init_file = os.path.join(tmp, "rendezvous")
+        mp.spawn(_worker, args=(2, init_file, tmp), nprocs=2, join=True)
+        bank = synth.synth_images(0, 12, 24, 31, 1, n_set=12, planted=0.5)
+        want = oracle.ssim_batch(bank, np.arange(11), np.arange(11) + 1, exact=True)
+        got = np.concatenate([np.load(os.path.join(tmp, f"ssim_{r}.npy")) for r in range(2)])
+        assert np.allclose(got, want, atol=0, rtol=0)
