@@ -43,6 +43,10 @@ const char* ke_last_error(void);
 int ke_ctx_create(int device, ke_ctx** out);
 void ke_ctx_destroy(ke_ctx* ctx);
 int ke_ctx_device(const ke_ctx* ctx);
+/* Tuning / test knobs.  KE_OPT_PHASH_GENERIC=1 routes every image geometry through K1's generic
+ * kernel (the one used for unaligned or very wide rows) instead of the fast one. */
+#define KE_OPT_PHASH_GENERIC 1
+int ke_ctx_set_option(ke_ctx* ctx, int option, int value);
 int ke_ctx_sm_count(const ke_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------

@@ -59,6 +59,15 @@ extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
     delete ctx;
 }
 
+extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
+    KE_REQUIRE(ctx != nullptr, "ke_ctx_set_option: ctx is NULL");
+    switch (option) {
+        case KE_OPT_PHASH_GENERIC: ctx->force_generic_phash = value ? 1 : 0; return KE_OK;
+    }
+    ke_set_error("ke_ctx_set_option: unknown option %d", option);
+    return KE_E_INVALID;
+}
+
 extern "C" int ke_ctx_device(const ke_ctx* ctx) { return ctx ? ctx->device : -1; }
 extern "C" int ke_ctx_sm_count(const ke_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
 extern "C" int64_t ke_ctx_launch_count(const ke_ctx* ctx) { return ctx ? ctx->launches : -1; }

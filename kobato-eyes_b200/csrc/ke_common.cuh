@@ -46,6 +46,7 @@ struct ke_ctx {
     void* h_pinned[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_pinned_bytes[4] = {0, 0, 0, 0};
     KeTableCache* tables = nullptr;
+    int force_generic_phash = 0;  // KE_OPT_PHASH_GENERIC: route every geometry through the generic K1 kernel
 };
 
 int ke_ctx_scratch(ke_ctx* ctx, int slot, size_t bytes, void** out);

@@ -540,6 +540,314 @@ __global__ void __launch_bounds__(kThreads) ke_phash_kernel(const PhashArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ the fast kernel
+//
+// Same arithmetic, restructured for the common geometry (contiguous rows, w*c % 16 == 0, a
+// 64- or 32-row chunk fits shared memory).  288 threads: warps 0..7 compute, warp 8 is the TMA
+// producer.  Raw rows arrive in sub-chunks of `sub_rows` rows through a 2-deep ring of
+// full/empty mbarriers, so loads run ahead of the compute across chunk and image boundaries and
+// the compute warps only ever synchronise among themselves (named barrier 1).  In the horizontal
+// pass every lane owns RPL rows (lane, lane+32, ...), so one warp-uniform LDS.128 of tap words
+// feeds 3*RPL dp4a.
+
+constexpr int kFastThreads = kThreads + 32;
+constexpr int kMaxItems = 160;
+
+struct FastLayout {
+    int raw, coef, luma, acc, hrow, x32, x98, tmat, ymat, meta, items, bar, total;
+};
+
+__host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes, int chunk_rows, int pitch_words) {
+    FastLayout L;
+    int off = 0;
+    auto take = [&](int bytes, int align) {
+        off = (off + align - 1) / align * align;
+        int at = off;
+        off += bytes;
+        return at;
+    };
+    L.raw = take(2 * sub_bytes, 128);
+    L.coef = take(coef_words * 16, 16);
+    L.luma = take(chunk_rows * pitch_words * 4, 16);
+    L.acc = take(chunk_rows * kOuts * 4, 16);
+    L.hrow = take(chunk_rows * kOuts, 16);
+    L.x32 = take(1024, 16);
+    L.x98 = take(80, 16);
+    L.tmat = take(8 * 32 * 8, 16);
+    L.ymat = take(64 * 8, 16);
+    L.meta = take(2 * kOuts * 4, 16);
+    L.items = take(kMaxItems * 16, 16);
+    L.bar = take(4 * 8, 8);
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// luma of `rows` raw rows (row r at raw + r*row_bytes) -> luma rows (word pitch `pitch_words`).
+// warp -> rows, lanes -> 4-pixel groups: conflict-free LDS.32 x3 / STS.32 x1, no divisions.
+template <int C>
+__device__ __forceinline__ void luma_rows_fast(const uint8_t* __restrict__ raw, uint32_t* __restrict__ luma, int rows,
+                                               int w, int pitch_words, int warp, int lane) {
+    constexpr uint32_t LO = 0x002F468Bu, HI = 0x001D964Cu;
+    const int wq = w >> 2;
+    for (int r = warp; r < rows; r += kWarps) {
+        uint32_t* dst = luma + r * pitch_words;
+        if (C == 1) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)r * w);
+            for (int q = lane; q < wq; q += 32) dst[q] = src[q];
+        } else if (C == 3) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)r * w * 3);
+#pragma unroll 2
+            for (int q = lane; q < wq; q += 32) {
+                const uint32_t w0 = src[3 * q], w1 = src[3 * q + 1], w2 = src[3 * q + 2];
+                const uint32_t l0 = dp4a_uu(w0, LO, 0x8000u), h0 = dp4a_uu(w0, HI, 0u);
+                uint32_t l1 = dp4a_uu(w0, LO << 24, 0x8000u), h1 = dp4a_uu(w0, HI << 24, 0u);
+                l1 = dp4a_uu(w1, LO >> 8, l1), h1 = dp4a_uu(w1, HI >> 8, h1);
+                uint32_t l2 = dp4a_uu(w1, LO << 16, 0x8000u), h2 = dp4a_uu(w1, HI << 16, 0u);
+                l2 = dp4a_uu(w2, LO >> 16, l2), h2 = dp4a_uu(w2, HI >> 16, h2);
+                const uint32_t l3 = dp4a_uu(w2, LO << 8, 0x8000u), h3 = dp4a_uu(w2, HI << 8, 0u);
+                const uint32_t s0 = l0 + (h0 << 8), s1 = l1 + (h1 << 8), s2 = l2 + (h2 << 8), s3 = l3 + (h3 << 8);
+                dst[q] = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+            }
+        } else {
+            const uint4* src = reinterpret_cast<const uint4*>(raw + (size_t)r * w * 4);
+            for (int q = lane; q < wq; q += 32) {
+                const uint4 px = src[q];
+                const uint32_t s0 = dp4a_uu(px.x, LO, 0x8000u) + (dp4a_uu(px.x, HI, 0u) << 8);
+                const uint32_t s1 = dp4a_uu(px.y, LO, 0x8000u) + (dp4a_uu(px.y, HI, 0u) << 8);
+                const uint32_t s2 = dp4a_uu(px.z, LO, 0x8000u) + (dp4a_uu(px.z, HI, 0u) << 8);
+                const uint32_t s3 = dp4a_uu(px.w, LO, 0x8000u) + (dp4a_uu(px.w, HI, 0u) << 8);
+                dst[q] = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+            }
+        }
+    }
+}
+
+template <int C, int RPL>
+__global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const PhashArgs a, const int sub_rows) {
+    constexpr int CR = 32 * RPL;  // rows per chunk
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int row_bytes = a.w * C;
+    const int sub_bytes = sub_rows * row_bytes;
+    const FastLayout L = fast_layout(a.coef_words, sub_bytes, CR, a.pitch_words);
+    uint8_t* s_raw = smem + L.raw;
+    uint4* s_coef = reinterpret_cast<uint4*>(smem + L.coef);
+    uint32_t* s_luma = reinterpret_cast<uint32_t*>(smem + L.luma);
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
+    uint8_t* s_hrow = smem + L.hrow;
+    uint8_t* s_x32 = smem + L.x32;
+    uint8_t* s_x98 = smem + L.x98;
+    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
+    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
+    int* s_meta = reinterpret_cast<int*>(smem + L.meta);
+    int4* s_items = reinterpret_cast<int4*>(smem + L.items);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // [2]
+    uint64_t* s_empty = s_full + 2;                                // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_sub = (a.h + sub_rows - 1) / sub_rows;  // sub-chunks per image
+    const int subs_per_chunk = CR / sub_rows;
+
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], kWarps);
+        mbar_init(&s_empty[1], kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < a.coef_words; i += kFastThreads) s_coef[i] = a.coef[i];
+    for (int i = tid; i < 2 * kOuts; i += kFastThreads) s_meta[i] = a.meta[i];
+    for (int i = tid; i < a.n_items; i += kFastThreads) s_items[i] = a.items[i];
+    for (int i = tid; i < CR * kOuts; i += kFastThreads) s_acc[i] = 1u << (kPrec - 1);
+    __syncthreads();
+
+    if (warp == kWarps) {
+        // ===== TMA producer: one lane streams every sub-chunk of every image of this CTA =====
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+                const uint8_t* src = a.img + im * a.img_stride;
+                for (int s = 0; s < n_sub; ++s, ++seq) {
+                    const int b = seq & 1;
+                    const int rows = min(sub_rows, a.h - s * sub_rows);
+                    mbar_wait(&s_empty[b], ((seq >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
+                    bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
+                             &s_full[b]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    uint32_t seq = 0;
+    const int vx = tid & 31, vg = tid >> 5;
+    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+        int32_t vacc[4], dacc = 1 << (kPrec - 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vacc[q] = 1 << (kPrec - 1);
+
+        for (int r0 = 0; r0 < a.h; r0 += CR) {
+            const int rows = min(CR, a.h - r0);
+            // ---- luma of this chunk, sub-chunk by sub-chunk as the copies land
+            for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
+                const int b = seq & 1;
+                const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
+                mbar_wait(&s_full[b], (seq >> 1) & 1u);
+                luma_rows_fast<C>(s_raw + b * sub_bytes, s_luma + s * sub_rows * a.pitch_words, srows, a.w,
+                                  a.pitch_words, warp, lane);
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[b])) : "memory");
+            }
+            compute_sync();
+
+            // ---- horizontal taps: lane -> rows (lane, lane+32, ...), tap words warp-uniform
+            for (int it = warp; it < a.n_items; it += kWarps) {
+                const int4 item = s_items[it];
+                const int o = item.x;
+                const uint4* __restrict__ cf = s_coef + s_meta[kOuts + o] + item.y;
+                const uint32_t* __restrict__ px = s_luma + lane * a.pitch_words + s_meta[o] + item.y;
+                uint32_t d0[RPL], d1[RPL];
+                int32_t d2[RPL];
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) d0[r] = 0u, d1[r] = 0u, d2[r] = 0;
+#pragma unroll 4
+                for (int t = 0; t < item.z; ++t) {
+                    const uint4 cw = cf[t];
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        const uint32_t p = px[r * 32 * a.pitch_words + t];
+                        d0[r] = dp4a_uu(p, cw.x, d0[r]);
+                        d1[r] = dp4a_uu(p, cw.y, d1[r]);
+                        d2[r] = dp4a_us(p, cw.z, d2[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RPL; ++r)
+                    if (lane + 32 * r < rows)
+                        atomicAdd(&s_acc[(lane + 32 * r) * kOuts + o], d0[r] + (d1[r] << 8) + ((uint32_t)d2[r] << 16));
+            }
+            compute_sync();
+
+            // ---- round, clip, reset accumulators
+            for (int i = tid; i < rows * kOuts; i += kThreads) {
+                s_hrow[i] = clip8((int32_t)s_acc[i]);
+                s_acc[i] = 1u << (kPrec - 1);
+            }
+            compute_sync();
+
+            // ---- vertical taps, streamed into registers
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int yy = vg * 4 + q;
+                const int ymin = __ldg(a.b32 + 2 * yy), ylen = __ldg(a.b32 + 2 * yy + 1);
+                const int lo = max(ymin, r0), hi = min(ymin + ylen, r0 + rows);
+                const int* kk = a.kk32 + yy * a.ks32 - ymin;
+                const uint8_t* hp = s_hrow + vx - r0 * kOuts;
+                int32_t acc = vacc[q];
+#pragma unroll 4
+                for (int y = lo; y < hi; ++y) acc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
+                vacc[q] = acc;
+            }
+            if (tid < kDW * kDH) {
+                const int yy = tid / kDW, x = tid - yy * kDW;
+                const int ymin = __ldg(a.b8 + 2 * yy), ylen = __ldg(a.b8 + 2 * yy + 1);
+                const int lo = max(ymin, r0), hi = min(ymin + ylen, r0 + rows);
+                const int* kk = a.kk8 + yy * a.ks8 - ymin;
+                const uint8_t* hp = s_hrow + kOutW + x - r0 * kOuts;
+#pragma unroll 4
+                for (int y = lo; y < hi; ++y) dacc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
+            }
+        }
+
+        // ---- planes, DCT, hash bits (identical to the generic kernel)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_x32[(vg * 4 + q) * 32 + vx] = clip8(vacc[q]);
+        if (tid < kDW * kDH) s_x98[tid] = clip8(dacc);
+        compute_sync();
+        if (a.plane32)
+            for (int i = tid; i < 1024; i += kThreads) a.plane32[im * 1024 + i] = s_x32[i];
+        if (a.plane98 && tid < kDW * kDH) a.plane98[im * 72 + tid] = s_x98[tid];
+        {
+            const int k = tid >> 5, x = tid & 31;
+            double s = 0.0;
+#pragma unroll 8
+            for (int nn = 0; nn < 32; ++nn) s = fma(c_dct[k * 32 + nn], (double)s_x32[nn * 32 + x], s);
+            s_t[k * 32 + x] = s;
+        }
+        compute_sync();
+        if (tid < 64) {
+            const int k = tid >> 3, l = tid & 7;
+            double s = 0.0;
+#pragma unroll 8
+            for (int nn = 0; nn < 32; ++nn) s = fma(s_t[k * 32 + nn], c_dct[l * 32 + nn], s);
+            s_y[tid] = s;
+        }
+        compute_sync();
+        if (warp == 0) {
+            const double y0 = s_y[lane], y1 = s_y[lane + 32];
+            double sum = (lane == 0 ? 0.0 : y0) + y1;
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            const double mean = sum / 63.0;
+            const uint32_t bhi = __ballot_sync(0xffffffffu, y0 > mean), blo = __ballot_sync(0xffffffffu, y1 > mean);
+            double mg = fmin(fabs(y0 - mean), fabs(y1 - mean));
+#pragma unroll
+            for (int off = 16; off; off >>= 1) mg = fmin(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+            const int r_a = lane >> 3, c_a = lane & 7;
+            const uint32_t dhi = __ballot_sync(0xffffffffu, s_x98[r_a * 9 + c_a + 1] > s_x98[r_a * 9 + c_a]);
+            const uint32_t dlo =
+                __ballot_sync(0xffffffffu, s_x98[(r_a + 4) * 9 + c_a + 1] > s_x98[(r_a + 4) * 9 + c_a]);
+            if (lane == 0) {
+                a.phash[im] = ((uint64_t)__brev(bhi) << 32) | (uint64_t)__brev(blo);
+                a.dhash[im] = ((uint64_t)__brev(dhi) << 32) | (uint64_t)__brev(dlo);
+                if (a.min_margin) a.min_margin[im] = (float)mg;
+            }
+        }
+        // s_x32 / s_x98 / s_y are rewritten only after the next image's chunk barriers
+    }
+}
+
+// Picks (RPL, sub_rows) for the fast kernel; returns false when the geometry needs the generic one.
+template <int C>
+bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, FastLayout& L) {
+    const long long row_bytes = (long long)a.w * C;
+    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || a.n_items > kMaxItems) return false;
+    const int rpls[2] = {2, 1};
+    for (int budget : {113 * 1024, 227 * 1024}) {  // first try to keep two CTAs per SM
+        for (int r : rpls) {
+            for (int sub = 16; sub >= 1; sub >>= 1) {
+                if (32 * r % sub) continue;
+                const long long sub_bytes = sub * row_bytes;
+                if (sub_bytes > (1 << 20)) continue;
+                L = fast_layout(a.coef_words, (int)sub_bytes, 32 * r, a.pitch_words);
+                if (L.total <= budget) {
+                    rpl = r;
+                    sub_rows = sub;
+                    return true;
+                }
+            }
+        }
+    }
+    return false;
+}
+
+template <int C, int RPL>
+int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, const FastLayout& L, cudaStream_t s) {
+    KE_CUDA(cudaFuncSetAttribute(ke_phash_fast_kernel<C, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_fast_kernel<C, RPL>, kFastThreads, L.total));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.n) grid = a.n;
+    ke_phash_fast_kernel<C, RPL><<<(unsigned)grid, kFastThreads, L.total, s>>>(a, sub_rows);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 int g_dct_uploaded_device = -1;
 
 int ensure_dct(ke_ctx* ctx) {
@@ -559,6 +867,12 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
+    {
+        int rpl = 0, sub_rows = 0;
+        FastLayout FL;
+        if (!ctx->force_generic_phash && fast_config<C>(a, rpl, sub_rows, FL))
+            return rpl == 2 ? launch_fast<C, 2>(ctx, a, sub_rows, FL, s) : launch_fast<C, 1>(ctx, a, sub_rows, FL, s);
+    }
     int rc_rows = 32;
     SmemLayout L;
     for (;;) {

@@ -77,8 +77,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct HSum {
-    uint32_t s;  // Su | Sv << 16 (each <= 7*255)
-    uint32_t uu, vv, uv;
+    uint32_t s;   // Su | Sv << 16 (each <= 7*255)
+    uint32_t t;   // Suu + Svv (only their sum enters the formula)
+    uint32_t uv;  // Suv
 };
 
 // Horizontal 7-sums of the window starting at byte `k` (0..3) of word w0.
@@ -92,20 +93,19 @@ __device__ __forceinline__ HSum hsum7(const uint32_t* __restrict__ ru, const uin
     const uint32_t su = dp4a_uu(ua, 0x01010101u, dp4a_uu(ub, 0x00010101u, 0u));
     const uint32_t sv = dp4a_uu(va, 0x01010101u, dp4a_uu(vb, 0x00010101u, 0u));
     r.s = su + (sv << 16);
-    r.uu = dp4a_uu(ua, ua, dp4a_uu(ub, ubm, 0u));
-    r.vv = dp4a_uu(va, va, dp4a_uu(vb, vbm, 0u));
+    r.t = dp4a_uu(ua, ua, dp4a_uu(ub, ubm, dp4a_uu(va, va, dp4a_uu(vb, vbm, 0u))));
     r.uv = dp4a_uu(ua, va, dp4a_uu(ub, vbm, 0u));
     return r;
 }
 
-__device__ __forceinline__ float ssim_point(uint32_t s, uint32_t suu, uint32_t svv, uint32_t suv) {
+__device__ __forceinline__ float ssim_point(uint32_t s, uint32_t st, uint32_t suv) {
     constexpr float C1 = 1e-4f * 49.0f * 49.0f * 255.0f * 255.0f;
     constexpr float C2 = 9e-4f * 48.0f * 49.0f * 255.0f * 255.0f;
     const int a = (int)(s & 0xFFFFu), b = (int)(s >> 16);
     const int p = a * b;
     const int q = a * a + b * b;
     const int vxy = 49 * (int)suv - p;
-    const int vs = 49 * (int)(suu + svv) - q;
+    const int vs = 49 * (int)st - q;
     const float num = fmaf(2.0f, (float)p, C1) * fmaf(2.0f, (float)vxy, C2);
     const float den = ((float)q + C1) * ((float)vs + C2);
     return __fdividef(num, den);
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
 
         HSum ring[kWin];
 #pragma unroll
-        for (int i = 0; i < kWin; ++i) ring[i] = HSum{0u, 0u, 0u, 0u};
-        uint32_t acc_s = 0, acc_uu = 0, acc_vv = 0, acc_uv = 0;
+        for (int i = 0; i < kWin; ++i) ring[i] = HSum{0u, 0u, 0u};
+        uint32_t acc_s = 0, acc_t = 0, acc_uv = 0;
         double total = 0.0;
         const bool active = tid < out_cols;
         const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(tid & 3);
@@ -199,19 +199,16 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
                     for (int k = 0; k < kWin; ++k) {
                         const int r = rb + k;  // (r0 + r) % 7 == k because strips are multiples of 7
                         if (r < rows) {
-                            const HSum hs = hsum7(su + r * pw, sv + r * pw, sel);
-                            acc_s += hs.s;
-                            acc_uu += hs.uu;
-                            acc_vv += hs.vv;
-                            acc_uv += hs.uv;
-                            if (r0 + r >= kWin - 1) part += ssim_point(acc_s, acc_uu, acc_vv, acc_uv);
+                            // the slot of row (r0+r-7) is dead: build the new row's sums in place
+                            ring[k] = hsum7(su + r * pw, sv + r * pw, sel);
+                            acc_s += ring[k].s;
+                            acc_t += ring[k].t;
+                            acc_uv += ring[k].uv;
+                            if (r0 + r >= kWin - 1) part += ssim_point(acc_s, acc_t, acc_uv);
                             // slot (k+1)%7 holds row (r0+r-6): it leaves the window
-                            const HSum old = ring[(k + 1) % kWin];
-                            acc_s -= old.s;
-                            acc_uu -= old.uu;
-                            acc_vv -= old.vv;
-                            acc_uv -= old.uv;
-                            ring[k] = hs;
+                            acc_s -= ring[(k + 1) % kWin].s;
+                            acc_t -= ring[(k + 1) % kWin].t;
+                            acc_uv -= ring[(k + 1) % kWin].uv;
                         }
                     }
                 }

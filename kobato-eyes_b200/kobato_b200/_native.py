@@ -12,6 +12,7 @@ from pathlib import Path
 
 KE_OK, KE_E_INVALID, KE_E_CUDA, KE_E_CAPACITY, KE_E_NOMEM, KE_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 KE_JOIN_REQUIRE_BAND = 1
+KE_OPT_PHASH_GENERIC = 1
 
 _LIB_PATH = Path(__file__).resolve().parent / "libkobato_b200.so"
 _lib = None
@@ -40,6 +41,7 @@ _SIGNATURES = {
     "ke_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "ke_ctx_destroy": (None, [C.c_void_p]),
     "ke_ctx_device": (C.c_int, [C.c_void_p]),
+    "ke_ctx_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ke_ctx_sm_count": (C.c_int, [C.c_void_p]),
     "ke_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "ke_resample_ksize": (C.c_int, [C.c_int, C.c_int]),
@@ -129,6 +131,9 @@ class Context:
     @property
     def launches(self) -> int:
         return int(load().ke_ctx_launch_count(self.handle))
+
+    def set_option(self, option: int, value: int) -> None:
+        check(load().ke_ctx_set_option(self.handle, int(option), int(value)), "ke_ctx_set_option")
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:

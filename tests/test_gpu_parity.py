@@ -336,3 +336,22 @@ def test_ssim_scale_properties_at_bench_size():
     for k in range(0, 20000, 997):
         want = ref_py.ssim_of_planes(host[ia[k]], host[ib[k]])
         assert abs(float(s_ab[k]) - want) <= SSIM_TOL
+
+
+def test_phash_fast_and_generic_kernels_agree():
+    """K1 has two kernels (fast: aligned contiguous rows; generic: everything else); on geometries both
+    accept they must produce identical planes and hashes."""
+    torch = _torch()
+    from kobato_b200 import _native as nat
+
+    ctx = nat.context(torch.cuda.current_device())
+    for (h, w, c, n) in ((512, 512, 3, 300), (96, 160, 3, 40), (200, 64, 4, 20), (130, 256, 1, 20), (1100, 1024, 3, 6)):
+        imgs = ops.synth_images_device(0, n, h, w, c, n_set=n)
+        fast = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
+        ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
+        try:
+            gen = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
+        finally:
+            ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
+        assert torch.equal(fast[0], gen[0]) and torch.equal(fast[1], gen[1]) and torch.equal(fast[2], gen[2])
+        assert torch.equal(fast[3][0], gen[3][0]) and torch.equal(fast[3][1], gen[3][1])
