@@ -24,6 +24,8 @@
 // Algorithmic HBM bytes per image: h*w*c read + 16 written.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -43,8 +45,10 @@ constexpr int kPrec = 22;
 struct HTable {           // horizontal pass, one per input width
     uint4* d_coef = nullptr;   // packed byte-plane tap words, outputs back to back
     int4* d_items = nullptr;   // work items {out, word_begin, word_count, 0}
-    int* d_meta = nullptr;     // [kOuts] first pixel word, [kOuts] offset into d_coef
+    int4* d_bal = nullptr;     // the same word-steps cut into kWarps lists of equal length (fast kernel)
+    int* d_meta = nullptr;     // [kOuts] first pixel word, [kOuts] offset into d_coef, [kWarps+1] list starts
     int n_items = 0;
+    int n_bal = 0;
     int coef_words = 0;
 };
 struct VTable {           // vertical pass, one per input height
@@ -67,6 +71,7 @@ void ke_tables_free(KeTableCache* cache) {
     for (auto& kv : cache->h) {
         cudaFree(kv.second.d_coef);
         cudaFree(kv.second.d_items);
+        cudaFree(kv.second.d_bal);
         cudaFree(kv.second.d_meta);
     }
     for (auto& kv : cache->v) {
@@ -95,7 +100,7 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         return KE_OK;
     }
     std::vector<uint4> coef;
-    std::vector<int> meta(2 * kOuts);
+    std::vector<int> meta(2 * kOuts + kWarps + 1);
     std::vector<int> nwords(kOuts);
     const int outs[2] = {kOutW, kDW};
     int o_base = 0;
@@ -146,12 +151,31 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         }
     }
     std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return a.z > b.z; });
+    // Balanced lists: the concatenated word-steps of all outputs, cut into kWarps equal ranges.
+    std::vector<int4> bal;
+    {
+        long long total = 0;
+        for (int o = 0; o < kOuts; ++o) total += nwords[o];
+        for (int wv = 0; wv < kWarps; ++wv) {
+            meta[2 * kOuts + wv] = (int)bal.size();
+            const long long lo = total * wv / kWarps, hi = total * (wv + 1) / kWarps;
+            long long base = 0;
+            for (int o = 0; o < kOuts; ++o) {
+                const long long b = std::max(lo, base), e = std::min(hi, base + nwords[o]);
+                if (e > b) bal.push_back(make_int4(o, (int)(b - base), (int)(e - b), 0));
+                base += nwords[o];
+            }
+        }
+        meta[2 * kOuts + kWarps] = (int)bal.size();
+    }
     HTable t;
+    t.n_bal = (int)bal.size();
     t.n_items = (int)items.size();
     t.coef_words = (int)coef.size();
     int rc;
     if ((rc = upload(coef, &t.d_coef))) return rc;
     if ((rc = upload(items, &t.d_items))) return rc;
+    if ((rc = upload(bal, &t.d_bal))) return rc;
     if ((rc = upload(meta, &t.d_meta))) return rc;
     auto ins = ctx->tables->h.emplace(w, t);
     *out = &ins.first->second;
@@ -214,6 +238,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    // producer side: nobody else can use this lane's issue slots productively, so sleep between polls
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
@@ -238,8 +277,9 @@ struct PhashArgs {
     // tables
     const uint4* coef;
     const int4* items;
+    const int4* bal;
     const int* meta;
-    int n_items, coef_words;
+    int n_items, n_bal, coef_words;
     const int* kk32;
     const int* b32;
     const int* kk8;
@@ -552,12 +592,14 @@ __global__ void __launch_bounds__(kThreads) ke_phash_kernel(const PhashArgs a) {
 
 constexpr int kFastThreads = kThreads + 32;
 constexpr int kMaxItems = 160;
+constexpr int kMaxSlots = 8;
 
 struct FastLayout {
     int raw, coef, luma, acc, hrow, x32, x98, tmat, ymat, meta, items, bar, total;
 };
 
-__host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes, int chunk_rows, int pitch_words) {
+__host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes, int chunk_rows, int pitch_words,
+                                                  int n_slots) {
     FastLayout L;
     int off = 0;
     auto take = [&](int bytes, int align) {
@@ -566,7 +608,7 @@ __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes,
         off += bytes;
         return at;
     };
-    L.raw = take(2 * sub_bytes, 128);
+    L.raw = take(n_slots * sub_bytes, 128);
     L.coef = take(coef_words * 16, 16);
     L.luma = take(chunk_rows * pitch_words * 4, 16);
     L.acc = take(chunk_rows * kOuts * 4, 16);
@@ -575,9 +617,9 @@ __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes,
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
     L.ymat = take(64 * 8, 16);
-    L.meta = take(2 * kOuts * 4, 16);
+    L.meta = take((2 * kOuts + kWarps + 1) * 4, 16);
     L.items = take(kMaxItems * 16, 16);
-    L.bar = take(4 * 8, 8);
+    L.bar = take(2 * kMaxSlots * 8, 8);
     L.total = off;
     return L;
 }
@@ -625,12 +667,14 @@ __device__ __forceinline__ void luma_rows_fast(const uint8_t* __restrict__ raw, 
 }
 
 template <int C, int RPL>
-__global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const PhashArgs a, const int sub_rows) {
+__global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, const int dbg) {
     constexpr int CR = 32 * RPL;  // rows per chunk
     extern __shared__ __align__(128) uint8_t smem[];
     const int row_bytes = a.w * C;
     const int sub_bytes = sub_rows * row_bytes;
-    const FastLayout L = fast_layout(a.coef_words, sub_bytes, CR, a.pitch_words);
+    const int n_slots = 1 << slot_shift;
+    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
+    const FastLayout L = fast_layout(a.coef_words, sub_bytes, CR, a.pitch_words, n_slots);
     uint8_t* s_raw = smem + L.raw;
     uint4* s_coef = reinterpret_cast<uint4*>(smem + L.coef);
     uint32_t* s_luma = reinterpret_cast<uint32_t*>(smem + L.luma);
@@ -642,23 +686,23 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
     double* s_y = reinterpret_cast<double*>(smem + L.ymat);
     int* s_meta = reinterpret_cast<int*>(smem + L.meta);
     int4* s_items = reinterpret_cast<int4*>(smem + L.items);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // [2]
-    uint64_t* s_empty = s_full + 2;                                // [2]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // [kMaxSlots]
+    uint64_t* s_empty = s_full + kMaxSlots;                        // [kMaxSlots]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_sub = (a.h + sub_rows - 1) / sub_rows;  // sub-chunks per image
     const int subs_per_chunk = CR / sub_rows;
 
     if (tid == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], kWarps);
-        mbar_init(&s_empty[1], kWarps);
+        for (int b = 0; b < n_slots; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], kWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < a.coef_words; i += kFastThreads) s_coef[i] = a.coef[i];
-    for (int i = tid; i < 2 * kOuts; i += kFastThreads) s_meta[i] = a.meta[i];
-    for (int i = tid; i < a.n_items; i += kFastThreads) s_items[i] = a.items[i];
+    for (int i = tid; i < 2 * kOuts + kWarps + 1; i += kFastThreads) s_meta[i] = a.meta[i];
+    for (int i = tid; i < a.n_bal; i += kFastThreads) s_items[i] = a.bal[i];
     for (int i = tid; i < CR * kOuts; i += kFastThreads) s_acc[i] = 1u << (kPrec - 1);
     __syncthreads();
 
@@ -669,9 +713,13 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
             for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
                 const uint8_t* src = a.img + im * a.img_stride;
                 for (int s = 0; s < n_sub; ++s, ++seq) {
-                    const int b = seq & 1;
+                    const int b = seq & slot_mask;
                     const int rows = min(sub_rows, a.h - s * sub_rows);
-                    mbar_wait(&s_empty[b], ((seq >> 1) & 1u) ^ 1u);
+                    mbar_wait_backoff(&s_empty[b], ((seq >> slot_shift) & 1u) ^ 1u);
+                    if (dbg & 1) {  // tuning probe: no HBM traffic, stale shared memory is hashed
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[b])) : "memory");
+                        continue;
+                    }
                     mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
                     bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
                              &s_full[b]);
@@ -693,18 +741,19 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
             const int rows = min(CR, a.h - r0);
             // ---- luma of this chunk, sub-chunk by sub-chunk as the copies land
             for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
-                const int b = seq & 1;
+                const int b = seq & slot_mask;
                 const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
-                mbar_wait(&s_full[b], (seq >> 1) & 1u);
+                mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
                 luma_rows_fast<C>(s_raw + b * sub_bytes, s_luma + s * sub_rows * a.pitch_words, srows, a.w,
                                   a.pitch_words, warp, lane);
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[b])) : "memory");
             }
             compute_sync();
+            if (dbg & 2) continue;  // tuning probe: loads + luma only
 
             // ---- horizontal taps: lane -> rows (lane, lane+32, ...), tap words warp-uniform
-            for (int it = warp; it < a.n_items; it += kWarps) {
+            for (int it = s_meta[2 * kOuts + warp]; it < ((dbg & 4) ? 0 : s_meta[2 * kOuts + warp + 1]); ++it) {
                 const int4 item = s_items[it];
                 const int o = item.x;
                 const uint4* __restrict__ cf = s_coef + s_meta[kOuts + o] + item.y;
@@ -810,24 +859,37 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
     }
 }
 
-// Picks (RPL, sub_rows) for the fast kernel; returns false when the geometry needs the generic one.
+// Picks (RPL, sub_rows, ring slots) for the fast kernel; false when the geometry needs the generic one.
+// Order = measured on B200 at 512x512x3 (tools/sweep_phash.sh): the kernel is issue / shared-memory
+// bound, not load bound, so the smallest footprint (most L1 left, two CTAs per SM) wins and a
+// deeper ring does not help.
 template <int C>
-bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, FastLayout& L) {
+bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, int& slot_shift, FastLayout& L) {
     const long long row_bytes = (long long)a.w * C;
-    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || a.n_items > kMaxItems) return false;
-    const int rpls[2] = {2, 1};
-    for (int budget : {113 * 1024, 227 * 1024}) {  // first try to keep two CTAs per SM
-        for (int r : rpls) {
-            for (int sub = 16; sub >= 1; sub >>= 1) {
-                if (32 * r % sub) continue;
-                const long long sub_bytes = sub * row_bytes;
-                if (sub_bytes > (1 << 20)) continue;
-                L = fast_layout(a.coef_words, (int)sub_bytes, 32 * r, a.pitch_words);
-                if (L.total <= budget) {
-                    rpl = r;
-                    sub_rows = sub;
-                    return true;
-                }
+    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || a.n_bal > kMaxItems) return false;
+    struct Cand { int rpl, sub, shift; };
+    const Cand cands[] = {{1, 8, 1}, {2, 8, 1}, {1, 4, 1}, {1, 2, 1}, {1, 1, 1}};
+    if (const char* env = getenv("KE_PHASH_CFG")) {  // tuning override: "rpl,sub_rows,slot_shift"
+        Cand cd{0, 0, 0};
+        if (sscanf(env, "%d,%d,%d", &cd.rpl, &cd.sub, &cd.shift) == 3 && (cd.rpl == 1 || cd.rpl == 2) && cd.sub >= 1 &&
+            (32 * cd.rpl) % cd.sub == 0 && cd.shift >= 1 && cd.shift <= 3) {
+            L = fast_layout(a.coef_words, (int)(cd.sub * row_bytes), 32 * cd.rpl, a.pitch_words, 1 << cd.shift);
+            if (L.total <= 227 * 1024) {
+                rpl = cd.rpl, sub_rows = cd.sub, slot_shift = cd.shift;
+                return true;
+            }
+        }
+    }
+    for (int budget : {113 * 1024, 227 * 1024}) {
+        for (const Cand& cd : cands) {
+            const long long sub_bytes = cd.sub * row_bytes;
+            if (sub_bytes > (1 << 20)) continue;
+            L = fast_layout(a.coef_words, (int)sub_bytes, 32 * cd.rpl, a.pitch_words, 1 << cd.shift);
+            if (L.total <= budget) {
+                rpl = cd.rpl;
+                sub_rows = cd.sub;
+                slot_shift = cd.shift;
+                return true;
             }
         }
     }
@@ -835,14 +897,16 @@ bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, FastLayout& L) {
 }
 
 template <int C, int RPL>
-int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, const FastLayout& L, cudaStream_t s) {
+int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, const FastLayout& L, cudaStream_t s) {
     KE_CUDA(cudaFuncSetAttribute(ke_phash_fast_kernel<C, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int per_sm = 0;
     KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_fast_kernel<C, RPL>, kFastThreads, L.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > a.n) grid = a.n;
-    ke_phash_fast_kernel<C, RPL><<<(unsigned)grid, kFastThreads, L.total, s>>>(a, sub_rows);
+    const char* dbg_env = getenv("KE_PHASH_DBG");
+    ke_phash_fast_kernel<C, RPL><<<(unsigned)grid, kFastThreads, L.total, s>>>(a, sub_rows, slot_shift,
+                                                                                dbg_env ? atoi(dbg_env) : 0);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;
@@ -868,10 +932,11 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
     {
-        int rpl = 0, sub_rows = 0;
+        int rpl = 0, sub_rows = 0, slot_shift = 1;
         FastLayout FL;
-        if (!ctx->force_generic_phash && fast_config<C>(a, rpl, sub_rows, FL))
-            return rpl == 2 ? launch_fast<C, 2>(ctx, a, sub_rows, FL, s) : launch_fast<C, 1>(ctx, a, sub_rows, FL, s);
+        if (!ctx->force_generic_phash && fast_config<C>(a, rpl, sub_rows, slot_shift, FL))
+            return rpl == 2 ? launch_fast<C, 2>(ctx, a, sub_rows, slot_shift, FL, s)
+                            : launch_fast<C, 1>(ctx, a, sub_rows, slot_shift, FL, s);
     }
     int rc_rows = 32;
     SmemLayout L;
@@ -932,6 +997,8 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     a.use_bulk = (row_stride == (int64_t)w * c) && ((reinterpret_cast<uintptr_t>(d_img) & 15) == 0);
     a.coef = ht->d_coef;
     a.items = ht->d_items;
+    a.bal = ht->d_bal;
+    a.n_bal = ht->n_bal;
     a.meta = ht->d_meta;
     a.n_items = ht->n_items;
     a.coef_words = ht->coef_words;

@@ -23,7 +23,7 @@ data = [r for r in rows[s + 2:e] if len(r) > ii]
 base = int(data[0][ia], 16)
 # map function offsets -> source line from nvdisasm -g output
 fn = re.search(r"ke_\w+_kernel\w*", kname).group(0)
-tmpl = re.search(r"<\(int\)(\d+)>", kname)
+tmpl = re.findall(r"\(int\)(\d+)", kname)
 line_of = {}
 cur = None
 infn = False
@@ -32,7 +32,7 @@ for ln in open(sass):
     m = re.match(r"\s*\.section\s+\.text\.(\S+)", ln)
     if m:
         name = m.group(1)
-        infn = fn in name and (tmpl is None or f"ILi{tmpl.group(1)}E" in name)
+        infn = (fn + "I" in name or fn + "E" in name) and "".join(f"Li{t}E" for t in tmpl) in name
         continue
     if not infn:
         continue
