@@ -199,7 +199,9 @@ def run_cuda(args) -> dict:
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {}
-    with ClockSampler(local) as clocks:
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    if True:
         e0.record()
         for _ in range(args.steps):
             out = pipeline.scan(bank, threshold=8, ssim_threshold=0.9)
@@ -230,7 +232,7 @@ def run_cuda(args) -> dict:
     k1_ms = stage["phash"] / args.steps  # live, inside the timed region: one launch per step
     k1_bytes = n * (IMG_BYTES + 16)
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
-    roof_k1 = {"kernel": "ke_phash_kernel<3>", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roof_k1 = {"kernel": "ke_phash_fast_kernel<3,1> (512x512x3)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                "images_per_s": n / (k1_ms * 1e-3)}
@@ -320,6 +322,7 @@ def run_cuda(args) -> dict:
     if world > 1:
         torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
     e2e_value = world * n_e2e * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    clocks.__exit__(None, None, None)
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(eo.bytes_h2d),
            "d2h_bytes_per_step": int(eo.bytes_d2h), "images_per_step_per_gpu": int(n_e2e), "steps": e2e_steps,
            "api": "kobato_b200.pipeline.scan(host_images=pinned uint8 [n,512,512,3]) -> hashes, candidates, SSIM, clusters"}
