@@ -50,6 +50,11 @@ struct HTable {           // horizontal pass, one per input width
     int n_items = 0;
     int n_bal = 0;
     int coef_words = 0;
+    // lanes=outputs kernel: warp-tasks of 32 lane-tasks (output, first 16-pixel group, <= 8 groups)
+    uint4* d_lt_coef = nullptr;  // [(task*8 + group)*3 + plane][lane] -> 4 tap words
+    int2* d_lt_meta = nullptr;   // [task][lane] -> {output or -1, first group}
+    int* d_lt_ng = nullptr;      // [task] -> groups to process (uniform per warp-task)
+    int n_wtasks = 0;
 };
 struct VTable {           // vertical pass, one per input height
     int* d_kk32 = nullptr;
@@ -73,6 +78,9 @@ void ke_tables_free(KeTableCache* cache) {
         cudaFree(kv.second.d_items);
         cudaFree(kv.second.d_bal);
         cudaFree(kv.second.d_meta);
+        cudaFree(kv.second.d_lt_coef);
+        cudaFree(kv.second.d_lt_meta);
+        cudaFree(kv.second.d_lt_ng);
     }
     for (auto& kv : cache->v) {
         cudaFree(kv.second.d_kk32);
@@ -168,7 +176,65 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         }
         meta[2 * kOuts + kWarps] = (int)bal.size();
     }
+    // Lane-task tables: every output's taps, aligned to 16-pixel groups, cut into segments of <= 8
+    // groups; 32 lane-tasks (segment-major order) form one warp-task.
+    std::vector<uint4> lt_coef;
+    std::vector<int2> lt_meta;
+    std::vector<int> lt_ng;
+    {
+        int ob = 0;
+        for (int tbl = 0; tbl < 2; ++tbl) {
+            const int ow = outs[tbl];
+            const int ks = ke_resample_ksize(w, ow);
+            std::vector<int32_t> kk((size_t)ks * ow), bd(2 * (size_t)ow);
+            int rc = ke_resample_table(w, ow, kk.data(), bd.data(), ks);
+            if (rc) return rc;
+            int max_seg = 1;
+            std::vector<int> gfirst(ow), ngr(ow);
+            for (int o = 0; o < ow; ++o) {
+                gfirst[o] = bd[2 * o] / 16;
+                ngr[o] = (bd[2 * o] + bd[2 * o + 1] - 1) / 16 - gfirst[o] + 1;
+                max_seg = std::max(max_seg, (ngr[o] + 7) / 8);
+            }
+            struct LT { int o, g0, len; };
+            std::vector<LT> lts;
+            for (int sgi = 0; sgi < max_seg; ++sgi)
+                for (int o = 0; o < ow; ++o) {
+                    const int nseg = (ngr[o] + 7) / 8;
+                    if (sgi >= nseg) continue;
+                    const int b = ngr[o] * sgi / nseg, e = ngr[o] * (sgi + 1) / nseg;
+                    lts.push_back({o, gfirst[o] + b, e - b});
+                }
+            for (size_t base = 0; base < lts.size(); base += 32) {
+                const int task = (int)lt_ng.size();
+                int ng = 1;
+                for (size_t l = base; l < std::min(lts.size(), base + 32); ++l) ng = std::max(ng, lts[l].len);
+                lt_ng.push_back(ng);
+                lt_meta.resize((size_t)(task + 1) * 32, make_int2(-1, 0));
+                lt_coef.resize((size_t)(task + 1) * 8 * 3 * 32, make_uint4(0, 0, 0, 0));
+                for (int lane = 0; lane < 32 && base + lane < lts.size(); ++lane) {
+                    const LT& lt = lts[base + lane];
+                    lt_meta[(size_t)task * 32 + lane] = make_int2(ob + lt.o, lt.g0);
+                    const int first = bd[2 * lt.o], count = bd[2 * lt.o + 1];
+                    for (int g = 0; g < lt.len; ++g)
+                        for (int p = 0; p < 3; ++p) {
+                            uint32_t wd[4] = {0, 0, 0, 0};
+                            for (int b = 0; b < 16; ++b) {
+                                const int x = (lt.g0 + g) * 16 + b, tap = x - first;
+                                const int32_t k = (tap >= 0 && tap < count) ? kk[(size_t)lt.o * ks + tap] : 0;
+                                const uint32_t byte = p == 0 ? ((uint32_t)k & 0xFFu)
+                                                      : p == 1 ? (((uint32_t)k >> 8) & 0xFFu) : ((uint32_t)(k >> 16) & 0xFFu);
+                                wd[b >> 2] |= byte << (8 * (b & 3));
+                            }
+                            lt_coef[((size_t)(task * 8 + g) * 3 + p) * 32 + lane] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                        }
+                }
+            }
+            ob += ow;
+        }
+    }
     HTable t;
+    t.n_wtasks = (int)lt_ng.size();
     t.n_bal = (int)bal.size();
     t.n_items = (int)items.size();
     t.coef_words = (int)coef.size();
@@ -176,6 +242,9 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
     if ((rc = upload(coef, &t.d_coef))) return rc;
     if ((rc = upload(items, &t.d_items))) return rc;
     if ((rc = upload(bal, &t.d_bal))) return rc;
+    if ((rc = upload(lt_coef, &t.d_lt_coef))) return rc;
+    if ((rc = upload(lt_meta, &t.d_lt_meta))) return rc;
+    if ((rc = upload(lt_ng, &t.d_lt_ng))) return rc;
     if ((rc = upload(meta, &t.d_meta))) return rc;
     auto ins = ctx->tables->h.emplace(w, t);
     *out = &ins.first->second;
@@ -250,7 +319,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(200);
+        __nanosleep(800);
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -280,6 +349,10 @@ struct PhashArgs {
     const int4* bal;
     const int* meta;
     int n_items, n_bal, coef_words;
+    const uint4* lt_coef;
+    const int2* lt_meta;
+    const int* lt_ng;
+    int n_wtasks;
     const int* kk32;
     const int* b32;
     const int* kk8;
@@ -580,6 +653,134 @@ __global__ void __launch_bounds__(kThreads) ke_phash_kernel(const PhashArgs a) {
     }
 }
 
+
+// Vertical taps of one chunk, in registers.  Output row yy of the 32x32 plane is owned by warp
+// (yy % 8) (lane = output column): the ~8 output rows whose tap range meets a 32-row chunk are
+// consecutive, so every warp has work in every chunk (a contiguous block of 4 rows per warp left 6
+// of 8 warps idle).  The 8x9 plane: warp = output row, lane = (column, row phase 0..2); the three
+// phases are summed with shuffles when the image is finished.
+template <int NW = kWarps>
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
+
+template <int NW>
+struct VertState {
+    static constexpr int Q = kOutH / NW;   // 32x32 plane rows owned by a warp: warp, warp+NW, ...
+    static constexpr int D = kDH / NW;     // 8x9 plane rows owned by a warp
+    int32_t acc[Q];
+    int32_t dacc[D];
+    int ymin[Q], ylen[Q], dmin[D], dlen[D];
+};
+
+template <int NW>
+__device__ __forceinline__ void vertical_init(const PhashArgs& a, VertState<NW>& v, int lane, int warp) {
+#pragma unroll
+    for (int q = 0; q < VertState<NW>::Q; ++q) {
+        v.ymin[q] = __ldg(a.b32 + 2 * (q * NW + warp));
+        v.ylen[q] = __ldg(a.b32 + 2 * (q * NW + warp) + 1);
+    }
+#pragma unroll
+    for (int d = 0; d < VertState<NW>::D; ++d) {
+        v.dmin[d] = __ldg(a.b8 + 2 * (d * NW + warp));
+        v.dlen[d] = __ldg(a.b8 + 2 * (d * NW + warp) + 1);
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void vertical_reset(VertState<NW>& v, int lane) {
+#pragma unroll
+    for (int q = 0; q < VertState<NW>::Q; ++q) v.acc[q] = 1 << (kPrec - 1);
+#pragma unroll
+    for (int d = 0; d < VertState<NW>::D; ++d) v.dacc[d] = (lane < kDW) ? (1 << (kPrec - 1)) : 0;  // rounding term once
+}
+
+template <int NW>
+__device__ __forceinline__ void vertical_chunk(const PhashArgs& a, VertState<NW>& v, const uint8_t* s_hrow, int r0,
+                                               int rows, int lane, int warp) {
+#pragma unroll
+    for (int q = 0; q < VertState<NW>::Q; ++q) {
+        const int lo = max(v.ymin[q], r0), hi = min(v.ymin[q] + v.ylen[q], r0 + rows);
+        if (lo < hi) {
+            const int* kk = a.kk32 + (q * NW + warp) * a.ks32 - v.ymin[q];
+            const uint8_t* hp = s_hrow + lane - r0 * kOuts;
+            int32_t acc = v.acc[q];
+#pragma unroll 8
+            for (int y = lo; y < hi; ++y) acc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
+            v.acc[q] = acc;
+        }
+    }
+    if (lane < 3 * kDW) {
+        const int x = lane % kDW, ph = lane / kDW;
+#pragma unroll
+        for (int d = 0; d < VertState<NW>::D; ++d) {
+            const int lo = max(v.dmin[d], r0), hi = min(v.dmin[d] + v.dlen[d], r0 + rows);
+            const int* kk = a.kk8 + (d * NW + warp) * a.ks8 - v.dmin[d];
+            const uint8_t* hp = s_hrow + kOutW + x - r0 * kOuts;
+            int32_t acc = v.dacc[d];
+#pragma unroll 4
+            for (int y = lo + ph; y < hi; y += 3) acc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
+            v.dacc[d] = acc;
+        }
+    }
+}
+
+// planes from the vertical accumulators (all compute threads call this)
+template <int NW>
+__device__ __forceinline__ void vertical_finish(VertState<NW>& v, uint8_t* s_x32, uint8_t* s_x98, int lane, int warp) {
+#pragma unroll
+    for (int q = 0; q < VertState<NW>::Q; ++q) s_x32[(q * NW + warp) * 32 + lane] = clip8(v.acc[q]);
+#pragma unroll
+    for (int d = 0; d < VertState<NW>::D; ++d) {
+        // lanes x, x+9, x+18 hold the three row phases of output (d*NW+warp, x)
+        const int32_t s0 = v.dacc[d];
+        const int32_t s1 = __shfl_sync(0xffffffffu, s0, (lane + kDW) & 31), s2 = __shfl_sync(0xffffffffu, s0, (lane + 2 * kDW) & 31);
+        if (lane < kDW) s_x98[(d * NW + warp) * kDW + lane] = clip8(s0 + s1 + s2);
+    }
+}
+
+// DCT low block + hash bits from s_x32 / s_x98 (all NW compute warps call this)
+template <int NW>
+__device__ __forceinline__ void dct_and_bits(const PhashArgs& a, long long im, const uint8_t* s_x32, const uint8_t* s_x98,
+                                             double* s_t, double* s_y, int tid, int lane, int warp) {
+    if (a.plane32)
+        for (int i = tid; i < 1024; i += NW * 32) a.plane32[im * 1024 + i] = s_x32[i];
+    if (a.plane98 && tid < kDW * kDH) a.plane98[im * 72 + tid] = s_x98[tid];
+    for (int idx = tid; idx < 256; idx += NW * 32) {
+        const int k = idx >> 5, x = idx & 31;
+        double s = 0.0;
+#pragma unroll 8
+        for (int nn = 0; nn < 32; ++nn) s = fma(c_dct[k * 32 + nn], (double)s_x32[nn * 32 + x], s);
+        s_t[k * 32 + x] = s;
+    }
+    compute_sync<NW>();
+    if (tid < 64) {
+        const int k = tid >> 3, l = tid & 7;
+        double s = 0.0;
+#pragma unroll 8
+        for (int nn = 0; nn < 32; ++nn) s = fma(s_t[k * 32 + nn], c_dct[l * 32 + nn], s);
+        s_y[tid] = s;
+    }
+    compute_sync<NW>();
+    if (warp == 0) {
+        const double y0 = s_y[lane], y1 = s_y[lane + 32];
+        double sum = (lane == 0 ? 0.0 : y0) + y1;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const double mean = sum / 63.0;
+        const uint32_t bhi = __ballot_sync(0xffffffffu, y0 > mean), blo = __ballot_sync(0xffffffffu, y1 > mean);
+        double mg = fmin(fabs(y0 - mean), fabs(y1 - mean));
+#pragma unroll
+        for (int off = 16; off; off >>= 1) mg = fmin(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+        const int r_a = lane >> 3, c_a = lane & 7;
+        const uint32_t dhi = __ballot_sync(0xffffffffu, s_x98[r_a * 9 + c_a + 1] > s_x98[r_a * 9 + c_a]);
+        const uint32_t dlo = __ballot_sync(0xffffffffu, s_x98[(r_a + 4) * 9 + c_a + 1] > s_x98[(r_a + 4) * 9 + c_a]);
+        if (lane == 0) {
+            a.phash[im] = ((uint64_t)__brev(bhi) << 32) | (uint64_t)__brev(blo);
+            a.dhash[im] = ((uint64_t)__brev(dhi) << 32) | (uint64_t)__brev(dlo);
+            if (a.min_margin) a.min_margin[im] = (float)mg;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the fast kernel
 //
 // Same arithmetic, restructured for the common geometry (contiguous rows, w*c % 16 == 0, a
@@ -595,7 +796,7 @@ constexpr int kMaxItems = 160;
 constexpr int kMaxSlots = 8;
 
 struct FastLayout {
-    int raw, coef, luma, acc, hrow, x32, x98, tmat, ymat, meta, items, bar, total;
+    int raw, coef, luma, acc, hrow, vacc, x32, x98, tmat, ymat, meta, items, bar, total;
 };
 
 __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes, int chunk_rows, int pitch_words,
@@ -613,6 +814,7 @@ __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes,
     L.luma = take(chunk_rows * pitch_words * 4, 16);
     L.acc = take(chunk_rows * kOuts * 4, 16);
     L.hrow = take(chunk_rows * kOuts, 16);
+    L.vacc = take((1024 + kDW * kDH) * 4, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
@@ -624,16 +826,15 @@ __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes,
     return L;
 }
 
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // luma of `rows` raw rows (row r at raw + r*row_bytes) -> luma rows (word pitch `pitch_words`).
 // warp -> rows, lanes -> 4-pixel groups: conflict-free LDS.32 x3 / STS.32 x1, no divisions.
-template <int C>
+template <int C, int NW = kWarps>
 __device__ __forceinline__ void luma_rows_fast(const uint8_t* __restrict__ raw, uint32_t* __restrict__ luma, int rows,
                                                int w, int pitch_words, int warp, int lane) {
     constexpr uint32_t LO = 0x002F468Bu, HI = 0x001D964Cu;
     const int wq = w >> 2;
-    for (int r = warp; r < rows; r += kWarps) {
+    for (int r = warp; r < rows; r += NW) {
         uint32_t* dst = luma + r * pitch_words;
         if (C == 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)r * w);
@@ -680,6 +881,7 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
     uint32_t* s_luma = reinterpret_cast<uint32_t*>(smem + L.luma);
     uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
     uint8_t* s_hrow = smem + L.hrow;
+    int32_t* s_vacc = reinterpret_cast<int32_t*>(smem + L.vacc);
     uint8_t* s_x32 = smem + L.x32;
     uint8_t* s_x98 = smem + L.x98;
     double* s_t = reinterpret_cast<double*>(smem + L.tmat);
@@ -731,11 +933,10 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
 
     // ===== compute warps =====
     uint32_t seq = 0;
-    const int vx = tid & 31, vg = tid >> 5;
+    VertState<kWarps> vs;
+    vertical_init(a, vs, lane, warp);
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-        int32_t vacc[4], dacc = 1 << (kPrec - 1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) vacc[q] = 1 << (kPrec - 1);
+        vertical_reset(vs, lane);
 
         for (int r0 = 0; r0 < a.h; r0 += CR) {
             const int rows = min(CR, a.h - r0);
@@ -788,73 +989,13 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
             compute_sync();
 
             // ---- vertical taps, streamed into registers
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int yy = vg * 4 + q;
-                const int ymin = __ldg(a.b32 + 2 * yy), ylen = __ldg(a.b32 + 2 * yy + 1);
-                const int lo = max(ymin, r0), hi = min(ymin + ylen, r0 + rows);
-                const int* kk = a.kk32 + yy * a.ks32 - ymin;
-                const uint8_t* hp = s_hrow + vx - r0 * kOuts;
-                int32_t acc = vacc[q];
-#pragma unroll 4
-                for (int y = lo; y < hi; ++y) acc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
-                vacc[q] = acc;
-            }
-            if (tid < kDW * kDH) {
-                const int yy = tid / kDW, x = tid - yy * kDW;
-                const int ymin = __ldg(a.b8 + 2 * yy), ylen = __ldg(a.b8 + 2 * yy + 1);
-                const int lo = max(ymin, r0), hi = min(ymin + ylen, r0 + rows);
-                const int* kk = a.kk8 + yy * a.ks8 - ymin;
-                const uint8_t* hp = s_hrow + kOutW + x - r0 * kOuts;
-#pragma unroll 4
-                for (int y = lo; y < hi; ++y) dacc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
-            }
+            vertical_chunk(a, vs, s_hrow, r0, rows, lane, warp);
         }
 
         // ---- planes, DCT, hash bits (identical to the generic kernel)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s_x32[(vg * 4 + q) * 32 + vx] = clip8(vacc[q]);
-        if (tid < kDW * kDH) s_x98[tid] = clip8(dacc);
+        vertical_finish(vs, s_x32, s_x98, lane, warp);
         compute_sync();
-        if (a.plane32)
-            for (int i = tid; i < 1024; i += kThreads) a.plane32[im * 1024 + i] = s_x32[i];
-        if (a.plane98 && tid < kDW * kDH) a.plane98[im * 72 + tid] = s_x98[tid];
-        {
-            const int k = tid >> 5, x = tid & 31;
-            double s = 0.0;
-#pragma unroll 8
-            for (int nn = 0; nn < 32; ++nn) s = fma(c_dct[k * 32 + nn], (double)s_x32[nn * 32 + x], s);
-            s_t[k * 32 + x] = s;
-        }
-        compute_sync();
-        if (tid < 64) {
-            const int k = tid >> 3, l = tid & 7;
-            double s = 0.0;
-#pragma unroll 8
-            for (int nn = 0; nn < 32; ++nn) s = fma(s_t[k * 32 + nn], c_dct[l * 32 + nn], s);
-            s_y[tid] = s;
-        }
-        compute_sync();
-        if (warp == 0) {
-            const double y0 = s_y[lane], y1 = s_y[lane + 32];
-            double sum = (lane == 0 ? 0.0 : y0) + y1;
-#pragma unroll
-            for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            const double mean = sum / 63.0;
-            const uint32_t bhi = __ballot_sync(0xffffffffu, y0 > mean), blo = __ballot_sync(0xffffffffu, y1 > mean);
-            double mg = fmin(fabs(y0 - mean), fabs(y1 - mean));
-#pragma unroll
-            for (int off = 16; off; off >>= 1) mg = fmin(mg, __shfl_xor_sync(0xffffffffu, mg, off));
-            const int r_a = lane >> 3, c_a = lane & 7;
-            const uint32_t dhi = __ballot_sync(0xffffffffu, s_x98[r_a * 9 + c_a + 1] > s_x98[r_a * 9 + c_a]);
-            const uint32_t dlo =
-                __ballot_sync(0xffffffffu, s_x98[(r_a + 4) * 9 + c_a + 1] > s_x98[(r_a + 4) * 9 + c_a]);
-            if (lane == 0) {
-                a.phash[im] = ((uint64_t)__brev(bhi) << 32) | (uint64_t)__brev(blo);
-                a.dhash[im] = ((uint64_t)__brev(dhi) << 32) | (uint64_t)__brev(dlo);
-                if (a.min_margin) a.min_margin[im] = (float)mg;
-            }
-        }
+        dct_and_bits<kWarps>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
         // s_x32 / s_x98 / s_y are rewritten only after the next image's chunk barriers
     }
 }
@@ -912,6 +1053,227 @@ int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, c
     return KE_OK;
 }
 
+
+// ------------------------------------------------------------------ lanes = outputs kernel (v3)
+//
+// Horizontal taps with the tap words in REGISTERS: lane = (output, segment of <= 8 sixteen-pixel
+// groups), warps walk rows.  Per row and pass of P <= 4 groups a lane issues P LDS.128 of pixels
+// (consecutive lanes read consecutive 16-byte groups: conflict free) and 12*P dp4a; no tap word
+// ever crosses shared memory, which was the limiter of the lanes=rows layout.  Everything else
+// (TMA ring, luma, clip, streamed vertical taps, DCT, bits) is shared with the fast kernel.
+
+struct V3Layout {
+    int raw, luma, acc, hrow, vacc, x32, x98, tmat, ymat, bar, total;
+};
+
+__host__ __device__ inline V3Layout v3_layout(int sub_bytes, int pitch_bytes, int n_slots) {
+    V3Layout L;
+    int off = 0;
+    auto take = [&](int bytes, int align) {
+        off = (off + align - 1) / align * align;
+        int at = off;
+        off += bytes;
+        return at;
+    };
+    L.raw = take(n_slots * sub_bytes, 128);
+    L.luma = take(32 * pitch_bytes + 8 * 16 + 64, 128);  // + slack: padded groups may run past the last row
+    L.acc = take(32 * kOuts * 4, 16);
+    L.hrow = take(32 * kOuts, 16);
+    L.vacc = take((1024 + kDW * kDH) * 4, 16);
+    L.x32 = take(1024, 16);
+    L.x98 = take(80, 16);
+    L.tmat = take(8 * 32 * 8, 16);
+    L.ymat = take(64 * 8, 16);
+    L.bar = take(2 * kMaxSlots * 8, 8);
+    L.total = off;
+    return L;
+}
+
+template <int P>
+__device__ __forceinline__ void v3_pass(const PhashArgs& a, int task, int g, int2 lm, int lane, const uint8_t* s_luma,
+                                        int pitch_bytes, uint32_t* s_acc, int row_lo, int row_hi) {
+    uint4 c[P][3];
+#pragma unroll
+    for (int gg = 0; gg < P; ++gg)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) c[gg][p] = __ldg(a.lt_coef + ((size_t)(task * 8 + g + gg) * 3 + p) * 32 + lane);
+    const uint8_t* px = s_luma + (size_t)(lm.y + g) * 16;
+    // two rows per iteration: 12 independent dp4a chains hide the accumulate latency
+    for (int r = row_lo; r < row_hi; r += 2) {
+        const bool two = r + 1 < row_hi;
+        const uint8_t* p0 = px + (size_t)r * pitch_bytes;
+        const uint8_t* p1 = two ? p0 + pitch_bytes : p0;
+        uint32_t d0 = 0u, d1 = 0u, e0 = 0u, e1 = 0u, f0 = 0u, f1 = 0u, h0 = 0u, h1 = 0u;
+        int32_t d2 = 0, e2 = 0, f2 = 0, h2 = 0;
+#pragma unroll
+        for (int gg = 0; gg < P; ++gg) {
+            const uint4 x = *reinterpret_cast<const uint4*>(p0 + gg * 16);
+            const uint4 y = *reinterpret_cast<const uint4*>(p1 + gg * 16);
+            d0 = dp4a_uu(x.x, c[gg][0].x, d0), d1 = dp4a_uu(x.x, c[gg][1].x, d1), d2 = dp4a_us(x.x, c[gg][2].x, d2);
+            f0 = dp4a_uu(y.x, c[gg][0].x, f0), f1 = dp4a_uu(y.x, c[gg][1].x, f1), f2 = dp4a_us(y.x, c[gg][2].x, f2);
+            e0 = dp4a_uu(x.y, c[gg][0].y, e0), e1 = dp4a_uu(x.y, c[gg][1].y, e1), e2 = dp4a_us(x.y, c[gg][2].y, e2);
+            h0 = dp4a_uu(y.y, c[gg][0].y, h0), h1 = dp4a_uu(y.y, c[gg][1].y, h1), h2 = dp4a_us(y.y, c[gg][2].y, h2);
+            d0 = dp4a_uu(x.z, c[gg][0].z, d0), d1 = dp4a_uu(x.z, c[gg][1].z, d1), d2 = dp4a_us(x.z, c[gg][2].z, d2);
+            f0 = dp4a_uu(y.z, c[gg][0].z, f0), f1 = dp4a_uu(y.z, c[gg][1].z, f1), f2 = dp4a_us(y.z, c[gg][2].z, f2);
+            e0 = dp4a_uu(x.w, c[gg][0].w, e0), e1 = dp4a_uu(x.w, c[gg][1].w, e1), e2 = dp4a_us(x.w, c[gg][2].w, e2);
+            h0 = dp4a_uu(y.w, c[gg][0].w, h0), h1 = dp4a_uu(y.w, c[gg][1].w, h1), h2 = dp4a_us(y.w, c[gg][2].w, h2);
+        }
+        if (lm.x >= 0) {
+            atomicAdd(&s_acc[r * kOuts + lm.x], (d0 + e0) + ((d1 + e1) << 8) + ((uint32_t)(d2 + e2) << 16));
+            if (two) atomicAdd(&s_acc[(r + 1) * kOuts + lm.x], (f0 + h0) + ((f1 + h1) << 8) + ((uint32_t)(f2 + h2) << 16));
+        }
+    }
+}
+
+template <int C, int NW>
+__global__ void __launch_bounds__(NW * 32 + 32, NW == 4 ? 4 : 2) ke_phash_v3_kernel(const PhashArgs a, const int sub_rows,
+                                                                     const int slot_shift, const int pitch_bytes,
+                                                                     const int dbg) {
+    constexpr int CR = 32;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int row_bytes = a.w * C;
+    const int sub_bytes = sub_rows * row_bytes;
+    const int n_slots = 1 << slot_shift;
+    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
+    const V3Layout L = v3_layout(sub_bytes, pitch_bytes, n_slots);
+    uint8_t* s_raw = smem + L.raw;
+    uint8_t* s_luma = smem + L.luma;
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
+    uint8_t* s_hrow = smem + L.hrow;
+    int32_t* s_vacc = reinterpret_cast<int32_t*>(smem + L.vacc);
+    uint8_t* s_x32 = smem + L.x32;
+    uint8_t* s_x98 = smem + L.x98;
+    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
+    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);
+    uint64_t* s_empty = s_full + kMaxSlots;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_sub = (a.h + sub_rows - 1) / sub_rows;
+    const int subs_per_chunk = CR / sub_rows;
+    const int pitch_words = pitch_bytes >> 2;
+
+    if (tid == 0) {
+        for (int b = 0; b < n_slots; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < CR * kOuts; i += NW * 32 + 32) s_acc[i] = 1u << (kPrec - 1);
+    for (int i = tid; i < (8 * 16 + 64) / 4; i += NW * 32 + 32)
+        reinterpret_cast<uint32_t*>(s_luma + 32 * pitch_bytes)[i] = 0u;
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+                const uint8_t* src = a.img + im * a.img_stride;
+                for (int s = 0; s < n_sub; ++s, ++seq) {
+                    const int b = seq & slot_mask;
+                    const int rows = min(sub_rows, a.h - s * sub_rows);
+                    mbar_wait_backoff(&s_empty[b], ((seq >> slot_shift) & 1u) ^ 1u);
+                    mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
+                    bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
+                             &s_full[b]);
+                }
+            }
+        }
+        return;
+    }
+
+    uint32_t seq = 0;
+    VertState<NW> vs;
+    vertical_init(a, vs, lane, warp);
+    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+        vertical_reset(vs, lane);
+
+        for (int r0 = 0; r0 < a.h; r0 += CR) {
+            const int rows = min(CR, a.h - r0);
+            for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
+                const int b = seq & slot_mask;
+                const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
+                mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
+                luma_rows_fast<C, NW>(s_raw + b * sub_bytes, reinterpret_cast<uint32_t*>(s_luma) + s * sub_rows * pitch_words,
+                                  srows, a.w, pitch_words, warp, lane);
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[b])) : "memory");
+            }
+            compute_sync<NW>();
+            if (dbg & 2) continue;  // tuning probe: loads + luma only
+
+            // ---- horizontal taps: item = (warp-task, 8-row group); tap words live in registers
+            for (int item = warp; item < ((dbg & 4) ? 0 : a.n_wtasks * 4); item += NW) {
+                const int task = item >> 2, rg = item & 3;
+                const int row_lo = rg * 8, row_hi = min(row_lo + 8, rows);
+                if (row_lo >= row_hi) continue;
+                const int2 lm = __ldg(a.lt_meta + task * 32 + lane);
+                const int ng = __ldg(a.lt_ng + task);
+                for (int g = 0; g < ng; g += 4) {
+                    switch (min(4, ng - g)) {
+                        case 4: v3_pass<4>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                        case 3: v3_pass<3>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                        case 2: v3_pass<2>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                        default: v3_pass<1>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                    }
+                }
+            }
+            compute_sync<NW>();
+            if (dbg & 8) continue;  // tuning probe: no clip / vertical taps
+
+            for (int i = tid; i < rows * kOuts; i += NW * 32) {
+                s_hrow[i] = clip8((int32_t)s_acc[i]);
+                s_acc[i] = 1u << (kPrec - 1);
+            }
+            compute_sync<NW>();
+            if (dbg & 16) continue;  // tuning probe: no vertical taps
+
+            vertical_chunk(a, vs, s_hrow, r0, rows, lane, warp);
+        }
+        if (dbg & 32) continue;  // tuning probe: no DCT / bits
+
+        vertical_finish(vs, s_x32, s_x98, lane, warp);
+        compute_sync<NW>();
+        dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
+    }
+}
+
+template <int C>
+bool v3_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V3Layout& L) {
+    const long long row_bytes = (long long)a.w * C;
+    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.n_wtasks < 1) return false;
+    pitch_bytes = a.w;  // rows 16-byte aligned; a warp reads one row at a time, so no padding is needed
+    for (int sub : {8, 4, 2, 1}) {
+        if (sub * row_bytes > (1 << 20)) continue;
+        L = v3_layout((int)(sub * row_bytes), pitch_bytes, 2);
+        if (L.total <= 100 * 1024) {
+            sub_rows = sub;
+            slot_shift = 1;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int C, int NW>
+int launch_v3(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, const V3Layout& L,
+              cudaStream_t s) {
+    constexpr int kBlock = NW * 32 + 32;
+    KE_CUDA(cudaFuncSetAttribute(ke_phash_v3_kernel<C, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_v3_kernel<C, NW>, kBlock, L.total));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.n) grid = a.n;
+    const char* dbg_env = getenv("KE_PHASH_DBG");
+    ke_phash_v3_kernel<C, NW><<<(unsigned)grid, kBlock, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes,
+                                                                        dbg_env ? atoi(dbg_env) : 0);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 int g_dct_uploaded_device = -1;
 
 int ensure_dct(ke_ctx* ctx) {
@@ -931,6 +1293,16 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
+    const char* which = getenv("KE_PHASH_KERNEL");  // tuning override: "v3" (default) | "fast"
+    if (!ctx->force_generic_phash && !(which && !strcmp(which, "fast"))) {
+        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
+        V3Layout VL;
+        if (v3_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL)) {
+            const char* nw = getenv("KE_PHASH_NW");  // tuning override: compute warps per CTA (4 | 8)
+            if (nw && atoi(nw) == 4) return launch_v3<C, 4>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
+            return launch_v3<C, 8>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);  // measured: 8x2 CTAs > 4x4 CTAs
+        }
+    }
     {
         int rpl = 0, sub_rows = 0, slot_shift = 1;
         FastLayout FL;
@@ -999,6 +1371,10 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     a.items = ht->d_items;
     a.bal = ht->d_bal;
     a.n_bal = ht->n_bal;
+    a.lt_coef = ht->d_lt_coef;
+    a.lt_meta = ht->d_lt_meta;
+    a.lt_ng = ht->d_lt_ng;
+    a.n_wtasks = ht->n_wtasks;
     a.meta = ht->d_meta;
     a.n_items = ht->n_items;
     a.coef_words = ht->coef_words;
