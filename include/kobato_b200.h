@@ -46,6 +46,9 @@ int ke_ctx_device(const ke_ctx* ctx);
 /* Tuning / test knobs.  KE_OPT_PHASH_GENERIC=1 routes every image geometry through K1's generic
  * kernel (the one used for unaligned or very wide rows) instead of the fast one. */
 #define KE_OPT_PHASH_GENERIC 1
+/* KE_OPT_JOIN_MODE: 0 auto (hybrid for large tables with threshold <= 15), 1 POPC kernel only,
+ * 2 hybrid (POPC kernel + bit-sliced LOP3 kernel running concurrently), 3 bit-sliced kernel only. */
+#define KE_OPT_JOIN_MODE 2
 int ke_ctx_set_option(ke_ctx* ctx, int option, int value);
 int ke_ctx_sm_count(const ke_ctx* ctx);
 

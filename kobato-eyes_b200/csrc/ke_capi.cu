@@ -40,6 +40,7 @@ extern "C" int ke_ctx_create(int device, ke_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     for (auto& s : ctx->copy_stream) KE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    KE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) KE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     *out = ctx;
     return KE_OK;
@@ -54,6 +55,7 @@ extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
     for (auto p : ctx->h_pinned) cudaFreeHost(p);
     for (auto s : ctx->copy_stream)
         if (s) cudaStreamDestroy(s);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     for (auto ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     delete ctx;
@@ -63,6 +65,10 @@ extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
     KE_REQUIRE(ctx != nullptr, "ke_ctx_set_option: ctx is NULL");
     switch (option) {
         case KE_OPT_PHASH_GENERIC: ctx->force_generic_phash = value ? 1 : 0; return KE_OK;
+        case KE_OPT_JOIN_MODE:
+            KE_REQUIRE(value >= 0 && value <= 3, "ke_ctx_set_option: join mode must be 0..3");
+            ctx->join_mode = value;
+            return KE_OK;
     }
     ke_set_error("ke_ctx_set_option: unknown option %d", option);
     return KE_E_INVALID;

@@ -39,14 +39,16 @@ struct ke_ctx {
     int sm_count = 0;
     int64_t launches = 0;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream = nullptr;  // second lane for kernels that run concurrently (hybrid join)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // growable device / pinned scratch owned by the context
-    void* d_scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t d_scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* d_scratch[12] = {};
+    size_t d_scratch_bytes[12] = {};
     void* h_pinned[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_pinned_bytes[4] = {0, 0, 0, 0};
     KeTableCache* tables = nullptr;
-    int force_generic_phash = 0;  // KE_OPT_PHASH_GENERIC: route every geometry through the generic K1 kernel
+    int force_generic_phash = 0;
+    int join_mode = 0;  // KE_OPT_JOIN_MODE: 0 auto, 1 POPC kernel only, 2 hybrid (POPC + bit-sliced), 3 bit-sliced only  // KE_OPT_PHASH_GENERIC: route every geometry through the generic K1 kernel
 };
 
 int ke_ctx_scratch(ke_ctx* ctx, int slot, size_t bytes, void** out);

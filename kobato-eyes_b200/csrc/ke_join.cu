@@ -18,6 +18,9 @@
 //     slow path, which re-evaluates those pairs with bounds, i<j, the optional band predicate,
 //     and appends (i, j, d) through one global atomic per hit.
 //   * Bounding pipe: POPC (2 per pair).  Algorithmic work per pair = 6 integer instructions.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ke_common.cuh"
 
 namespace {
@@ -42,6 +45,8 @@ struct JoinArgs {
     uint8_t* out_d;
     long long capacity;
     unsigned long long* count;
+    unsigned long long* queue;   // nullable: dynamic tile queue shared by concurrently running kernels
+    const uint32_t* sliced;      // hybrid: bit-sliced copy of the table, [ceil(n/32)][64] words
 };
 
 __device__ __forceinline__ void tile_coords(long long t, long long nt, long long& r, long long& c) {
@@ -90,20 +95,32 @@ __device__ __noinline__ void emit_hits(const JoinArgs& a, const uint64_t* rows, 
     }
 }
 
-template <int RPT>
-__global__ void __launch_bounds__(kThreads) ke_join_kernel(const JoinArgs a) {
+// bar.sync on a named barrier: lets two roles inside one CTA synchronise independently
+template <int ID, int N>
+__device__ __forceinline__ void role_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory");
+}
+
+template <int RPT, int BAR>
+__device__ __forceinline__ void popc_role(const JoinArgs& a, uint64_t* cols, long long* s_next_p) {
     constexpr int TILE = kThreads * RPT;
-    __shared__ __align__(16) uint64_t cols[TILE];
     const int neg_t1 = -(a.threshold + 1);
+    long long& s_next = *s_next_p;
 
     for (long long local = blockIdx.x;; local += gridDim.x) {
+        role_sync<BAR, kThreads>();  // previous tile's readers are done with cols[] (and with s_next)
+        if (a.queue) {
+            if (threadIdx.x == 0) s_next = (long long)atomicAdd(a.queue, 1ull);
+            role_sync<BAR, kThreads>();
+            local = s_next;
+        }
         const long long t = local * a.part_count + a.part_index;
         if (t >= a.tile_total) break;
+        if (a.queue && threadIdx.x == 0) atomicAdd(a.queue + 1, 1ull);
         long long tr, tc;
         tile_coords(t, a.tiles_per_dim, tr, tc);
         const long long row0 = tr * TILE, col0 = tc * TILE;
 
-        __syncthreads();  // previous tile's readers are done with cols[]
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const long long j = col0 + threadIdx.x + (long long)k * kThreads;
@@ -118,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) ke_join_kernel(const JoinArgs a) {
             al[k] = (uint32_t)rows[k];
             ah[k] = (uint32_t)(rows[k] >> 32);
         }
-        __syncthreads();
+        role_sync<BAR, kThreads>();
 
         const long long col_valid = a.n - col0 < TILE ? a.n - col0 : TILE;
         const int jend = (int)((col_valid + kColBatch - 1) / kColBatch) * kColBatch;
@@ -139,6 +156,181 @@ __global__ void __launch_bounds__(kThreads) ke_join_kernel(const JoinArgs a) {
     }
 }
 
+
+template <int RPT>
+__global__ void __launch_bounds__(kThreads) ke_join_kernel(const JoinArgs a) {
+    __shared__ __align__(16) uint64_t cols[kThreads * RPT];
+    __shared__ long long s_next;
+    popc_role<RPT, 0>(a, cols, &s_next);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bit-sliced partner kernel (hybrid mode).  The POPC kernel saturates the XU pipe (16 POPC
+// lanes/clk/SM) and leaves most of the ALU pipe idle; this kernel computes the same distances
+// with LOP3 only, so the two run CONCURRENTLY on every SM and pull tiles from one queue.
+//
+// The table is also kept bit-sliced: for every block of 32 hashes, word k holds bit k of the 32
+// hashes.  A thread owns one row hash a and its 64 masks M_k = -(bit k of a); for a block of 32
+// columns, x_k = W_k ^ M_k has bit j set iff column j differs from a in bit k, so the per-column
+// distance is the bitwise population count over the 64 words x_k.  A Harley-Seal carry-save tree
+// (60 CSAs = 120 LOP3) reduces them to ones/twos/fours/eights planes plus four "sixteen" planes;
+// for a threshold <= 15 a column hits iff no sixteen plane is set and the 4-bit value <= T.
+// ~200 LOP3 per 32 pairs and lane = 6.3 ALU instructions per pair, no POPC at all.
+
+constexpr int kBThreads = 128;
+constexpr int kBTile = 2048;  // must equal the POPC kernel's tile (RPT = 8)
+
+__global__ void __launch_bounds__(256) ke_bitslice_kernel(const uint64_t* __restrict__ hashes, long long n,
+                                                          uint32_t* __restrict__ sliced) {
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nblk = (n + 31) / 32;
+    if (warp_global >= nblk) return;
+    const long long i = warp_global * 32 + lane;
+    const uint64_t h = i < n ? hashes[i] : 0ull;
+    uint32_t mine_lo = 0, mine_hi = 0;  // lane k keeps words k and k+32
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t wlo = __ballot_sync(0xffffffffu, (h >> k) & 1ull);
+        const uint32_t whi = __ballot_sync(0xffffffffu, (h >> (k + 32)) & 1ull);
+        if (lane == k) mine_lo = wlo, mine_hi = whi;
+    }
+    sliced[warp_global * 64 + lane] = mine_lo;
+    sliced[warp_global * 64 + 32 + lane] = mine_hi;
+}
+
+__device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+__device__ __noinline__ void emit_sliced_hits(const JoinArgs& a, uint64_t row, long long i, long long colbase, uint32_t hits) {
+    while (hits) {
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const long long col = colbase + j;
+        if (i >= a.n || col >= a.n || col <= i) continue;
+        const uint64_t x = row ^ __ldg(a.hashes + col);
+        const int d = __popcll(x);
+        if (d > a.threshold) continue;
+        if (a.flags & KE_JOIN_REQUIRE_BAND) {
+            const uint64_t allow = a.band_allow ? (a.band_allow[i] & a.band_allow[col]) : ~0ull;
+            if (!band_match(x, a, allow)) continue;
+        }
+        const unsigned long long slot = atomicAdd(a.count, 1ull);
+        if ((long long)slot < a.capacity) {
+            a.out_i[slot] = (uint32_t)i;
+            a.out_j[slot] = (uint32_t)col;
+            a.out_d[slot] = (uint8_t)d;
+        }
+    }
+}
+
+template <int BAR>
+__device__ __forceinline__ void sliced_role(const JoinArgs& a, uint32_t* cols, long long* s_next_p, const int tid) {
+    long long& s_next = *s_next_p;
+    const long long nblk_total = (a.n + 31) / 32;
+    // 4-bit compare planes for the uniform threshold
+    uint32_t tb[4], ntb[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        tb[b] = ((a.threshold >> b) & 1) ? 0xFFFFFFFFu : 0u;
+        ntb[b] = ~tb[b];
+    }
+
+    for (long long local = blockIdx.x;; local += gridDim.x) {
+        role_sync<BAR, kBThreads>();
+        if (a.queue) {
+            if (tid == 0) s_next = (long long)atomicAdd(a.queue, 1ull);
+            role_sync<BAR, kBThreads>();
+            local = s_next;
+        }
+        const long long t = local * a.part_count + a.part_index;
+        if (t >= a.tile_total) break;
+        if (a.queue && tid == 0) atomicAdd(a.queue + 2, 1ull);
+        long long tr, tc;
+        tile_coords(t, a.tiles_per_dim, tr, tc);
+        const long long row0 = tr * kBTile, col0 = tc * kBTile;
+        const long long blk0 = col0 / 32;
+        const int nblk = (int)min((long long)(kBTile / 32), nblk_total - blk0);
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(a.sliced + blk0 * 64);
+            uint4* dst = reinterpret_cast<uint4*>(cols);
+            for (int q = tid; q < nblk * 16; q += kBThreads) dst[q] = __ldg(src + q);
+        }
+        role_sync<BAR, kBThreads>();
+
+        for (int pass = 0; pass < kBTile / kBThreads; ++pass) {
+            const long long i = row0 + (long long)pass * kBThreads + tid;
+            if (row0 + (long long)pass * kBThreads >= a.n) break;
+            const uint64_t row = i < a.n ? __ldg(a.hashes + i) : 0ull;
+            const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+            uint32_t M[64];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                M[k] = (uint32_t)((int32_t)(rlo << (31 - k)) >> 31);
+                M[k + 32] = (uint32_t)((int32_t)(rhi << (31 - k)) >> 31);
+            }
+#pragma unroll 1
+            for (int blk = 0; blk < nblk; ++blk) {
+                const uint4* w4 = reinterpret_cast<const uint4*>(cols + blk * 64);
+                uint32_t ones = 0, twos = 0, fours = 0, eights = 0, big = 0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {  // 16 inputs per round
+                    const uint4 wa = w4[g * 4], wb = w4[g * 4 + 1], wc = w4[g * 4 + 2], wd = w4[g * 4 + 3];
+                    const int k = g * 16;
+                    uint32_t twosA, twosB, foursA, foursB, eightsA, eightsB, sixteen;
+                    csa(twosA, ones, ones, wa.x ^ M[k + 0], wa.y ^ M[k + 1]);
+                    csa(twosB, ones, ones, wa.z ^ M[k + 2], wa.w ^ M[k + 3]);
+                    csa(foursA, twos, twos, twosA, twosB);
+                    csa(twosA, ones, ones, wb.x ^ M[k + 4], wb.y ^ M[k + 5]);
+                    csa(twosB, ones, ones, wb.z ^ M[k + 6], wb.w ^ M[k + 7]);
+                    csa(foursB, twos, twos, twosA, twosB);
+                    csa(eightsA, fours, fours, foursA, foursB);
+                    csa(twosA, ones, ones, wc.x ^ M[k + 8], wc.y ^ M[k + 9]);
+                    csa(twosB, ones, ones, wc.z ^ M[k + 10], wc.w ^ M[k + 11]);
+                    csa(foursA, twos, twos, twosA, twosB);
+                    csa(twosA, ones, ones, wd.x ^ M[k + 12], wd.y ^ M[k + 13]);
+                    csa(twosB, ones, ones, wd.z ^ M[k + 14], wd.w ^ M[k + 15]);
+                    csa(foursB, twos, twos, twosA, twosB);
+                    csa(eightsB, fours, fours, foursA, foursB);
+                    csa(sixteen, eights, eights, eightsA, eightsB);
+                    big |= sixteen;  // any weight-16 carry means distance >= 16 > T
+                }
+                // value = 8*eights + 4*fours + 2*twos + ones; hit iff !big && value <= T
+                const uint32_t v[4] = {ones, twos, fours, eights};
+                uint32_t gt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+                for (int b = 3; b >= 0; --b) {
+                    gt |= eq & v[b] & ntb[b];
+                    eq &= ~(v[b] ^ tb[b]);
+                }
+                const uint32_t hits = ~(gt | big);
+                if (hits) emit_sliced_hits(a, row, i, col0 + (long long)blk * 32, hits);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBThreads) ke_join_sliced_kernel(const JoinArgs a) {
+    __shared__ __align__(16) uint32_t cols[(kBTile / 32) * 64];  // 16 KB: 64 blocks x 64 words
+    __shared__ long long s_next;
+    sliced_role<0>(a, cols, &s_next, threadIdx.x);
+}
+
+// Fused hybrid: warps 0..7 run the POPC role, warps 8..11 the bit-sliced role, each with its own
+// column tile and named barrier, all pulling tiles from one queue.  Co-residency of the two
+// instruction mixes on every SM is then guaranteed by construction (two separate kernels on two
+// streams only co-run when the block scheduler happens to interleave them).
+__global__ void __launch_bounds__(kThreads + kBThreads, 2) ke_join_fused_kernel(const JoinArgs a) {
+    __shared__ __align__(16) uint64_t cols_p[kBTile];
+    __shared__ __align__(16) uint32_t cols_b[(kBTile / 32) * 64];
+    __shared__ long long s_next[2];
+    if (threadIdx.x < kThreads) popc_role<8, 1>(a, cols_p, &s_next[0]);
+    else sliced_role<2>(a, cols_b, &s_next[1], threadIdx.x - kThreads);
+}
+
 template <int RPT>
 int launch_join(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream) {
     constexpr int TILE = kThreads * RPT;
@@ -155,6 +347,43 @@ int launch_join(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream) {
     ke_join_kernel<RPT><<<(unsigned)grid, kThreads, 0, stream>>>(a);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
+
+// Hybrid launch: bit-slice the table, then the fused kernel (or the bit-sliced kernel alone) with a
+// dynamic tile queue.
+int launch_hybrid(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream, int mode) {
+    constexpr int TILE = kBTile;
+    a.tiles_per_dim = (a.n + TILE - 1) / TILE;
+    a.tile_total = a.tiles_per_dim * (a.tiles_per_dim + 1) / 2;
+    const long long nblk = (a.n + 31) / 32;
+    void *d_sliced = nullptr, *d_queue = nullptr;
+    int rc;
+    if ((rc = ke_ctx_scratch(ctx, 8, (size_t)nblk * 256 + 256, &d_sliced))) return rc;
+    if ((rc = ke_ctx_scratch(ctx, 9, 64, &d_queue))) return rc;
+    a.sliced = (const uint32_t*)d_sliced;
+    a.queue = (unsigned long long*)d_queue;
+    KE_CUDA(cudaMemsetAsync(d_queue, 0, 32, stream));
+    ke_bitslice_kernel<<<(unsigned)((nblk * 32 + 255) / 256), 256, 0, stream>>>(a.hashes, a.n, (uint32_t*)d_sliced);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    const long long mine = (a.tile_total - a.part_index + a.part_count - 1) / a.part_count;
+    if (mode == 3) {
+        long long grid = std::min<long long>((long long)ctx->sm_count * 4, mine);
+        ke_join_sliced_kernel<<<(unsigned)grid, kBThreads, 0, stream>>>(a);
+    } else {
+        long long grid = std::min<long long>((long long)ctx->sm_count * 2, mine);
+        ke_join_fused_kernel<<<(unsigned)grid, kThreads + kBThreads, 0, stream>>>(a);
+    }
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    if (getenv("KE_JOIN_DEBUG")) {  // tuning probe: how many tiles each kernel took
+        unsigned long long q[4] = {0, 0, 0, 0};
+        KE_CUDA(cudaStreamSynchronize(stream));
+        KE_CUDA(cudaMemcpy(q, d_queue, 32, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[ke_join] tiles=%lld popc=%llu sliced=%llu\n", a.tile_total, q[1], q[2]);
+    }
     return KE_OK;
 }
 
@@ -215,7 +444,12 @@ extern "C" int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n,
     a.out_d = d_out_dist;
     a.capacity = capacity;
     a.count = d_count;
-    switch (pick_rpt(ctx, n, part_count)) {
+    a.queue = nullptr;
+    a.sliced = nullptr;
+    const int rpt = pick_rpt(ctx, n, part_count);
+    const int mode = ctx->join_mode;
+    if (threshold <= 15 && mode != 1 && (mode >= 2 || rpt == 8)) return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode);
+    switch (rpt) {
         case 8: return launch_join<8>(ctx, a, s);
         case 4: return launch_join<4>(ctx, a, s);
         default: return launch_join<2>(ctx, a, s);

@@ -13,6 +13,7 @@ from pathlib import Path
 KE_OK, KE_E_INVALID, KE_E_CUDA, KE_E_CAPACITY, KE_E_NOMEM, KE_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 KE_JOIN_REQUIRE_BAND = 1
 KE_OPT_PHASH_GENERIC = 1
+KE_OPT_JOIN_MODE = 2
 
 _LIB_PATH = Path(__file__).resolve().parent / "libkobato_b200.so"
 _lib = None

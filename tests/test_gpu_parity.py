@@ -355,3 +355,33 @@ def test_phash_fast_and_generic_kernels_agree():
             ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
         assert torch.equal(fast[0], gen[0]) and torch.equal(fast[1], gen[1]) and torch.equal(fast[2], gen[2])
         assert torch.equal(fast[3][0], gen[3][0]) and torch.equal(fast[3][1], gen[3][1])
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_join_hybrid_and_bit_sliced_kernels_match_oracle(mode):
+    """K2 has a second, LOP3-only (bit-sliced carry-save) kernel that runs concurrently with the POPC
+    kernel on large tables (mode 2) or alone (mode 3); both must give the oracle's pair set."""
+    torch = _torch()
+    from kobato_b200 import _native as nat
+
+    ctx = nat.context(torch.cuda.current_device())
+    ctx.set_option(nat.KE_OPT_JOIN_MODE, mode)
+    try:
+        h = synth.synth_hashes(20011, seed=17, planted=0.25, max_flips=16)
+        for threshold, band in ((0, False), (5, True), (8, False), (15, True), (16, False)):
+            want = oracle.hamming_join(h, threshold, require_band=band, threads=8)
+            got = ops.hamming_join(torch.from_numpy(h.view(np.int64)).cuda(), threshold, require_band=band)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), (mode, threshold, band)
+        for n in (2, 31, 32, 33, 2047, 2049, 4097):
+            hh = synth.synth_hashes(n, seed=3, planted=0.3)
+            hh[-1] = hh[0]
+            for g, w in zip(ops.hamming_join(hh, 6), oracle.hamming_join(hh, 6)):
+                assert np.array_equal(g, w), (mode, n)
+        pieces = [ops.hamming_join(h, 8, part_index=p, part_count=3) for p in range(3)]
+        full = oracle.hamming_join(h, 8, threads=8)
+        i = np.concatenate([p[0] for p in pieces]); j = np.concatenate([p[1] for p in pieces])
+        order = np.lexsort((j, i))
+        assert np.array_equal(i[order], full[0]) and np.array_equal(j[order], full[1])
+    finally:
+        ctx.set_option(nat.KE_OPT_JOIN_MODE, 0)
