@@ -1,0 +1,42 @@
+"""Summarise an .ncu-rep (raw page) into a small CSV-ish text for profiles/.
+
+    python tools/ncu_summary.py <report.ncu-rep> > profiles/<name>.txt
+"""
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(txt.splitlines()))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+WANT = [
+    "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "gpu__time_duration.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__sass_inst_executed_op_tma_ld.sum",
+]
+WANT += [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
+for r in rows[2:]:
+    print("=" * 100)
+    for w in WANT:
+        if w in idx and r[idx[w]] not in ("", "0", "n/a"):
+            print(f"{w:88s} {r[idx[w]][:70]} {units[idx[w]]}")
+    # traffic per launch = dram read + write
+    try:
+        def gb(name):
+            v, u = float(r[idx[name]]), units[idx[name]]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
+        print(f"{'traffic_bytes (dram read + write)':88s} {gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum'):.0f}")
+    except Exception:
+        pass
