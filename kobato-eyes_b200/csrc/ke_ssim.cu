@@ -20,6 +20,8 @@
 // exchange at all.
 //
 // Algorithmic HBM bytes per pair: 2*h*w*c read + 8 written.
+#include <type_traits>
+
 #include "ke_common.cuh"
 
 namespace {
@@ -39,6 +41,7 @@ struct SsimArgs {
     int n_cblocks;
     int pitch;     // shared-memory row pitch in bytes (multiple of 4)
     int use_bulk;  // contiguous 'L' planes, one column block: bulk copies straight into the strip
+    int rgb_words; // RGB bank whose rows and images start on 4-byte boundaries: vectorised luma staging
     double inv_count;
     double* out;
 };
@@ -160,8 +163,34 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
                     bulk_g2s(dv, img_v + (long long)r0 * a.row_stride, bytes, &bars[buf]);
                 }
             } else {
-                for (int idx = tid; idx < rows * in_cols; idx += kThreads) {
-                    const int r = idx / in_cols, x = idx - r * in_cols;
+                int x_done = 0;
+                if (C == 3 && a.rgb_words) {
+                    // RGB rows whose start is word aligned: Pillow luma of 4 pixels from 3 coalesced words
+                    constexpr uint32_t LO = 0x002F468Bu, HI = 0x001D964Cu;  // 19595, 38470, 7471 split in bytes
+                    const int groups = in_cols >> 2;
+                    x_done = groups << 2;
+                    for (int idx = tid; idx < rows * groups; idx += kThreads) {
+                        const int r = idx / groups, q = idx - r * groups;
+                        const long long g = (long long)(r0 + r) * a.row_stride + (long long)col0 * 3 + (long long)q * 12;
+#pragma unroll
+                        for (int im = 0; im < 2; ++im) {
+                            const uint32_t* src = reinterpret_cast<const uint32_t*>((im ? img_v : img_u) + g);
+                            const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+                            const uint32_t l0 = dp4a_uu(w0, LO, 0x8000u), h0 = dp4a_uu(w0, HI, 0u);
+                            uint32_t l1 = dp4a_uu(w0, LO << 24, 0x8000u), h1 = dp4a_uu(w0, HI << 24, 0u);
+                            l1 = dp4a_uu(w1, LO >> 8, l1), h1 = dp4a_uu(w1, HI >> 8, h1);
+                            uint32_t l2 = dp4a_uu(w1, LO << 16, 0x8000u), h2 = dp4a_uu(w1, HI << 16, 0u);
+                            l2 = dp4a_uu(w2, LO >> 16, l2), h2 = dp4a_uu(w2, HI >> 16, h2);
+                            const uint32_t l3 = dp4a_uu(w2, LO << 8, 0x8000u), h3 = dp4a_uu(w2, HI << 8, 0u);
+                            const uint32_t s0 = l0 + (h0 << 8), s1 = l1 + (h1 << 8), s2 = l2 + (h2 << 8), s3 = l3 + (h3 << 8);
+                            const uint32_t packed = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+                            *reinterpret_cast<uint32_t*>((im ? dv : du) + r * a.pitch + 4 * q) = packed;
+                        }
+                    }
+                }
+                const int tail = in_cols - x_done;
+                for (int idx = tid; idx < rows * tail; idx += kThreads) {
+                    const int r = idx / tail, x = x_done + (idx - r * tail);
                     const long long g = (long long)(r0 + r) * a.row_stride + (long long)(col0 + x) * C;
                     du[r * a.pitch + x] = luma_of<C>(img_u + g);
                     dv[r * a.pitch + x] = luma_of<C>(img_v + g);
@@ -194,23 +223,30 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
             const int pw = a.pitch >> 2;
             float part = 0.f;
             if (active) {
-                for (int rb = 0; rb < rows; rb += kWin) {
+                // One 7-row group; STEADY = all 7 rows exist and the window is already full, so the
+                // loop body carries no predicates (the common case: every strip but the first/last).
+                auto group = [&](int rb, auto steady) {
+                    constexpr bool STEADY = decltype(steady)::value;
 #pragma unroll
                     for (int k = 0; k < kWin; ++k) {
                         const int r = rb + k;  // (r0 + r) % 7 == k because strips are multiples of 7
-                        if (r < rows) {
+                        if (STEADY || r < rows) {
                             // the slot of row (r0+r-7) is dead: build the new row's sums in place
                             ring[k] = hsum7(su + r * pw, sv + r * pw, sel);
                             acc_s += ring[k].s;
                             acc_t += ring[k].t;
                             acc_uv += ring[k].uv;
-                            if (r0 + r >= kWin - 1) part += ssim_point(acc_s, acc_t, acc_uv);
+                            if (STEADY || r0 + r >= kWin - 1) part += ssim_point(acc_s, acc_t, acc_uv);
                             // slot (k+1)%7 holds row (r0+r-6): it leaves the window
                             acc_s -= ring[(k + 1) % kWin].s;
                             acc_t -= ring[(k + 1) % kWin].t;
                             acc_uv -= ring[(k + 1) % kWin].uv;
                         }
                     }
+                };
+                for (int rb = 0; rb < rows; rb += kWin) {
+                    if (r0 + rb >= kWin && rb + kWin <= rows) group(rb, std::true_type{});
+                    else group(rb, std::false_type{});
                 }
             }
             total += (double)part;
@@ -280,6 +316,7 @@ extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, i
     a.n_cblocks = ((w - 6) + kBlockCols - 1) / kBlockCols;
     a.use_bulk = (c == 1 && a.n_cblocks == 1 && (w % 16) == 0 && row_stride == w && (img_stride % 16) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_bank) & 15) == 0);
+    a.rgb_words = (c == 3 && (row_stride % 4) == 0 && (img_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(d_bank) & 3) == 0);
     a.pitch = a.use_bulk ? w : ((std::min(w, kBlockCols + 6) + 3) / 4 * 4 + 4);
     a.inv_count = 1.0 / ((double)(h - 6) * (double)(w - 6));
     a.out = d_ssim;
