@@ -375,6 +375,9 @@ def main():
     ap.add_argument("--ref-unique", type=int, default=256, help="unique synthetic images behind the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # Only the JSON line may reach stdout (NCCL / libraries print banners there): park the real stdout.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "cuda":
         print(f"bench.py: warmup {args.warmup} < 3 — numbers from this run are not valid bench values", file=sys.stderr)
 
@@ -388,7 +391,8 @@ def main():
             raise SystemExit(subprocess.call(cmd))
         res = run_cuda(args)
     if res:
-        print(json.dumps(res), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(res) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -1274,6 +1274,212 @@ int launch_v3(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
     return KE_OK;
 }
 
+// ------------------------------------------------------------------ warp-specialised kernel (v4)
+//
+// The v3 kernel runs load+luma (HBM bound on its own: 5 TB/s) and the tap phases (dp4a bound)
+// one after the other; two CTAs per SM overlap them only by accident.  Here the roles are split
+// inside the CTA and decoupled through shared-memory rings:
+//     warp 10      TMA producer      raw rows  -> raw ring        (full/empty mbarriers)
+//     warps 8..9   luma warps        raw ring  -> luma chunk ring (2 x 32 rows)
+//     warps 0..7   tap warps         luma ring -> horizontal taps (v3 layout) -> clip -> vertical -> DCT
+// so the memory stream runs continuously behind the arithmetic.
+
+constexpr int kV4Tap = 8, kV4Luma = 2;
+constexpr int kV4Threads = (kV4Tap + kV4Luma + 1) * 32;
+
+struct V4Layout {
+    int raw, luma, acc, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
+};
+
+__host__ __device__ inline V4Layout v4_layout(int sub_bytes, int pitch_bytes, int n_slots) {
+    V4Layout L;
+    int off = 0;
+    auto take = [&](int bytes, int align) {
+        off = (off + align - 1) / align * align;
+        int at = off;
+        off += bytes;
+        return at;
+    };
+    L.luma_bytes = (32 * pitch_bytes + 8 * 16 + 64 + 127) / 128 * 128;  // one chunk + slack for padded groups
+    L.raw = take(n_slots * sub_bytes, 128);
+    L.luma = take(2 * L.luma_bytes, 128);
+    L.acc = take(32 * kOuts * 4, 16);
+    L.hrow = take(32 * kOuts, 16);
+    L.x32 = take(1024, 16);
+    L.x98 = take(80, 16);
+    L.tmat = take(8 * 32 * 8, 16);
+    L.ymat = take(64 * 8, 16);
+    L.bar = take((2 * kMaxSlots + 4) * 8, 8);
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kV4Threads, 2) ke_phash_v4_kernel(const PhashArgs a, const int sub_rows,
+                                                                   const int slot_shift, const int pitch_bytes) {
+    constexpr int CR = 32, NW = kV4Tap;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int row_bytes = a.w * C;
+    const int sub_bytes = sub_rows * row_bytes;
+    const int n_slots = 1 << slot_shift;
+    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
+    const V4Layout L = v4_layout(sub_bytes, pitch_bytes, n_slots);
+    uint8_t* s_raw = smem + L.raw;
+    uint8_t* s_luma = smem + L.luma;
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
+    uint8_t* s_hrow = smem + L.hrow;
+    uint8_t* s_x32 = smem + L.x32;
+    uint8_t* s_x98 = smem + L.x98;
+    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
+    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // raw ring
+    uint64_t* s_empty = s_full + kMaxSlots;
+    uint64_t* l_full = s_empty + kMaxSlots;  // luma chunk ring [2]
+    uint64_t* l_empty = l_full + 2;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_sub = (a.h + sub_rows - 1) / sub_rows;
+    const int subs_per_chunk = CR / sub_rows;
+    const int pitch_words = pitch_bytes >> 2;
+
+    if (tid == 0) {
+        for (int b = 0; b < n_slots; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], kV4Luma);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&l_full[b], kV4Luma);
+            mbar_init(&l_empty[b], kV4Tap);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < CR * kOuts; i += kV4Threads) s_acc[i] = 1u << (kPrec - 1);
+    for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV4Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
+    __syncthreads();
+
+    if (warp == kV4Tap + kV4Luma) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+                const uint8_t* src = a.img + im * a.img_stride;
+                for (int s = 0; s < n_sub; ++s, ++seq) {
+                    const int b = seq & slot_mask;
+                    const int rows = min(sub_rows, a.h - s * sub_rows);
+                    mbar_wait_backoff(&s_empty[b], ((seq >> slot_shift) & 1u) ^ 1u);
+                    mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
+                    bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
+                             &s_full[b]);
+                }
+            }
+        }
+        return;
+    }
+
+    if (warp >= kV4Tap) {
+        // ===== luma warps: raw ring -> luma chunk ring =====
+        const int lw = warp - kV4Tap;
+        uint32_t seq = 0, chunk = 0;
+        for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
+                const int lb = chunk & 1;
+                mbar_wait(&l_empty[lb], ((chunk >> 1) & 1u) ^ 1u);  // tap warps are done with this buffer
+                uint32_t* dst = reinterpret_cast<uint32_t*>(s_luma + lb * L.luma_bytes);
+                for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
+                    const int b = seq & slot_mask;
+                    const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
+                    mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
+                    luma_rows_fast<C, kV4Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
+                                               pitch_words, lw, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive1(&s_empty[b]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive1(&l_full[lb]);  // release: the chunk's luma rows are written
+            }
+        }
+        return;
+    }
+
+    // ===== tap warps =====
+    uint32_t chunk = 0;
+    VertState<NW> vs;
+    vertical_init(a, vs, lane, warp);
+    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+        vertical_reset(vs, lane);
+        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
+            const int rows = min(CR, a.h - r0);
+            const int lb = chunk & 1;
+            const uint8_t* luma = s_luma + lb * L.luma_bytes;
+            mbar_wait(&l_full[lb], (chunk >> 1) & 1u);
+            for (int item = warp; item < a.n_wtasks * 4; item += NW) {
+                const int task = item >> 2, rg = item & 3;
+                const int row_lo = rg * 8, row_hi = min(row_lo + 8, rows);
+                if (row_lo >= row_hi) continue;
+                const int2 lm = __ldg(a.lt_meta + task * 32 + lane);
+                const int ng = __ldg(a.lt_ng + task);
+                for (int g = 0; g < ng; g += 4) {
+                    switch (min(4, ng - g)) {
+                        case 4: v3_pass<4>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                        case 3: v3_pass<3>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                        case 2: v3_pass<2>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                        default: v3_pass<1>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
+            compute_sync<NW>();
+            for (int i = tid; i < rows * kOuts; i += NW * 32) {
+                s_hrow[i] = clip8((int32_t)s_acc[i]);
+                s_acc[i] = 1u << (kPrec - 1);
+            }
+            compute_sync<NW>();
+            vertical_chunk(a, vs, s_hrow, r0, rows, lane, warp);
+            // s_hrow / s_acc are next written after the next chunk's two tap barriers
+        }
+        vertical_finish(vs, s_x32, s_x98, lane, warp);
+        compute_sync<NW>();
+        dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
+    }
+}
+
+template <int C>
+bool v4_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V4Layout& L) {
+    const long long row_bytes = (long long)a.w * C;
+    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.n_wtasks < 1) return false;
+    pitch_bytes = a.w;
+    for (int sub : {8, 4, 2, 1}) {
+        if (sub * row_bytes > (1 << 20)) continue;
+        L = v4_layout((int)(sub * row_bytes), pitch_bytes, 2);
+        if (L.total <= 110 * 1024) {
+            sub_rows = sub;
+            slot_shift = 1;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int C>
+int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, const V4Layout& L,
+              cudaStream_t s) {
+    KE_CUDA(cudaFuncSetAttribute(ke_phash_v4_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_v4_kernel<C>, kV4Threads, L.total));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.n) grid = a.n;
+    ke_phash_v4_kernel<C><<<(unsigned)grid, kV4Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 int g_dct_uploaded_device = -1;
 
 int ensure_dct(ke_ctx* ctx) {
@@ -1293,7 +1499,15 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
-    const char* which = getenv("KE_PHASH_KERNEL");  // tuning override: "v3" (default) | "fast"
+    // "v3" (default) | "v4" (warp-specialised luma/tap roles: same speed on B200, kept as the base for the
+    // next round's pipelining work) | "fast" (lanes = rows)
+    const char* which = getenv("KE_PHASH_KERNEL");
+    if (!ctx->force_generic_phash && which && !strcmp(which, "v4")) {
+        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
+        V4Layout VL;
+        if (v4_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
+            return launch_v4<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
+    }
     if (!ctx->force_generic_phash && !(which && !strcmp(which, "fast"))) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
         V3Layout VL;

@@ -57,6 +57,25 @@ def all_gather_hashes(local):
     return torch.cat([p[:c] for p, c in zip(parts, counts)])
 
 
+def all_gather_varlen(local):
+    """Concatenate 1-D tensors of any dtype and per-rank length on every rank (padded all_gather)."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    if size == 1:
+        return local
+    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(size)]
+    dist.all_gather(counts, torch.tensor([local.numel()], dtype=torch.int64, device=local.device))
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros(cap, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    parts = [torch.empty(cap, dtype=local.dtype, device=local.device) for _ in range(size)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
 def broadcast_table(table, src: int = 0):
     """Rank `src` holds the table (int64 tensor); every rank returns its own copy."""
     import torch

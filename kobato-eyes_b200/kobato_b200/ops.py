@@ -167,6 +167,40 @@ def hamming_join(hashes, threshold: int, *, require_band: bool = False, band_bit
     return ii[order], jj[order], dd[order]
 
 
+def hamming_join_device(hashes, threshold: int, *, require_band: bool = False, band_bits: int = 16, band_count: int = 4,
+                        band_allow=None, part_index: int = 0, part_count: int = 1, capacity: int | None = None):
+    """Like ``hamming_join`` for a CUDA table, but the (unsorted) result stays on the device:
+    returns int32 ``i``, int32 ``j`` (bit patterns of the uint32 indices) and uint8 ``dist`` tensors."""
+    torch = _torch()
+    lib = nat.load()
+    if not (_is_tensor(hashes) and hashes.is_cuda and hashes.dtype in (torch.int64, torch.uint64)):
+        raise ValueError("hamming_join_device wants a CUDA int64/uint64 tensor")
+    h = hashes.contiguous().view(-1)
+    n = h.numel()
+    dev = h.device.index
+    ctx = nat.context(dev)
+    flags = nat.KE_JOIN_REQUIRE_BAND if require_band else 0
+    allow = None
+    if band_allow is not None:
+        allow = band_allow.contiguous() if _is_tensor(band_allow) else \
+            torch.from_numpy(np.ascontiguousarray(band_allow, np.uint64).view(np.int64)).to(h.device)
+    cap = int(capacity) if capacity is not None else max(1 << 16, 4 * n)
+    while True:
+        oi = torch.empty(cap, dtype=torch.int32, device=h.device)
+        oj = torch.empty(cap, dtype=torch.int32, device=h.device)
+        od = torch.empty(cap, dtype=torch.uint8, device=h.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=h.device)
+        with ctx.lock:
+            nat.check(lib.ke_hamming_join(ctx.handle, h.data_ptr(), n, int(threshold), flags, band_bits, band_count,
+                                          allow.data_ptr() if allow is not None else None, part_index, part_count,
+                                          oi.data_ptr(), oj.data_ptr(), od.data_ptr(), cap, cnt.data_ptr(),
+                                          _stream_ptr(dev)), "ke_hamming_join")
+        total = int(cnt.item())
+        if total <= cap:
+            return oi[:total], oj[:total], od[:total]
+        cap = total
+
+
 # ----------------------------------------------------------------------------- K3
 
 

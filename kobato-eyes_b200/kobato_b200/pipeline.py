@@ -44,25 +44,22 @@ def _torch():
 
 
 def _components(i, j, keep):
-    parent: dict[int, int] = {}
+    """Connected components of the accepted pairs -> sorted [(representative, [members])]
+    (the reference's ClusterBuilder semantics, src/dup/cluster.py:22-70)."""
+    a, b = i[keep], j[keep]
+    if a.size == 0:
+        return []
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
 
-    def find(x):
-        parent.setdefault(x, x)
-        r = x
-        while parent[r] != r:
-            r = parent[r]
-        while parent[x] != r:
-            parent[x], x = r, parent[x]
-        return r
-
-    for a, b in zip(i[keep].tolist(), j[keep].tolist()):
-        ra, rb = find(a), find(b)
-        if ra != rb:
-            parent[max(ra, rb)] = min(ra, rb)
-    comps: dict[int, list[int]] = {}
-    for x in parent:
-        comps.setdefault(find(x), []).append(x)
-    return sorted((min(m), sorted(m)) for m in comps.values())
+    nodes, inv = np.unique(np.concatenate([a, b]), return_inverse=True)
+    m = nodes.size
+    graph = coo_matrix((np.ones(a.size, np.int8), (inv[: a.size], inv[a.size:])), shape=(m, m))
+    _, labels = connected_components(graph, directed=False)
+    order = np.lexsort((nodes, labels))
+    cuts = np.flatnonzero(np.diff(labels[order])) + 1
+    groups = np.split(nodes[order], cuts)
+    return sorted((int(g[0]), g.tolist()) for g in groups)
 
 
 class Timer:
@@ -130,33 +127,30 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
     table = kdist.all_gather_hashes(ph)
     tm.mark("exchange")
     total = table.numel()
-    cap = max(1 << 16, 2 * total)
-    lib_i, lib_j, lib_d = ops.hamming_join(table, threshold, require_band=require_band, part_index=rank,
-                                           part_count=size, capacity=cap)
+    li, lj, ld = ops.hamming_join_device(table, threshold, require_band=require_band, part_index=rank,
+                                         part_count=size, capacity=max(1 << 16, 2 * total))
     tm.mark("join")
-    out.bytes_d2h += lib_i.nbytes + lib_j.nbytes + lib_d.nbytes
-    merged = kdist.gather_candidates(lib_i, lib_j, lib_d)
-    if size > 1:
-        box = [merged]
-        kdist._dist().broadcast_object_list(box, src=0)
-        merged = box[0]
-    ci, cj, cd = merged
+    # every rank gets every candidate (three small NCCL all_gathers), sorted by (i, j) on the device
+    gi, gj, gd = kdist.all_gather_varlen(li), kdist.all_gather_varlen(lj), kdist.all_gather_varlen(ld)
+    key = (gi.to(torch.int64) & 0xFFFFFFFF) << 32 | (gj.to(torch.int64) & 0xFFFFFFFF)
+    order = torch.argsort(key)
+    ci = (gi[order].to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    cj = (gj[order].to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    cd = gd[order].cpu().numpy()
+    out.bytes_d2h += 9 * len(ci)
     out.counts.update(images_local=int(n), images_total=int(total), candidates=int(len(ci)))
 
     # ---- K3 ---------------------------------------------------------------------------------
     n_loc = int(n_local if n_local is not None else n)
-    own_i = ci.astype(np.int64) // n_loc
-    own_j = cj.astype(np.int64) // n_loc
+    own_i = ci // n_loc
+    own_j = cj // n_loc
     mine = np.flatnonzero((own_i == rank) & (own_j == rank))
-    scores = np.full(len(ci), np.nan, np.float64)
+    scores_dev = torch.zeros(len(ci), dtype=torch.float64, device=dev)
     tm.mark("pre_ssim")
     if len(mine):
-        s = ops.ssim_batch(bank, ci[mine].astype(np.int64) - rank * n_loc, cj[mine].astype(np.int64) - rank * n_loc)
-        tm.mark("ssim")
-        scores[mine] = s.cpu().numpy()
-        out.bytes_d2h += 8 * len(mine)
-    else:
-        tm.mark("ssim")
+        s = ops.ssim_batch(bank, ci[mine] - rank * n_loc, cj[mine] - rank * n_loc)
+        scores_dev[torch.from_numpy(mine).to(dev)] = s
+    tm.mark("ssim")
     cross = np.flatnonzero(own_i != own_j)
     if size > 1 and len(cross):
         dist = kdist._dist()
@@ -170,16 +164,12 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
                 dist.send(bank[int(cj[q]) - b * n_loc].contiguous(), dst=a)
         sel = [k for k, q in enumerate(cross.tolist()) if int(own_i[q]) == rank]
         if sel:
-            s = ops.ssim_batch(tmp, [2 * k for k in sel], [2 * k + 1 for k in sel]).cpu().numpy()
-            scores[cross[sel]] = s
+            s = ops.ssim_batch(tmp, [2 * k for k in sel], [2 * k + 1 for k in sel])
+            scores_dev[torch.from_numpy(cross[sel]).to(dev)] = s
     if size > 1:
-        box = [None] * size if rank == 0 else None
-        kdist._dist().gather_object(scores, box, dst=0)
-        if rank == 0:
-            scores = np.full(len(ci), np.nan, np.float64)
-            for part in box:  # every pair was scored by exactly one rank
-                got = ~np.isnan(part)
-                scores[got] = part[got]
+        kdist._dist().all_reduce(scores_dev)  # every pair was scored by exactly one rank: SUM merges
+    scores = scores_dev.cpu().numpy()
+    out.bytes_d2h += 8 * len(ci)
     tm.mark("post")
 
     # ---- host assembly (rank 0) ---------------------------------------------------------------

@@ -344,17 +344,25 @@ def test_phash_fast_and_generic_kernels_agree():
     torch = _torch()
     from kobato_b200 import _native as nat
 
+    import os
+
     ctx = nat.context(torch.cuda.current_device())
-    for (h, w, c, n) in ((512, 512, 3, 300), (96, 160, 3, 40), (200, 64, 4, 20), (130, 256, 1, 20), (1100, 1024, 3, 6)):
+    for (h, w, c, n) in ((512, 512, 3, 300), (96, 160, 3, 40), (200, 64, 4, 20), (130, 256, 1, 20), (1100, 1024, 3, 6),
+                         (70, 100, 3, 9)):
         imgs = ops.synth_images_device(0, n, h, w, c, n_set=n)
-        fast = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
         ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
         try:
             gen = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
         finally:
             ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
-        assert torch.equal(fast[0], gen[0]) and torch.equal(fast[1], gen[1]) and torch.equal(fast[2], gen[2])
-        assert torch.equal(fast[3][0], gen[3][0]) and torch.equal(fast[3][1], gen[3][1])
+        for kernel in ("v3", "v4", "fast"):  # the library falls back by itself when a kernel does not take the shape
+            os.environ["KE_PHASH_KERNEL"] = kernel
+            try:
+                got = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
+            finally:
+                os.environ.pop("KE_PHASH_KERNEL", None)
+            assert torch.equal(got[0], gen[0]) and torch.equal(got[1], gen[1]) and torch.equal(got[2], gen[2]), kernel
+            assert torch.equal(got[3][0], gen[3][0]) and torch.equal(got[3][1], gen[3][1]), kernel
 
 
 @pytest.mark.parametrize("mode", [2, 3])
