@@ -232,7 +232,7 @@ def run_cuda(args) -> dict:
     k1_ms = stage["phash"] / args.steps  # live, inside the timed region: one launch per step
     k1_bytes = n * (IMG_BYTES + 16)
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
-    roof_k1 = {"kernel": "ke_phash_v3_kernel<3,8> (512x512x3)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roof_k1 = {"kernel": "ke_phash_v4_kernel<3> (512x512x3)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k1_gbs / hbm_peak,
                # dram read+write per launch: 789 698 B/image measured by `ncu --set full` on a 4096-image launch of
                # the same kernel (profiles/r1_ncu_full_summary.txt), scaled to this launch's image count

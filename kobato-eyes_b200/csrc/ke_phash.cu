@@ -796,7 +796,7 @@ constexpr int kMaxItems = 160;
 constexpr int kMaxSlots = 8;
 
 struct FastLayout {
-    int raw, coef, luma, acc, hrow, vacc, x32, x98, tmat, ymat, meta, items, bar, total;
+    int raw, coef, luma, acc, hrow, x32, x98, tmat, ymat, meta, items, bar, total;
 };
 
 __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes, int chunk_rows, int pitch_words,
@@ -814,7 +814,6 @@ __host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes,
     L.luma = take(chunk_rows * pitch_words * 4, 16);
     L.acc = take(chunk_rows * kOuts * 4, 16);
     L.hrow = take(chunk_rows * kOuts, 16);
-    L.vacc = take((1024 + kDW * kDH) * 4, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
@@ -841,7 +840,7 @@ __device__ __forceinline__ void luma_rows_fast(const uint8_t* __restrict__ raw, 
             for (int q = lane; q < wq; q += 32) dst[q] = src[q];
         } else if (C == 3) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)r * w * 3);
-#pragma unroll 2
+#pragma unroll 4
             for (int q = lane; q < wq; q += 32) {
                 const uint32_t w0 = src[3 * q], w1 = src[3 * q + 1], w2 = src[3 * q + 2];
                 const uint32_t l0 = dp4a_uu(w0, LO, 0x8000u), h0 = dp4a_uu(w0, HI, 0u);
@@ -881,7 +880,6 @@ __global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const Phash
     uint32_t* s_luma = reinterpret_cast<uint32_t*>(smem + L.luma);
     uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
     uint8_t* s_hrow = smem + L.hrow;
-    int32_t* s_vacc = reinterpret_cast<int32_t*>(smem + L.vacc);
     uint8_t* s_x32 = smem + L.x32;
     uint8_t* s_x98 = smem + L.x98;
     double* s_t = reinterpret_cast<double*>(smem + L.tmat);
@@ -1063,7 +1061,7 @@ int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, c
 // (TMA ring, luma, clip, streamed vertical taps, DCT, bits) is shared with the fast kernel.
 
 struct V3Layout {
-    int raw, luma, acc, hrow, vacc, x32, x98, tmat, ymat, bar, total;
+    int raw, luma, acc, hrow, x32, x98, tmat, ymat, bar, total;
 };
 
 __host__ __device__ inline V3Layout v3_layout(int sub_bytes, int pitch_bytes, int n_slots) {
@@ -1079,7 +1077,6 @@ __host__ __device__ inline V3Layout v3_layout(int sub_bytes, int pitch_bytes, in
     L.luma = take(32 * pitch_bytes + 8 * 16 + 64, 128);  // + slack: padded groups may run past the last row
     L.acc = take(32 * kOuts * 4, 16);
     L.hrow = take(32 * kOuts, 16);
-    L.vacc = take((1024 + kDW * kDH) * 4, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
@@ -1140,7 +1137,6 @@ __global__ void __launch_bounds__(NW * 32 + 32, NW == 4 ? 4 : 2) ke_phash_v3_ker
     uint8_t* s_luma = smem + L.luma;
     uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
     uint8_t* s_hrow = smem + L.hrow;
-    int32_t* s_vacc = reinterpret_cast<int32_t*>(smem + L.vacc);
     uint8_t* s_x32 = smem + L.x32;
     uint8_t* s_x98 = smem + L.x98;
     double* s_t = reinterpret_cast<double*>(smem + L.tmat);
@@ -1279,13 +1275,13 @@ int launch_v3(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
 // The v3 kernel runs load+luma (HBM bound on its own: 5 TB/s) and the tap phases (dp4a bound)
 // one after the other; two CTAs per SM overlap them only by accident.  Here the roles are split
 // inside the CTA and decoupled through shared-memory rings:
-//     warp 10      TMA producer      raw rows  -> raw ring        (full/empty mbarriers)
-//     warps 8..9   luma warps        raw ring  -> luma chunk ring (2 x 32 rows)
+//     warps 8..9   luma warps        raw rows -> raw ring (1-D TMA issued by warp 8 / lane 0, a few
+//                                    sub-chunks ahead) -> luma chunk ring (2 x 32 rows)
 //     warps 0..7   tap warps         luma ring -> horizontal taps (v3 layout) -> clip -> vertical -> DCT
 // so the memory stream runs continuously behind the arithmetic.
 
 constexpr int kV4Tap = 8, kV4Luma = 2;
-constexpr int kV4Threads = (kV4Tap + kV4Luma + 1) * 32;
+constexpr int kV4Threads = (kV4Tap + kV4Luma) * 32;  // no producer warp: luma warp 0 / lane 0 issues the copies
 
 struct V4Layout {
     int raw, luma, acc, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
@@ -1361,38 +1357,38 @@ __global__ void __launch_bounds__(kV4Threads, 2) ke_phash_v4_kernel(const PhashA
     for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV4Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
     __syncthreads();
 
-    if (warp == kV4Tap + kV4Luma) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            uint32_t seq = 0;
-            for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-                const uint8_t* src = a.img + im * a.img_stride;
-                for (int s = 0; s < n_sub; ++s, ++seq) {
-                    const int b = seq & slot_mask;
-                    const int rows = min(sub_rows, a.h - s * sub_rows);
-                    mbar_wait_backoff(&s_empty[b], ((seq >> slot_shift) & 1u) ^ 1u);
-                    mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
-                    bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
-                             &s_full[b]);
-                }
-            }
-        }
-        return;
-    }
-
     if (warp >= kV4Tap) {
-        // ===== luma warps: raw ring -> luma chunk ring =====
+        // ===== luma warps: raw rows -> (TMA) raw ring -> luma chunk ring =====
         const int lw = warp - kV4Tap;
-        uint32_t seq = 0, chunk = 0;
+        const long long my_images = blockIdx.x < a.n ? (a.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long long total_seq = my_images * n_sub;
+        long long issued = 0;
+        auto issue_upto = [&](long long upto) {  // lane 0 of luma warp 0 only
+            for (; issued < upto && issued < total_seq; ++issued) {
+                const long long k = issued / n_sub;
+                const int s = (int)(issued - k * n_sub);
+                const int b = (int)(issued & slot_mask);
+                const int rows = min(sub_rows, a.h - s * sub_rows);
+                mbar_wait(&s_empty[b], (((uint32_t)(issued >> slot_shift)) & 1u) ^ 1u);
+                mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
+                bulk_g2s(s_raw + b * sub_bytes, a.img + (blockIdx.x + k * gridDim.x) * a.img_stride + (long long)s * sub_bytes,
+                         (uint32_t)(rows * row_bytes), &s_full[b]);
+            }
+        };
+        if (lw == 0 && lane == 0) issue_upto(n_slots - 1);
+        long long seq = 0;
+        uint32_t chunk = 0;
         for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
             for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
                 const int lb = chunk & 1;
                 mbar_wait(&l_empty[lb], ((chunk >> 1) & 1u) ^ 1u);  // tap warps are done with this buffer
                 uint32_t* dst = reinterpret_cast<uint32_t*>(s_luma + lb * L.luma_bytes);
                 for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
-                    const int b = seq & slot_mask;
+                    if (lw == 0 && lane == 0) issue_upto(seq + n_slots);  // keep the ring n_slots-1 ahead
+                    __syncwarp();
+                    const int b = (int)(seq & slot_mask);
                     const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
-                    mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
+                    mbar_wait(&s_full[b], ((uint32_t)(seq >> slot_shift)) & 1u);
                     luma_rows_fast<C, kV4Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
                                                pitch_words, lw, lane);
                     __syncwarp();
@@ -1455,11 +1451,13 @@ bool v4_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_by
     pitch_bytes = a.w;
     for (int sub : {8, 4, 2, 1}) {
         if (sub * row_bytes > (1 << 20)) continue;
-        L = v4_layout((int)(sub * row_bytes), pitch_bytes, 2);
-        if (L.total <= 110 * 1024) {
-            sub_rows = sub;
-            slot_shift = 1;
-            return true;
+        for (int shift : {2, 1}) {
+            L = v4_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift);
+            if (L.total <= 110 * 1024) {
+                sub_rows = sub;
+                slot_shift = shift;
+                return true;
+            }
         }
     }
     return false;
@@ -1499,10 +1497,11 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
-    // "v3" (default) | "v4" (warp-specialised luma/tap roles: same speed on B200, kept as the base for the
-    // next round's pipelining work) | "fast" (lanes = rows)
+    // "v4" (default: luma warps + tap warps decoupled through shared-memory rings) | "v3" (same tap layout,
+    // all warps walk the phases together) | "fast" (lanes = rows).  Measured on B200, 512x512x3: 2.19 / 2.05 /
+    // 2.0 M images/s.
     const char* which = getenv("KE_PHASH_KERNEL");
-    if (!ctx->force_generic_phash && which && !strcmp(which, "v4")) {
+    if (!ctx->force_generic_phash && !(which && (!strcmp(which, "v3") || !strcmp(which, "fast")))) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
         V4Layout VL;
         if (v4_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
