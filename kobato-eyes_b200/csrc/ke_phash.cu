@@ -205,15 +205,45 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
                     const int b = ngr[o] * sgi / nseg, e = ngr[o] * (sgi + 1) / nseg;
                     lts.push_back({o, gfirst[o] + b, e - b});
                 }
+            // LDS.128 is served 8 lanes at a time: inside each quarter-warp, lanes reading DIFFERENT
+            // 16-byte groups must fall into different (group % 8) bank sets.  Greedily deal every
+            // block of 32 lane-tasks into 4 quarters with distinct residues (equal groups may share).
+            for (size_t base = 0; base < lts.size(); base += 32) {
+                const size_t cnt = std::min<size_t>(32, lts.size() - base);
+                std::vector<LT> blk(lts.begin() + base, lts.begin() + base + cnt), placed(32, LT{-1, 0, 0});
+                std::vector<int> fill(4, 0);
+                std::vector<std::vector<int>> used(4);  // groups already present per quarter
+                for (const LT& lt : blk) {
+                    int best = -1;
+                    for (int q = 0; q < 4 && best < 0; ++q) {
+                        if (fill[q] >= 8) continue;
+                        bool ok = true;
+                        for (int gq : used[q])
+                            if (gq != lt.g0 && (gq & 7) == (lt.g0 & 7)) ok = false;
+                        if (ok) best = q;
+                    }
+                    if (best < 0)
+                        for (int q = 0; q < 4 && best < 0; ++q)
+                            if (fill[q] < 8) best = q;
+                    placed[best * 8 + fill[best]++] = lt;
+                    used[best].push_back(lt.g0);
+                }
+                for (size_t l = 0; l < 32; ++l)
+                    if (base + l < lts.size() + 0) { /* written back below */ }
+                lts.resize(std::max(lts.size(), base + 32), LT{-1, 0, 0});
+                for (size_t l = 0; l < 32; ++l) lts[base + l] = placed[l];
+            }
             for (size_t base = 0; base < lts.size(); base += 32) {
                 const int task = (int)lt_ng.size();
                 int ng = 1;
-                for (size_t l = base; l < std::min(lts.size(), base + 32); ++l) ng = std::max(ng, lts[l].len);
+                for (size_t l = base; l < std::min(lts.size(), base + 32); ++l)
+                    if (lts[l].o >= 0) ng = std::max(ng, lts[l].len);
                 lt_ng.push_back(ng);
                 lt_meta.resize((size_t)(task + 1) * 32, make_int2(-1, 0));
                 lt_coef.resize((size_t)(task + 1) * 8 * 3 * 32, make_uint4(0, 0, 0, 0));
                 for (int lane = 0; lane < 32 && base + lane < lts.size(); ++lane) {
                     const LT& lt = lts[base + lane];
+                    if (lt.o < 0) continue;  // idle lane (kept at {-1, group 0}: reads row start, adds nothing)
                     lt_meta[(size_t)task * 32 + lane] = make_int2(ob + lt.o, lt.g0);
                     const int first = bd[2 * lt.o], count = bd[2 * lt.o + 1];
                     for (int g = 0; g < lt.len; ++g)
