@@ -393,3 +393,34 @@ def test_join_hybrid_and_bit_sliced_kernels_match_oracle(mode):
         assert np.array_equal(i[order], full[0]) and np.array_equal(j[order], full[1])
     finally:
         ctx.set_option(nat.KE_OPT_JOIN_MODE, 0)
+
+
+def test_join_config_c5_ten_million_hashes():
+    """Config C5 (10 M hashes, 5e13 pairs, T=8), run as 8 tile partitions on this GPU exactly as the
+    8-GPU split does: the union must contain every planted pair, nothing out of range, and equal the
+    CPU oracle on sampled row stripes."""
+    torch = _torch()
+    n = 10_000_000
+    h = synth.synth_hashes(n, planted=0.05)
+    table = torch.from_numpy(h.view(np.int64)).cuda()
+    parts = [ops.hamming_join_device(table, 8, part_index=p, part_count=8, capacity=1 << 22) for p in range(8)]
+    i = torch.cat([p[0] for p in parts]).to(torch.int64) & 0xFFFFFFFF
+    j = torch.cat([p[1] for p in parts]).to(torch.int64) & 0xFFFFFFFF
+    d = torch.cat([p[2] for p in parts])
+    order = torch.argsort((i << 32) | j)
+    i, j, d = i[order].cpu().numpy(), j[order].cpu().numpy(), d[order].cpu().numpy()
+    assert len(np.unique((i << 32) | j)) == len(i), "a pair was emitted by two partitions"
+    assert np.all(i < j) and j.max() < n and d.max() <= 8
+    x = h[i] ^ h[j]
+    assert np.array_equal(np.bitwise_count(x).astype(np.uint8), d)
+    for lo in (0, 4_999_900, 9_999_700):
+        wi, wj, wd = oracle.hamming_join(h, 8, row_begin=lo, row_end=lo + 200, threads=8)
+        sel = (i >= lo) & (i < lo + 200)
+        assert np.array_equal(i[sel], wi) and np.array_equal(j[sel], wj) and np.array_equal(d[sel], wd)
+    n_base = n - (n * 50) // 1000
+    t = np.arange(n_base, n, dtype=np.uint64)
+    src = (synth._mix(synth.SEED, t, 1) % np.uint64(n_base)).astype(np.int64)
+    dist = np.bitwise_count(h[src] ^ h[n_base:])
+    want = set(zip(src[dist <= 8].tolist(), (np.flatnonzero(dist <= 8) + n_base).tolist()))
+    got = set(zip(i.tolist(), j.tolist()))
+    assert want <= got and len(want) > 300_000
