@@ -129,6 +129,28 @@ int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int6
                        double* h_ssim);
 
 /* ---------------------------------------------------------------------------------------
+ * N1 — the refinement the shipped UI runs after a scan (SURVEY §8f "next" row): tile aHash and
+ * small-gray pixel MAE of ui.dup_refine_parallel (src/ui/dup_refine_parallel.py).
+ *
+ * ke_gray_resize_batch: `convert("L").resize((out_w, out_h), filter)` for a batch of decoded images
+ * (filter 1 = LANCZOS, 2 = BILINEAR; Pillow's 8bpc fixed-point arithmetic, byte-identical) —
+ * replaces the resize in tile_ahash_bits (:66-69) and _load_small_gray (:203-207).
+ * d_mid is caller scratch of n*h*out_w bytes, d_out receives n*out_h*out_w bytes.
+ * ke_tile_ahash_bits: planes n x (grid*tile)^2 -> bit strings of ceil((grid*tile)^2/32) uint32 words per
+ * image, bit order (gy, gx, ty, tx), little endian (:71-83), bit = pixel > mean of its tile.
+ * ke_bits_hamming_pairs: popcount(bits[ia] ^ bits[ib]) per pair (tile_hamming :86-88).
+ * ke_plane_sad_pairs: sum |a-b| over two planes per pair; _mae01 (:210-212) = sad / plane_bytes / 255. */
+int ke_gray_resize_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int w, int c, int64_t img_stride,
+                         int64_t row_stride, int out_w, int out_h, int filter, uint8_t* d_mid, uint8_t* d_out,
+                         void* stream);
+int ke_tile_ahash_bits(ke_ctx* ctx, const uint8_t* d_planes, int64_t n, int grid, int tile, uint32_t* d_bits,
+                       void* stream);
+int ke_bits_hamming_pairs(ke_ctx* ctx, const uint32_t* d_bits, int words, const int64_t* d_ia, const int64_t* d_ib,
+                          int64_t n_pairs, int32_t* d_out, void* stream);
+int ke_plane_sad_pairs(ke_ctx* ctx, const uint8_t* d_planes, int64_t plane_bytes, const int64_t* d_ia,
+                       const int64_t* d_ib, int64_t n_pairs, uint64_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py / tests only). */
 
 /* Synthetic image generator, the CUDA twin of kobato_b200.synth.synth_image (identical bytes). */

@@ -55,6 +55,10 @@ struct HTable {           // horizontal pass, one per input width
     int2* d_lt_meta = nullptr;   // [task][lane] -> {output or -1, first group}
     int* d_lt_ng = nullptr;      // [task] -> groups to process (uniform per warp-task)
     int n_wtasks = 0;
+    // tensor-core kernel (v5): per tap warp a run of mma.m16n8k32 B fragments [k-step][tile][lane]
+    uint2* d_mma_b = nullptr;
+    int mma_words = 0;           // uint2 words in d_mma_b (0: this width is not served by v5)
+    int mma_k0[8] = {}, mma_nk[8] = {}, mma_boff[8] = {};
 };
 struct VTable {           // vertical pass, one per input height
     int* d_kk32 = nullptr;
@@ -81,6 +85,7 @@ void ke_tables_free(KeTableCache* cache) {
         cudaFree(kv.second.d_lt_coef);
         cudaFree(kv.second.d_lt_meta);
         cudaFree(kv.second.d_lt_ng);
+        cudaFree(kv.second.d_mma_b);
     }
     for (auto& kv : cache->v) {
         cudaFree(kv.second.d_kk32);
@@ -263,6 +268,80 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
             ob += ow;
         }
     }
+
+    // Tensor-core tables (v5).  The horizontal pass is the banded product  luma[rows, w] x taps[w, 41 x 3 digits]:
+    // taps are written in balanced base-256 digits k = d0 + 256 d1 + 65536 d2, every d in [-128, 127], so one
+    // mma.m16n8k32.s32.u8.s8 per (16 rows, 8 columns, 32 pixels) accumulates a digit plane exactly.
+    // Tap warp q < 4: outputs 8q..8q+7 of the 32-wide target, three tiles (= digits) over one k range.
+    // Tap warps 4..7: the 9-wide target, one tile per output pair (a, b) with columns
+    // {a.d0, a.d1, b.d0, b.d1, a.d2, b.d2, 0, 0}; warp 7 carries the pairs (6,7) and (8,-).
+    std::vector<uint2> mma_b;
+    int mma_k0[8], mma_nk[8], mma_boff[8];
+    bool mma_ok = (w % 16 == 0);
+    if (mma_ok) {
+        std::vector<int32_t> kkP, bdP, kkD, bdD;
+        const int ksP = ke_resample_ksize(w, kOutW), ksD = ke_resample_ksize(w, kDW);
+        kkP.resize((size_t)ksP * kOutW), bdP.resize(2 * kOutW), kkD.resize((size_t)ksD * kDW), bdD.resize(2 * kDW);
+        int rc = ke_resample_table(w, kOutW, kkP.data(), bdP.data(), ksP);
+        if (rc) return rc;
+        if ((rc = ke_resample_table(w, kDW, kkD.data(), bdD.data(), ksD))) return rc;
+        auto tap = [&](int out, int x) -> int32_t {  // out: 0..31 wide target, 32..40 narrow target, else none
+            if (out < 0 || out >= kOuts) return 0;
+            const bool P = out < kOutW;
+            const int o = P ? out : out - kOutW;
+            const int first = P ? bdP[2 * o] : bdD[2 * o], count = P ? bdP[2 * o + 1] : bdD[2 * o + 1];
+            const int t = x - first;
+            if (t < 0 || t >= count) return 0;
+            return P ? kkP[(size_t)o * ksP + t] : kkD[(size_t)o * ksD + t];
+        };
+        auto digit = [&](int32_t k, int d) -> int {
+            int dd[3];
+            for (int i = 0; i < 3; ++i) {
+                dd[i] = ((k & 255) ^ 128) - 128;
+                k = (k - dd[i]) >> 8;
+            }
+            if (k != 0) mma_ok = false;  // does not fit three balanced digits
+            return dd[d];
+        };
+        auto range = [&](int o_lo, int o_hi, int& k0, int& nk) {  // k-steps of 32 pixels touched by outputs [o_lo, o_hi]
+            int first = w, last = 0;
+            for (int o = o_lo; o <= o_hi && o < kOuts; ++o) {
+                const bool P = o < kOutW;
+                const int f = P ? bdP[2 * o] : bdD[2 * (o - kOutW)], c = P ? bdP[2 * o + 1] : bdD[2 * (o - kOutW) + 1];
+                first = std::min(first, f), last = std::max(last, f + c - 1);
+            }
+            k0 = first / 32, nk = last / 32 - k0 + 1;
+        };
+        for (int wv = 0; wv < 8 && mma_ok; ++wv) {
+            int nt, o_lo, o_hi;
+            if (wv < 4) nt = 3, o_lo = 8 * wv, o_hi = 8 * wv + 7;
+            else if (wv < 7) nt = 1, o_lo = kOutW + 2 * (wv - 4), o_hi = o_lo + 1;
+            else nt = 2, o_lo = kOutW + 6, o_hi = kOutW + 8;
+            range(o_lo, o_hi, mma_k0[wv], mma_nk[wv]);
+            mma_boff[wv] = (int)mma_b.size();
+            for (int k = 0; k < mma_nk[wv]; ++k)
+                for (int tl = 0; tl < nt; ++tl)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int n = lane >> 2, t4 = lane & 3;
+                        int out, dg;
+                        if (wv < 4) out = o_lo + n, dg = tl;
+                        else {
+                            const int a_out = o_lo + 2 * tl, b_out = a_out + 1;
+                            static const int sel_out[8] = {0, 0, 1, 1, 0, 1, -1, -1}, sel_d[8] = {0, 1, 0, 1, 2, 2, 0, 0};
+                            out = sel_out[n] < 0 ? -1 : (sel_out[n] ? b_out : a_out);
+                            dg = sel_d[n];
+                        }
+                        uint32_t wd[2] = {0, 0};
+                        for (int half = 0; half < 2; ++half)
+                            for (int i = 0; i < 4; ++i) {
+                                const int x = (mma_k0[wv] + k) * 32 + half * 16 + 4 * t4 + i;
+                                const int dv = digit(tap(out, x), dg);
+                                wd[half] |= ((uint32_t)dv & 0xFFu) << (8 * i);
+                            }
+                        mma_b.push_back(make_uint2(wd[0], wd[1]));
+                    }
+        }
+    }
     HTable t;
     t.n_wtasks = (int)lt_ng.size();
     t.n_bal = (int)bal.size();
@@ -276,6 +355,11 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
     if ((rc = upload(lt_meta, &t.d_lt_meta))) return rc;
     if ((rc = upload(lt_ng, &t.d_lt_ng))) return rc;
     if ((rc = upload(meta, &t.d_meta))) return rc;
+    if (mma_ok) {
+        if ((rc = upload(mma_b, &t.d_mma_b))) return rc;
+        t.mma_words = (int)mma_b.size();
+        for (int i = 0; i < 8; ++i) t.mma_k0[i] = mma_k0[i], t.mma_nk[i] = mma_nk[i], t.mma_boff[i] = mma_boff[i];
+    }
     auto ins = ctx->tables->h.emplace(w, t);
     *out = &ins.first->second;
     return KE_OK;
@@ -383,6 +467,9 @@ struct PhashArgs {
     const int2* lt_meta;
     const int* lt_ng;
     int n_wtasks;
+    const uint2* mma_b;
+    int mma_words;
+    int mma_k0[8], mma_nk[8], mma_boff[8];
     const int* kk32;
     const int* b32;
     const int* kk8;
@@ -723,7 +810,7 @@ __device__ __forceinline__ void vertical_reset(VertState<NW>& v, int lane) {
     for (int d = 0; d < VertState<NW>::D; ++d) v.dacc[d] = (lane < kDW) ? (1 << (kPrec - 1)) : 0;  // rounding term once
 }
 
-template <int NW>
+template <int NW, int HP = kOuts>
 __device__ __forceinline__ void vertical_chunk(const PhashArgs& a, VertState<NW>& v, const uint8_t* s_hrow, int r0,
                                                int rows, int lane, int warp) {
 #pragma unroll
@@ -731,10 +818,10 @@ __device__ __forceinline__ void vertical_chunk(const PhashArgs& a, VertState<NW>
         const int lo = max(v.ymin[q], r0), hi = min(v.ymin[q] + v.ylen[q], r0 + rows);
         if (lo < hi) {
             const int* kk = a.kk32 + (q * NW + warp) * a.ks32 - v.ymin[q];
-            const uint8_t* hp = s_hrow + lane - r0 * kOuts;
+            const uint8_t* hp = s_hrow + lane - r0 * HP;
             int32_t acc = v.acc[q];
 #pragma unroll 8
-            for (int y = lo; y < hi; ++y) acc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
+            for (int y = lo; y < hi; ++y) acc += (int32_t)hp[y * HP] * __ldg(kk + y);
             v.acc[q] = acc;
         }
     }
@@ -744,10 +831,10 @@ __device__ __forceinline__ void vertical_chunk(const PhashArgs& a, VertState<NW>
         for (int d = 0; d < VertState<NW>::D; ++d) {
             const int lo = max(v.dmin[d], r0), hi = min(v.dmin[d] + v.dlen[d], r0 + rows);
             const int* kk = a.kk8 + (d * NW + warp) * a.ks8 - v.dmin[d];
-            const uint8_t* hp = s_hrow + kOutW + x - r0 * kOuts;
+            const uint8_t* hp = s_hrow + kOutW + x - r0 * HP;
             int32_t acc = v.dacc[d];
 #pragma unroll 4
-            for (int y = lo + ph; y < hi; y += 3) acc += (int32_t)hp[y * kOuts] * __ldg(kk + y);
+            for (int y = lo + ph; y < hi; y += 3) acc += (int32_t)hp[y * HP] * __ldg(kk + y);
             v.dacc[d] = acc;
         }
     }
@@ -1508,6 +1595,279 @@ int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
     return KE_OK;
 }
 
+
+// ------------------------------------------------------------------ tensor-core kernel (v5)
+//
+// The horizontal resample IS a matrix product (luma rows x banded tap matrix), and with the taps in
+// balanced base-256 digits it is an exact u8 x s8 -> s32 one.  v5 keeps v4's rings (1-D TMA raw ring ->
+// luma warps -> 2 x 32-row luma ring) and replaces the dp4a tap phase by mma.sync.m16n8k32 on the tensor
+// pipe, which otherwise idles: per 32-row chunk a tap warp loads A fragments with ldmatrix.x4 (luma pitch
+// = w rounded to 32, + 16: conflict free), B fragments (constant per width, staged once in shared
+// memory, lane-major 8 bytes -> conflict-free LDS.64) and keeps two 16-row blocks of accumulators in
+// registers.  Digits are recombined in the epilogue: (2^21 + d0 + 256 d1 + 65536 d2) >> 22, clip, and the
+// bytes go to a double-buffered [32][48] row plane for the (unchanged) streamed vertical pass.
+//     warps 0..3   outputs 8q..8q+7 of the 32-wide target: 3 tiles (digits) x <= 8 k-steps
+//     warps 4..7   output pairs of the 9-wide target: 1 tile (2 for warp 7) x <= 16 k-steps
+//     warps 8..11  luma warps (warp 8 / lane 0 issues the TMA copies)
+
+constexpr int kV5Tap = 8, kV5Luma = 4;
+constexpr int kV5Threads = (kV5Tap + kV5Luma) * 32;
+constexpr int kHP = 48;  // row pitch of the horizontal-pass output plane
+
+struct V5Layout {
+    int raw, luma, bfrag, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
+};
+
+__host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, int n_slots, int mma_words) {
+    V5Layout L;
+    int off = 0;
+    auto take = [&](int bytes, int align) {
+        off = (off + align - 1) / align * align;
+        int at = off;
+        off += bytes;
+        return at;
+    };
+    L.luma_bytes = (32 * pitch_bytes + 127) / 128 * 128;
+    L.raw = take(n_slots * sub_bytes, 128);
+    L.luma = take(2 * L.luma_bytes, 128);
+    L.bfrag = take(mma_words * 8, 16);
+    L.hrow = take(2 * 32 * kHP, 16);
+    L.x32 = take(1024, 16);
+    L.x98 = take(80, 16);
+    L.tmat = take(8 * 32 * 8, 16);
+    L.ymat = take(64 * 8, 16);
+    L.bar = take((2 * kMaxSlots + 4) * 8, 8);
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_u8s8(int32_t (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ uint32_t clip8u(int32_t v) {
+    v >>= kPrec;
+    return (uint32_t)min(max(v, 0), 255);
+}
+
+// One 32-row luma chunk -> this warp's columns of the row plane.  NT tiles share the k range.
+// WIDE: tiles are the three digits of outputs out0..out0+7; else tile tl is the output pair (out0 + 2 tl, +1).
+template <int NT, bool WIDE>
+__device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict__ bw, int nk, int pitch_bytes,
+                                        uint8_t* __restrict__ hrow, int out0, int lane) {
+    int32_t c[2][NT][4];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[rb][tl][i] = 0;
+#pragma unroll 2
+    for (int k = 0; k < nk; ++k) {
+        uint32_t a0[4], a1[4];
+        ldmatrix_x4(a0, a_addr + k * 32);
+        ldmatrix_x4(a1, a_addr + k * 32 + 16 * pitch_bytes);
+#pragma unroll
+        for (int tl = 0; tl < NT; ++tl) {
+            const uint2 b = bw[(k * NT + tl) * 32];
+            mma_u8s8(c[0][tl], a0, b);
+            mma_u8s8(c[1][tl], a1, b);
+        }
+    }
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int32_t kRound = 1 << (kPrec - 1);
+    if (WIDE) {
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int32_t v0 = kRound + c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
+                const int32_t v1 = kRound + c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
+                *reinterpret_cast<uint16_t*>(hrow + (rb * 16 + hf * 8 + g) * kHP + out0 + 2 * t) =
+                    (uint16_t)(clip8u(v0) | (clip8u(v1) << 8));
+            }
+    } else {
+        const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+            for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int32_t xa = __shfl_sync(0xffffffffu, c[rb][tl][2 * hf], src);
+                    const int32_t xb = __shfl_sync(0xffffffffu, c[rb][tl][2 * hf + 1], src);
+                    const int32_t d2 = t == 0 ? xa : xb;
+                    const int32_t v = kRound + c[rb][tl][2 * hf] + (c[rb][tl][2 * hf + 1] << 8) + (d2 << 16);
+                    if (t < 2) hrow[(rb * 16 + hf * 8 + g) * kHP + out0 + 2 * tl + t] = (uint8_t)clip8u(v);
+                }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows,
+                                                                   const int slot_shift, const int pitch_bytes,
+                                                                   const int dbg) {
+    constexpr int CR = 32, NW = kV5Tap;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int row_bytes = a.w * C;
+    const int sub_bytes = sub_rows * row_bytes;
+    const int n_slots = 1 << slot_shift;
+    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
+    const V5Layout L = v5_layout(sub_bytes, pitch_bytes, n_slots, a.mma_words);
+    uint8_t* s_raw = smem + L.raw;
+    uint8_t* s_luma = smem + L.luma;
+    uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
+    uint8_t* s_hrow = smem + L.hrow;
+    uint8_t* s_x32 = smem + L.x32;
+    uint8_t* s_x98 = smem + L.x98;
+    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
+    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // raw ring
+    uint64_t* s_empty = s_full + kMaxSlots;
+    uint64_t* l_full = s_empty + kMaxSlots;  // luma chunk ring [2]
+    uint64_t* l_empty = l_full + 2;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_sub = (a.h + sub_rows - 1) / sub_rows;
+    const int subs_per_chunk = CR / sub_rows;
+    const int pitch_words = pitch_bytes >> 2;
+
+    if (tid == 0) {
+        for (int b = 0; b < n_slots; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], kV5Luma);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&l_full[b], kV5Luma);
+            mbar_init(&l_empty[b], kV5Tap);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < a.mma_words; i += kV5Threads) s_b[i] = __ldg(a.mma_b + i);
+    for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
+    for (int i = tid; i < 2 * 32 * kHP / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_hrow)[i] = 0u;
+    __syncthreads();
+
+    if (warp >= kV5Tap) {
+        // ===== luma warps: raw rows -> (TMA) raw ring -> luma chunk ring =====
+        const int lw = warp - kV5Tap;
+        const long long my_images = blockIdx.x < a.n ? (a.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long long total_seq = my_images * n_sub;
+        long long issued = 0;
+        auto issue_upto = [&](long long upto) {  // lane 0 of luma warp 0 only
+            for (; issued < upto && issued < total_seq; ++issued) {
+                const long long k = issued / n_sub;
+                const int s = (int)(issued - k * n_sub);
+                const int b = (int)(issued & slot_mask);
+                const int rows = min(sub_rows, a.h - s * sub_rows);
+                mbar_wait(&s_empty[b], (((uint32_t)(issued >> slot_shift)) & 1u) ^ 1u);
+                mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
+                bulk_g2s(s_raw + b * sub_bytes, a.img + (blockIdx.x + k * gridDim.x) * a.img_stride + (long long)s * sub_bytes,
+                         (uint32_t)(rows * row_bytes), &s_full[b]);
+            }
+        };
+        if (lw == 0 && lane == 0) issue_upto(n_slots - 1);
+        long long seq = 0;
+        uint32_t chunk = 0;
+        for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
+                const int lb = chunk & 1;
+                mbar_wait(&l_empty[lb], ((chunk >> 1) & 1u) ^ 1u);  // tap warps are done with this buffer
+                uint32_t* dst = reinterpret_cast<uint32_t*>(s_luma + lb * L.luma_bytes);
+                for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
+                    if (lw == 0 && lane == 0) issue_upto(seq + n_slots);  // keep the ring n_slots-1 ahead
+                    __syncwarp();
+                    const int b = (int)(seq & slot_mask);
+                    const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
+                    mbar_wait(&s_full[b], ((uint32_t)(seq >> slot_shift)) & 1u);
+                    luma_rows_fast<C, kV5Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
+                                               pitch_words, lw, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive1(&s_empty[b]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive1(&l_full[lb]);  // release: the chunk's luma rows are written
+            }
+        }
+        return;
+    }
+
+    // ===== tap warps =====
+    const uint2* bw = s_b + a.mma_boff[warp] + lane;
+    const int nk = (dbg & 2) ? 0 : a.mma_nk[warp];
+    const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mma_k0[warp] * 32);
+    uint32_t chunk = 0;
+    VertState<NW> vs;
+    vertical_init(a, vs, lane, warp);
+    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+        vertical_reset(vs, lane);
+        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
+            const int rows = min(CR, a.h - r0);
+            const int lb = chunk & 1;
+            uint8_t* hrow = s_hrow + lb * (32 * kHP);
+            mbar_wait(&l_full[lb], (chunk >> 1) & 1u);
+            const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
+            if (warp < 4) v5_taps<3, true>(a_addr, bw, nk, pitch_bytes, hrow, 8 * warp, lane);
+            else if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
+            else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 6, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
+            compute_sync<NW>();
+            // the row plane is double buffered: the next chunk's epilogue writes the other half, and the
+            // half read here is rewritten only after the next chunk's barrier
+            if (!(dbg & 4)) vertical_chunk<NW, kHP>(a, vs, hrow, r0, rows, lane, warp);
+        }
+        vertical_finish(vs, s_x32, s_x98, lane, warp);
+        compute_sync<NW>();
+        dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
+    }
+}
+
+template <int C>
+bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V5Layout& L) {
+    const long long row_bytes = (long long)a.w * C;
+    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.mma_words < 1) return false;
+    pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
+    int want_sub = 8, want_shift = 2;
+    if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d", &want_sub, &want_shift);  // tuning override
+    for (int sub : {want_sub, 8, 4, 2, 1}) {
+        if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
+        for (int shift : {want_shift, 2, 1}) {
+            if (shift < 1 || shift > 3) continue;
+            L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words);
+            if (L.total <= 113 * 1024) {
+                sub_rows = sub;
+                slot_shift = shift;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <int C>
+int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, const V5Layout& L,
+              cudaStream_t s) {
+    KE_CUDA(cudaFuncSetAttribute(ke_phash_v5_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_v5_kernel<C>, kV5Threads, L.total));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.n) grid = a.n;
+    const char* dbg_env = getenv("KE_PHASH_DBG");
+    ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes,
+                                                                      dbg_env ? atoi(dbg_env) : 0);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 int g_dct_uploaded_device = -1;
 
 int ensure_dct(ke_ctx* ctx) {
@@ -1531,6 +1891,12 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // all warps walk the phases together) | "fast" (lanes = rows).  Measured on B200, 512x512x3: 2.19 / 2.05 /
     // 2.0 M images/s.
     const char* which = getenv("KE_PHASH_KERNEL");
+    if (!ctx->force_generic_phash && (!which || !strcmp(which, "v5"))) {
+        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
+        V5Layout VL;
+        if (v5_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
+            return launch_v5<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
+    }
     if (!ctx->force_generic_phash && !(which && (!strcmp(which, "v3") || !strcmp(which, "fast")))) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
         V4Layout VL;
@@ -1618,6 +1984,9 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     a.lt_meta = ht->d_lt_meta;
     a.lt_ng = ht->d_lt_ng;
     a.n_wtasks = ht->n_wtasks;
+    a.mma_b = ht->d_mma_b;
+    a.mma_words = ht->mma_words;
+    for (int i = 0; i < 8; ++i) a.mma_k0[i] = ht->mma_k0[i], a.mma_nk[i] = ht->mma_nk[i], a.mma_boff[i] = ht->mma_boff[i];
     a.meta = ht->d_meta;
     a.n_items = ht->n_items;
     a.coef_words = ht->coef_words;

@@ -348,14 +348,14 @@ def test_phash_fast_and_generic_kernels_agree():
 
     ctx = nat.context(torch.cuda.current_device())
     for (h, w, c, n) in ((512, 512, 3, 300), (96, 160, 3, 40), (200, 64, 4, 20), (130, 256, 1, 20), (1100, 1024, 3, 6),
-                         (70, 100, 3, 9)):
+                         (70, 100, 3, 9), (512, 512, 1, 64), (512, 512, 4, 64), (300, 256, 3, 40), (31, 48, 3, 17), (640, 480, 3, 20)):
         imgs = ops.synth_images_device(0, n, h, w, c, n_set=n)
         ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
         try:
             gen = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
         finally:
             ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
-        for kernel in ("v3", "v4", "fast"):  # the library falls back by itself when a kernel does not take the shape
+        for kernel in ("v5", "v4", "v3", "fast"):  # the library falls back by itself when a kernel does not take the shape
             os.environ["KE_PHASH_KERNEL"] = kernel
             try:
                 got = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
