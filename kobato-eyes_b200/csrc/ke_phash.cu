@@ -66,6 +66,11 @@ struct VTable {           // vertical pass, one per input height
     int* d_kk8 = nullptr;
     int* d_b8 = nullptr;
     int ks32 = 0, ks8 = 0;
+    // tensor-core vertical pass (v5): A fragments [chunk of 32 rows][unit][digit][lane]; unit 0/1 = output rows
+    // 0..15 / 16..31 of the 32x32 plane, unit 2 = the 8 rows of the 8x9 plane
+    uint4* d_vmma = nullptr;
+    int vmma_ok = 0;
+    int v_lo[3] = {}, v_hi[3] = {};  // chunks [lo, hi] in which a unit has non-zero taps
 };
 
 }  // namespace
@@ -92,6 +97,7 @@ void ke_tables_free(KeTableCache* cache) {
         cudaFree(kv.second.d_b32);
         cudaFree(kv.second.d_kk8);
         cudaFree(kv.second.d_b8);
+        cudaFree(kv.second.d_vmma);
     }
     delete cache;
 }
@@ -383,6 +389,47 @@ int get_vtable(ke_ctx* ctx, int h, const VTable** out) {
     if ((rc = upload(b32, &t.d_b32))) return rc;
     if ((rc = upload(kk8, &t.d_kk8))) return rc;
     if ((rc = upload(b8, &t.d_b8))) return rc;
+    {
+        const int nch = (h + 31) / 32;
+        std::vector<uint4> vm((size_t)nch * 3 * 3 * 32, make_uint4(0, 0, 0, 0));
+        bool ok = true;
+        auto tap = [&](int unit, int r, int y) -> int32_t {  // tap of output row r of the unit at input row y
+            if (y >= h) return 0;
+            if (unit < 2) {
+                const int yy = 16 * unit + r, tpos = y - b32[2 * yy];
+                return (tpos >= 0 && tpos < b32[2 * yy + 1]) ? kk32[(size_t)yy * t.ks32 + tpos] : 0;
+            }
+            if (r >= kDH) return 0;
+            const int tpos = y - b8[2 * r];
+            return (tpos >= 0 && tpos < b8[2 * r + 1]) ? kk8[(size_t)r * t.ks8 + tpos] : 0;
+        };
+        for (int u = 0; u < 3; ++u) t.v_lo[u] = nch, t.v_hi[u] = -1;
+        for (int c = 0; c < nch; ++c)
+            for (int u = 0; u < 3; ++u)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t4 = lane & 3;
+                    uint32_t reg[3][4] = {};
+                    for (int ri = 0; ri < 4; ++ri) {  // a0: (g, k lo) a1: (g+8, k lo) a2: (g, k hi) a3: (g+8, k hi)
+                        const int r = g + 8 * (ri & 1), kb = 16 * (ri >> 1) + 4 * t4;
+                        for (int i = 0; i < 4; ++i) {
+                            int32_t k = tap(u, r, 32 * c + kb + i);
+                            if (k) t.v_lo[u] = std::min(t.v_lo[u], c), t.v_hi[u] = std::max(t.v_hi[u], c);
+                            for (int d = 0; d < 3; ++d) {
+                                const int dd = ((k & 255) ^ 128) - 128;
+                                k = (k - dd) >> 8;
+                                reg[d][ri] |= ((uint32_t)dd & 0xFFu) << (8 * i);
+                            }
+                            if (k != 0) ok = false;
+                        }
+                    }
+                    for (int d = 0; d < 3; ++d)
+                        vm[(((size_t)c * 3 + u) * 3 + d) * 32 + lane] = make_uint4(reg[d][0], reg[d][1], reg[d][2], reg[d][3]);
+                }
+        if (ok) {
+            if ((rc = upload(vm, &t.d_vmma))) return rc;
+            t.vmma_ok = 1;
+        }
+    }
     auto ins = ctx->tables->v.emplace(h, t);
     *out = &ins.first->second;
     return KE_OK;
@@ -436,6 +483,23 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         __nanosleep(800);
     }
 }
+
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    // consumer side: poll politely so the spinning warps do not take issue slots from the producers
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
@@ -470,6 +534,8 @@ struct PhashArgs {
     const uint2* mma_b;
     int mma_words;
     int mma_k0[8], mma_nk[8], mma_boff[8];
+    const uint4* vmma;
+    int v_lo[3], v_hi[3];
     const int* kk32;
     const int* b32;
     const int* kk8;
@@ -979,6 +1045,56 @@ __device__ __forceinline__ void luma_rows_fast(const uint8_t* __restrict__ raw, 
                 const uint32_t s3 = dp4a_uu(px.w, LO, 0x8000u) + (dp4a_uu(px.w, HI, 0u) << 8);
                 dst[q] = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
             }
+        }
+    }
+}
+
+
+// RGB rows -> luma rows, 16 pixels per lane: 3 LDS.128 of raw bytes (lane stride 48 B: conflict free), 48 dp4a,
+// one STS.128.  Two rows are in flight per warp so that the loads of one overlap the arithmetic of the other.
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// 4 RGB pixels (12 bytes in w0..w2) -> 4 luma bytes.  dp2a multiplies two 16-bit coefficients by a byte PAIR of
+// the pixel word, and every pixel of the 12-byte group splits into pairs at (0,1)|(2,3) boundaries:
+//   p0 = w0.b0..b2   p1 = w0.b3, w1.b0, w1.b1   p2 = w1.b2, w1.b3, w2.b0   p3 = w2.b1..b3
+// so each pixel costs exactly two dp2a (Pillow: L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16).
+__device__ __forceinline__ uint32_t luma4_rgb(uint32_t w0, uint32_t w1, uint32_t w2) {
+    constexpr uint32_t cR = 19595u, cG = 38470u, cB = 7471u;
+    constexpr uint32_t RG = cR | (cG << 16), B_ = cB, _R = cR << 16, GB = cG | (cB << 16);
+    const uint32_t s0 = dp2a_hi(B_, w0, dp2a_lo(RG, w0, 0x8000u));
+    const uint32_t s1 = dp2a_lo(GB, w1, dp2a_hi(_R, w0, 0x8000u));
+    const uint32_t s2 = dp2a_lo(B_, w2, dp2a_hi(RG, w1, 0x8000u));
+    const uint32_t s3 = dp2a_hi(GB, w2, dp2a_lo(_R, w2, 0x8000u));
+    return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);  // byte 2 of each sum
+}
+__device__ __forceinline__ uint4 luma16_rgb(const uint4 a, const uint4 b, const uint4 c) {
+    return make_uint4(luma4_rgb(a.x, a.y, a.z), luma4_rgb(a.w, b.x, b.y), luma4_rgb(b.z, b.w, c.x), luma4_rgb(c.y, c.z, c.w));
+}
+template <int NLW>
+__device__ __forceinline__ void luma_rows_rgb16(const uint8_t* __restrict__ raw, uint8_t* __restrict__ luma, int rows,
+                                                int w, int row_bytes, int pitch_bytes, int lw, int lane) {
+    const int ng = w >> 4;  // 16-pixel groups per row
+    for (int r = lw; r < rows; r += 2 * NLW) {
+        const bool two = r + NLW < rows;
+        const uint8_t* s0 = raw + r * row_bytes;
+        const uint8_t* s1 = s0 + (two ? NLW * row_bytes : 0);
+        uint8_t* d0 = luma + r * pitch_bytes;
+        uint8_t* d1 = d0 + NLW * pitch_bytes;
+        for (int g = lane; g < ng; g += 32) {
+            const uint4* p0 = reinterpret_cast<const uint4*>(s0 + 48 * g);
+            const uint4* p1 = reinterpret_cast<const uint4*>(s1 + 48 * g);
+            const uint4 a0 = p0[0], b0 = p0[1], c0 = p0[2];
+            const uint4 a1 = p1[0], b1 = p1[1], c1 = p1[2];
+            *reinterpret_cast<uint4*>(d0 + 16 * g) = luma16_rgb(a0, b0, c0);
+            if (two) *reinterpret_cast<uint4*>(d1 + 16 * g) = luma16_rgb(a1, b1, c1);
         }
     }
 }
@@ -1651,6 +1767,11 @@ __device__ __forceinline__ void mma_u8s8(int32_t (&c)[4], const uint32_t (&a)[4]
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
+__device__ __forceinline__ uint32_t pack_sat_u8(int32_t hi, int32_t lo) {  // sat_u8(hi) << 8 | sat_u8(lo)
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(0));
+    return d;
+}
 __device__ __forceinline__ uint32_t clip8u(int32_t v) {
     v >>= kPrec;
     return (uint32_t)min(max(v, 0), 255);
@@ -1667,7 +1788,8 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
 #pragma unroll
         for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) c[rb][tl][i] = 0;
+            for (int i = 0; i < 4; ++i)  // the rounding term 2^21 rides in the d0 accumulators
+                c[rb][tl][i] = WIDE ? (tl == 0 ? (1 << (kPrec - 1)) : 0) : ((i & 1) == 0 && (lane & 3) < 2 ? (1 << (kPrec - 1)) : 0);
 #pragma unroll 2
     for (int k = 0; k < nk; ++k) {
         uint32_t a0[4], a1[4];
@@ -1681,16 +1803,15 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
         }
     }
     const int g = lane >> 2, t = lane & 3;
-    constexpr int32_t kRound = 1 << (kPrec - 1);
     if (WIDE) {
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                const int32_t v0 = kRound + c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
-                const int32_t v1 = kRound + c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
+                const int32_t v0 = c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
+                const int32_t v1 = c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
                 *reinterpret_cast<uint16_t*>(hrow + (rb * 16 + hf * 8 + g) * kHP + out0 + 2 * t) =
-                    (uint16_t)(clip8u(v0) | (clip8u(v1) << 8));
+                    (uint16_t)pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
             }
     } else {
         const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
@@ -1703,8 +1824,8 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
                     const int32_t xa = __shfl_sync(0xffffffffu, c[rb][tl][2 * hf], src);
                     const int32_t xb = __shfl_sync(0xffffffffu, c[rb][tl][2 * hf + 1], src);
                     const int32_t d2 = t == 0 ? xa : xb;
-                    const int32_t v = kRound + c[rb][tl][2 * hf] + (c[rb][tl][2 * hf + 1] << 8) + (d2 << 16);
-                    if (t < 2) hrow[(rb * 16 + hf * 8 + g) * kHP + out0 + 2 * tl + t] = (uint8_t)clip8u(v);
+                    const int32_t v = c[rb][tl][2 * hf] + (c[rb][tl][2 * hf + 1] << 8) + (d2 << 16);
+                    if (t < 2) hrow[(rb * 16 + hf * 8 + g) * kHP + out0 + 2 * tl + t] = (uint8_t)pack_sat_u8(0, v >> kPrec);
                 }
     }
 }
@@ -1786,8 +1907,12 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                     const int b = (int)(seq & slot_mask);
                     const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
                     mbar_wait(&s_full[b], ((uint32_t)(seq >> slot_shift)) & 1u);
-                    luma_rows_fast<C, kV5Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
-                                               pitch_words, lw, lane);
+                    if (C == 3)
+                        luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, reinterpret_cast<uint8_t*>(dst) + s * sub_rows * pitch_bytes,
+                                                 srows, a.w, row_bytes, pitch_bytes, lw, lane);
+                    else
+                        luma_rows_fast<C, kV5Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
+                                                   pitch_words, lw, lane);
                     __syncwarp();
                     if (lane == 0) mbar_arrive1(&s_empty[b]);
                 }
@@ -1811,7 +1936,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             const int rows = min(CR, a.h - r0);
             const int lb = chunk & 1;
             uint8_t* hrow = s_hrow + lb * (32 * kHP);
-            mbar_wait(&l_full[lb], (chunk >> 1) & 1u);
+            mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, 200);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
             if (warp < 4) v5_taps<3, true>(a_addr, bw, nk, pitch_bytes, hrow, 8 * warp, lane);
             else if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
@@ -1987,6 +2112,8 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     a.mma_b = ht->d_mma_b;
     a.mma_words = ht->mma_words;
     for (int i = 0; i < 8; ++i) a.mma_k0[i] = ht->mma_k0[i], a.mma_nk[i] = ht->mma_nk[i], a.mma_boff[i] = ht->mma_boff[i];
+    a.vmma = vt->vmma_ok ? vt->d_vmma : nullptr;
+    for (int i = 0; i < 3; ++i) a.v_lo[i] = vt->v_lo[i], a.v_hi[i] = vt->v_hi[i];
     a.meta = ht->d_meta;
     a.n_items = ht->n_items;
     a.coef_words = ht->coef_words;
