@@ -1728,7 +1728,8 @@ int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
 
 constexpr int kV5Tap = 8, kV5Luma = 4;
 constexpr int kV5Threads = (kV5Tap + kV5Luma) * 32;
-constexpr int kHP = 48;  // row pitch of the horizontal-pass output plane
+constexpr int kHP = 48;   // horizontal-pass output plane, stored TRANSPOSED: [column 0..47][row 0..31], column pitch 48 B
+constexpr int kHCols = 48;
 
 struct V5Layout {
     int raw, luma, bfrag, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
@@ -1747,7 +1748,7 @@ __host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, in
     L.raw = take(n_slots * sub_bytes, 128);
     L.luma = take(2 * L.luma_bytes, 128);
     L.bfrag = take(mma_words * 8, 16);
-    L.hrow = take(2 * 32 * kHP, 16);
+    L.hrow = take(2 * kHCols * kHP, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
@@ -1766,6 +1767,11 @@ __device__ __forceinline__ void mma_u8s8(int32_t (&c)[4], const uint32_t (&a)[4]
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void mma_s8u8(int32_t (&c)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_sat_u8(int32_t hi, int32_t lo) {  // sat_u8(hi) << 8 | sat_u8(lo)
     uint32_t d;
@@ -1810,8 +1816,9 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
             for (int hf = 0; hf < 2; ++hf) {
                 const int32_t v0 = c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
                 const int32_t v1 = c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
-                *reinterpret_cast<uint16_t*>(hrow + (rb * 16 + hf * 8 + g) * kHP + out0 + 2 * t) =
-                    (uint16_t)pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+                const int row = rb * 16 + hf * 8 + g;
+                hrow[(out0 + 2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
+                hrow[(out0 + 2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
             }
     } else {
         const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
@@ -1825,7 +1832,7 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
                     const int32_t xb = __shfl_sync(0xffffffffu, c[rb][tl][2 * hf + 1], src);
                     const int32_t d2 = t == 0 ? xa : xb;
                     const int32_t v = c[rb][tl][2 * hf] + (c[rb][tl][2 * hf + 1] << 8) + (d2 << 16);
-                    if (t < 2) hrow[(rb * 16 + hf * 8 + g) * kHP + out0 + 2 * tl + t] = (uint8_t)pack_sat_u8(0, v >> kPrec);
+                    if (t < 2) hrow[(out0 + 2 * tl + t) * kHP + rb * 16 + hf * 8 + g] = (uint8_t)pack_sat_u8(0, v >> kPrec);
                 }
     }
 }
@@ -1872,7 +1879,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     }
     for (int i = tid; i < a.mma_words; i += kV5Threads) s_b[i] = __ldg(a.mma_b + i);
     for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
-    for (int i = tid; i < 2 * 32 * kHP / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_hrow)[i] = 0u;
+    for (int i = tid; i < 2 * kHCols * kHP / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_hrow)[i] = 0u;
     __syncthreads();
 
     if (warp >= kV5Tap) {
@@ -1927,15 +1934,32 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     const uint2* bw = s_b + a.mma_boff[warp] + lane;
     const int nk = (dbg & 2) ? 0 : a.mma_nk[warp];
     const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mma_k0[warp] * 32);
+    // Vertical pass, also on the tensor pipe: out[yy, x] = sum_y V[yy, y] * hrow[y, x] per 32-row chunk is one
+    // k-step of mma.m16n8k32.s8.u8 (A = tap digits from the per-height table, B = the transposed row plane).
+    // The accumulators live in warps 4..7 for the whole image: (unit, 8-column tile) pairs
+    //   warp 4: (0,0) (0,1) (0,2)   warp 5: (0,3) (1,0) (1,1)   warp 6: (1,2) (1,3)   warp 7: (2,0) (2,1)
+    constexpr int NVP = 3;
+    int32_t vc[NVP][3][4];
+    int v_unit[NVP], v_nt[NVP];
+#pragma unroll
+    for (int p = 0; p < NVP; ++p) {
+        const int idx = (warp - 4) * 3 + p;  // warps 4,5: pairs 0..5; warp 6: 6,7; warp 7: unit 2
+        v_unit[p] = warp < 4 ? -1 : (warp == 7 ? (p < 2 ? 2 : -1) : (idx < 8 ? idx >> 2 : -1));
+        v_nt[p] = warp == 7 ? 4 + p : (idx & 3);
+    }
+    const int g = lane >> 2, t = lane & 3;
     uint32_t chunk = 0;
-    VertState<NW> vs;
-    vertical_init(a, vs, lane, warp);
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-        vertical_reset(vs, lane);
-        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
-            const int rows = min(CR, a.h - r0);
+#pragma unroll
+        for (int p = 0; p < NVP; ++p)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vc[p][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+        int ci = 0;
+        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci) {
             const int lb = chunk & 1;
-            uint8_t* hrow = s_hrow + lb * (32 * kHP);
+            uint8_t* hrow = s_hrow + lb * (kHCols * kHP);
             mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, 200);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
             if (warp < 4) v5_taps<3, true>(a_addr, bw, nk, pitch_bytes, hrow, 8 * warp, lane);
@@ -1946,9 +1970,40 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             compute_sync<NW>();
             // the row plane is double buffered: the next chunk's epilogue writes the other half, and the
             // half read here is rewritten only after the next chunk's barrier
-            if (!(dbg & 4)) vertical_chunk<NW, kHP>(a, vs, hrow, r0, rows, lane, warp);
+            if (warp >= 4 && !(dbg & 4)) {
+#pragma unroll
+                for (int p = 0; p < NVP; ++p) {
+                    const int u = v_unit[p];
+                    if (u < 0 || ci < a.v_lo[u] || ci > a.v_hi[u]) continue;
+                    const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + (v_nt[p] * 8 + g) * kHP);
+                    const uint32_t b0 = col[t], b1 = col[4 + t];
+                    const uint4* af = a.vmma + ((size_t)(ci * 3 + u) * 3) * 32 + lane;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) mma_s8u8(vc[p][d], __ldg(af + d * 32), b0, b1);
+                }
+            }
         }
-        vertical_finish(vs, s_x32, s_x98, lane, warp);
+        // planes from the vertical accumulators
+        if (warp >= 4) {
+#pragma unroll
+            for (int p = 0; p < NVP; ++p) {
+                const int u = v_unit[p];
+                if (u < 0) continue;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int32_t v0 = vc[p][0][2 * hf] + (vc[p][1][2 * hf] << 8) + (vc[p][2][2 * hf] << 16);
+                    const int32_t v1 = vc[p][0][2 * hf + 1] + (vc[p][1][2 * hf + 1] << 8) + (vc[p][2][2 * hf + 1] << 16);
+                    const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+                    if (u < 2) {
+                        *reinterpret_cast<uint16_t*>(s_x32 + (u * 16 + hf * 8 + g) * 32 + v_nt[p] * 8 + 2 * t) = (uint16_t)pk;
+                    } else if (hf == 0) {  // 8x9 plane: rows g, columns (nt-4)*8 + 2t (+1) < 9
+                        const int x = (v_nt[p] - 4) * 8 + 2 * t;
+                        if (x < kDW) s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+                        if (x + 1 < kDW) s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
+                    }
+                }
+            }
+        }
         compute_sync<NW>();
         dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
     }
@@ -1957,7 +2012,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 template <int C>
 bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V5Layout& L) {
     const long long row_bytes = (long long)a.w * C;
-    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.mma_words < 1) return false;
+    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.mma_words < 1 || !a.vmma) return false;
     pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
     int want_sub = 8, want_shift = 2;
     if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d", &want_sub, &want_shift);  // tuning override
