@@ -1914,7 +1914,8 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                     const int b = (int)(seq & slot_mask);
                     const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
                     mbar_wait(&s_full[b], ((uint32_t)(seq >> slot_shift)) & 1u);
-                    if (C == 3)
+                    if (dbg & 8) {  // tuning probe: the TMA feed alone
+                    } else if (C == 3)
                         luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, reinterpret_cast<uint8_t*>(dst) + s * sub_rows * pitch_bytes,
                                                  srows, a.w, row_bytes, pitch_bytes, lw, lane);
                     else
@@ -1960,7 +1961,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci) {
             const int lb = chunk & 1;
             uint8_t* hrow = s_hrow + lb * (kHCols * kHP);
-            mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, 200);
+            mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, (uint32_t)dbg >> 8);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
             if (warp < 4) v5_taps<3, true>(a_addr, bw, nk, pitch_bytes, hrow, 8 * warp, lane);
             else if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
@@ -2041,8 +2042,10 @@ int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > a.n) grid = a.n;
     const char* dbg_env = getenv("KE_PHASH_DBG");
+    const char* ns_env = getenv("KE_PHASH_SLEEP");  // tuning override: consumer poll interval in ns
+    const int ns = ns_env ? atoi(ns_env) : 200;
     ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes,
-                                                                      dbg_env ? atoi(dbg_env) : 0);
+                                                                      ((dbg_env ? atoi(dbg_env) : 0) & 0xFF) | (ns << 8));
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;
