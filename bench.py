@@ -47,31 +47,70 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs.
+
+    NVML in a background thread (every 100 ms).  An `nvidia-smi -lms` child was measured to stall kernel
+    launches for ~10 ms per query on these boxes (it showed up as a 12 ms bubble in front of the join), so it
+    is only the fallback when the NVML binding is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop = index, [], None, threading.Event()
+        self.source = None
 
     def __enter__(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.source = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
         return self
 
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if rs & bits[k] else "Not Active" for k in self.NAMES])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
@@ -80,20 +119,22 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(names, r[3:7]):
+            for name, v in zip(self.NAMES, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx),
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -232,11 +273,11 @@ def run_cuda(args) -> dict:
     k1_ms = stage["phash"] / args.steps  # live, inside the timed region: one launch per step
     k1_bytes = n * (IMG_BYTES + 16)
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
-    roof_k1 = {"kernel": "ke_phash_v4_kernel<3> (512x512x3)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roof_k1 = {"kernel": "ke_phash_v5_kernel<3> (512x512x3; TMA ring + dp2a luma + mma.sync u8xs8 resample)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k1_gbs / hbm_peak,
-               # dram read+write per launch: 789 698 B/image measured by `ncu --set full` on a 4096-image launch of
-               # the same kernel (profiles/r1_ncu_full_summary.txt), scaled to this launch's image count
-               "traffic": int(n * 789698), "peak_source": peak_src,
+               # dram read+write per launch: 795 543 B/image measured by `ncu --set full` on an 8192-image launch of
+               # the same kernel (profiles/r1_ncu_k1v5_summary.txt), scaled to this launch's image count
+               "traffic": int(n * 795543), "peak_source": peak_src,
                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                "images_per_s": n / (k1_ms * 1e-3)}
 
