@@ -1753,7 +1753,7 @@ __host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, in
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
     L.ymat = take(64 * 8, 16);
-    L.bar = take((2 * kMaxSlots + 4) * 8, 8);
+    L.bar = take((2 * kMaxSlots + 4) * 8 + kMaxSlots * 4, 8);
     L.total = off;
     return L;
 }
@@ -1860,6 +1860,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     uint64_t* s_empty = s_full + kMaxSlots;
     uint64_t* l_full = s_empty + kMaxSlots;  // luma chunk ring [2]
     uint64_t* l_empty = l_full + 2;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(l_empty + 2);  // readers done with a raw slot (mod kV5Luma)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_sub = (a.h + sub_rows - 1) / sub_rows;
@@ -1869,7 +1870,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     if (tid == 0) {
         for (int b = 0; b < n_slots; ++b) {
             mbar_init(&s_full[b], 1);
-            mbar_init(&s_empty[b], kV5Luma);
+            s_cnt[b] = 0u;
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&l_full[b], kV5Luma);
@@ -1884,45 +1885,76 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 
     if (warp >= kV5Tap) {
         // ===== luma warps: raw rows -> (TMA) raw ring -> luma chunk ring =====
+        // A raw slot is refilled by whichever luma warp finishes reading it LAST (a shared-memory counter
+        // per slot tells): no issuer warp, no "slot empty" barrier to wait on, the copy of sub-chunk
+        // seq + n_slots leaves the moment slot seq % n_slots is free.
         const int lw = warp - kV5Tap;
         const long long my_images = blockIdx.x < a.n ? (a.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const long long total_seq = my_images * n_sub;
-        long long issued = 0;
-        auto issue_upto = [&](long long upto) {  // lane 0 of luma warp 0 only
-            for (; issued < upto && issued < total_seq; ++issued) {
-                const long long k = issued / n_sub;
-                const int s = (int)(issued - k * n_sub);
-                const int b = (int)(issued & slot_mask);
-                const int rows = min(sub_rows, a.h - s * sub_rows);
-                mbar_wait(&s_empty[b], (((uint32_t)(issued >> slot_shift)) & 1u) ^ 1u);
-                mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
-                bulk_g2s(s_raw + b * sub_bytes, a.img + (blockIdx.x + k * gridDim.x) * a.img_stride + (long long)s * sub_bytes,
-                         (uint32_t)(rows * row_bytes), &s_full[b]);
+        const uint32_t total_seq = (uint32_t)(my_images * n_sub);  // per-CTA sub-chunk count fits 32 bits (launch checks)
+        auto issue = [&](uint32_t q) {  // one lane: copy sub-chunk q of this CTA's stream into slot q % n_slots
+            const uint32_t k = q / (uint32_t)n_sub, sq = q - k * (uint32_t)n_sub;
+            const int b = (int)(q & slot_mask);
+            const int rows = min(sub_rows, a.h - (int)sq * sub_rows);
+            mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
+            bulk_g2s(s_raw + b * sub_bytes, a.img + (blockIdx.x + (long long)k * gridDim.x) * a.img_stride + (long long)sq * sub_bytes,
+                     (uint32_t)(rows * row_bytes), &s_full[b]);
+        };
+        auto release = [&](uint32_t seq_, int b) {  // lane 0, after the warp's reads of slot b (ordered by __syncwarp)
+            __threadfence_block();
+            const uint32_t old = atomicAdd(&s_cnt[b], 1u);
+            if ((old & (kV5Luma - 1)) == kV5Luma - 1) {
+                __threadfence_block();
+                if (seq_ + (uint32_t)n_slots < total_seq) issue(seq_ + (uint32_t)n_slots);
             }
         };
-        if (lw == 0 && lane == 0) issue_upto(n_slots - 1);
-        long long seq = 0;
+        if (lw == 0 && lane == 0)
+            for (uint32_t q = 0; q < (uint32_t)n_slots && q < total_seq; ++q) issue(q);
+        // early release: when a warp's share of a sub-chunk (<= 2 rows of <= 512 pixels) fits its registers the
+        // raw slot is handed back right after the loads, before the arithmetic
+        const bool early = (C == 3) && sub_rows <= 2 * kV5Luma && a.w <= 512;
+        const int ng = a.w >> 4;
+        const bool act = lane < ng;
+        const int src_off = lw * row_bytes + 48 * lane, dst_off = lw * pitch_bytes + 16 * lane;
+        uint32_t seq = 0;
         uint32_t chunk = 0;
         for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
             for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
                 const int lb = chunk & 1;
                 mbar_wait(&l_empty[lb], ((chunk >> 1) & 1u) ^ 1u);  // tap warps are done with this buffer
-                uint32_t* dst = reinterpret_cast<uint32_t*>(s_luma + lb * L.luma_bytes);
+                uint8_t* dst8 = s_luma + lb * L.luma_bytes;
                 for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
-                    if (lw == 0 && lane == 0) issue_upto(seq + n_slots);  // keep the ring n_slots-1 ahead
-                    __syncwarp();
                     const int b = (int)(seq & slot_mask);
                     const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
-                    mbar_wait(&s_full[b], ((uint32_t)(seq >> slot_shift)) & 1u);
+                    mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
                     if (dbg & 8) {  // tuning probe: the TMA feed alone
-                    } else if (C == 3)
-                        luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, reinterpret_cast<uint8_t*>(dst) + s * sub_rows * pitch_bytes,
-                                                 srows, a.w, row_bytes, pitch_bytes, lw, lane);
-                    else
-                        luma_rows_fast<C, kV5Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
-                                                   pitch_words, lw, lane);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive1(&s_empty[b]);
+                        __syncwarp();
+                        if (lane == 0) release(seq, b);
+                    } else if (early) {
+                        const bool one = act && lw < srows, two = act && lw + kV5Luma < srows;
+                        const uint4* p0 = reinterpret_cast<const uint4*>(s_raw + b * sub_bytes + src_off);
+                        const uint4* p1 = reinterpret_cast<const uint4*>(s_raw + b * sub_bytes + src_off + kV5Luma * row_bytes);
+                        uint4 x0[3], x1[3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            x0[i] = one ? p0[i] : make_uint4(0, 0, 0, 0);
+                            x1[i] = two ? p1[i] : make_uint4(0, 0, 0, 0);
+                        }
+                        __syncwarp();
+                        if (lane == 0) release(seq, b);
+                        uint8_t* d0 = dst8 + s * sub_rows * pitch_bytes + dst_off;
+                        if (one) *reinterpret_cast<uint4*>(d0) = luma16_rgb(x0[0], x0[1], x0[2]);
+                        if (two) *reinterpret_cast<uint4*>(d0 + kV5Luma * pitch_bytes) = luma16_rgb(x1[0], x1[1], x1[2]);
+                    } else {
+                        if (C == 3)
+                            luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, dst8 + s * sub_rows * pitch_bytes, srows, a.w,
+                                                     row_bytes, pitch_bytes, lw, lane);
+                        else
+                            luma_rows_fast<C, kV5Luma>(s_raw + b * sub_bytes,
+                                                       reinterpret_cast<uint32_t*>(dst8) + s * sub_rows * pitch_words, srows,
+                                                       a.w, pitch_words, lw, lane);
+                        __syncwarp();
+                        if (lane == 0) release(seq, b);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive1(&l_full[lb]);  // release: the chunk's luma rows are written
@@ -2022,7 +2054,7 @@ bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_by
         for (int shift : {want_shift, 2, 1}) {
             if (shift < 1 || shift > 3) continue;
             L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words);
-            if (L.total <= 113 * 1024) {
+            if (L.total <= 113 * 1024 && a.n * ((a.h + sub - 1) / sub) < (1ll << 31)) {
                 sub_rows = sub;
                 slot_shift = shift;
                 return true;
