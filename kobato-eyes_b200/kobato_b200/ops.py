@@ -264,6 +264,131 @@ def ssim_pairs(a, b) -> np.ndarray:
 # ----------------------------------------------------------------------------- helpers
 
 
+# ----------------------------------------------------------------------------- N1 (tile aHash / pixel MAE refinement)
+
+_FILTERS = {"lanczos": 1, "bilinear": 2, 1: 1, 2: 2}
+
+
+def _as_cuda_u8(images):
+    torch = _torch()
+    if _is_tensor(images):
+        if not images.is_cuda or images.dtype != torch.uint8:
+            raise ValueError("expected a CUDA uint8 tensor (or a numpy array)")
+        x = images
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(images, dtype=np.uint8)).cuda()
+    if x.dim() == 3:
+        x = x.unsqueeze(-1)
+    if x.dim() != 4 or x.shape[3] not in (1, 3, 4):
+        raise ValueError("images must be [n,h,w] or [n,h,w,c] with c in {1,3,4}")
+    if x.stride(3) != 1 or x.stride(2) != x.shape[3]:
+        x = x.contiguous()
+    return x
+
+
+def gray_resize_batch(images, out_w: int, out_h: int, filter="bilinear"):
+    """``convert("L").resize((out_w, out_h), filter)`` for a batch of decoded images, byte-identical to Pillow
+    (reference src/ui/dup_refine_parallel.py:66-69, :203-207).  Returns a CUDA uint8 tensor ``[n,out_h,out_w]``."""
+    torch = _torch()
+    lib = nat.load()
+    if filter not in _FILTERS:
+        raise ValueError("filter must be 'bilinear' or 'lanczos'")
+    x = _as_cuda_u8(images)
+    n, h, w, c = x.shape
+    out_w, out_h = int(out_w), int(out_h)
+    if out_w <= 0 or out_h <= 0:
+        raise ValueError("height and width must be > 0")  # Pillow's message for resize((0, n))
+    dev = x.device.index
+    mid = torch.empty((n, h, out_w), dtype=torch.uint8, device=x.device)
+    out = torch.empty((n, out_h, out_w), dtype=torch.uint8, device=x.device)
+    if n:
+        ctx = nat.context(dev)
+        with ctx.lock:
+            nat.check(lib.ke_gray_resize_batch(ctx.handle, x.data_ptr(), n, h, w, c, x.stride(0), x.stride(1), out_w, out_h,
+                                               _FILTERS[filter], mid.data_ptr(), out.data_ptr(), _stream_ptr(dev)),
+                      "ke_gray_resize_batch")
+    return out
+
+
+def tile_ahash_bits(planes, grid: int = 4, tile: int = 8):
+    """Tile-mean threshold bits of ``[n, grid*tile, grid*tile]`` uint8 planes (reference :71-83): returns an int32
+    CUDA tensor ``[n, words]`` whose little-endian bit string is the reference's packed integer."""
+    torch = _torch()
+    lib = nat.load()
+    x = planes if _is_tensor(planes) else torch.from_numpy(np.ascontiguousarray(planes, np.uint8)).cuda()
+    side = int(grid) * int(tile)
+    if x.dim() != 3 or x.shape[1] != side or x.shape[2] != side or x.dtype != torch.uint8:
+        raise ValueError(f"planes must be uint8 [n,{side},{side}]")
+    x = x.contiguous()
+    n = x.shape[0]
+    words = (side * side + 31) // 32
+    bits = torch.zeros((n, words), dtype=torch.int32, device=x.device)
+    if n:
+        dev = x.device.index
+        ctx = nat.context(dev)
+        with ctx.lock:
+            nat.check(lib.ke_tile_ahash_bits(ctx.handle, x.data_ptr(), n, int(grid), int(tile), bits.data_ptr(),
+                                             _stream_ptr(dev)), "ke_tile_ahash_bits")
+    return bits
+
+
+def bits_to_ints(bits) -> list[int]:
+    """``[n, words]`` int32 bit words -> Python ints (little endian), the reference's tile_ahash_bits values."""
+    arr = bits.cpu().numpy() if _is_tensor(bits) else np.asarray(bits)
+    raw = np.ascontiguousarray(arr.astype("<i4", copy=False)).view(np.uint8).reshape(arr.shape[0], -1)
+    return [int.from_bytes(row.tobytes(), "little") for row in raw]
+
+
+def _pair_index(ia, ib, m: int, device):
+    torch = _torch()
+    ia_t = torch.as_tensor(ia, dtype=torch.int64).to(device).contiguous()
+    ib_t = torch.as_tensor(ib, dtype=torch.int64).to(device).contiguous()
+    if ia_t.shape != ib_t.shape or ia_t.dim() != 1:
+        raise ValueError("ia and ib must be 1-D and of equal length")
+    n = ia_t.numel()
+    if n and (int(torch.max(torch.maximum(ia_t, ib_t))) >= m or int(torch.min(torch.minimum(ia_t, ib_t))) < 0):
+        raise ValueError("pair index out of range")
+    return ia_t, ib_t, n
+
+
+def bits_hamming_pairs(bits, ia, ib):
+    """popcount(bits[ia] ^ bits[ib]) per pair (reference tile_hamming :86-88) -> int32 CUDA tensor."""
+    torch = _torch()
+    lib = nat.load()
+    if not (_is_tensor(bits) and bits.is_cuda and bits.dtype == torch.int32 and bits.dim() == 2):
+        raise ValueError("bits must be the int32 CUDA tensor returned by tile_ahash_bits")
+    b = bits.contiguous()
+    ia_t, ib_t, n = _pair_index(ia, ib, b.shape[0], b.device)
+    out = torch.empty(n, dtype=torch.int32, device=b.device)
+    if n:
+        dev = b.device.index
+        ctx = nat.context(dev)
+        with ctx.lock:
+            nat.check(lib.ke_bits_hamming_pairs(ctx.handle, b.data_ptr(), b.shape[1], ia_t.data_ptr(), ib_t.data_ptr(), n,
+                                                out.data_ptr(), _stream_ptr(dev)), "ke_bits_hamming_pairs")
+    return out
+
+
+def plane_sad_pairs(planes, ia, ib):
+    """sum |planes[ia] - planes[ib]| per pair -> int64 CUDA tensor; reference ``_mae01`` (:210-212) is
+    ``sad / plane.size / 255.0``."""
+    torch = _torch()
+    lib = nat.load()
+    if not (_is_tensor(planes) and planes.is_cuda and planes.dtype == torch.uint8 and planes.dim() >= 2):
+        raise ValueError("planes must be a CUDA uint8 tensor [m, ...]")
+    x = planes.contiguous()
+    plane_bytes = int(x[0].numel()) if x.shape[0] else 1
+    ia_t, ib_t, n = _pair_index(ia, ib, x.shape[0], x.device)
+    out = torch.empty(n, dtype=torch.int64, device=x.device)
+    if n:
+        dev = x.device.index
+        ctx = nat.context(dev)
+        with ctx.lock:
+            nat.check(lib.ke_plane_sad_pairs(ctx.handle, x.data_ptr(), plane_bytes, ia_t.data_ptr(), ib_t.data_ptr(), n,
+                                             out.data_ptr(), _stream_ptr(dev)), "ke_plane_sad_pairs")
+    return out
+
+
 def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n_set: int = 1 << 30,
                         seed: int | None = None, planted: float = 0.05, device=None, out=None):
     """CUDA twin of ``synth.synth_image`` (identical bytes) -> uint8 CUDA tensor [count,h,w,c]."""

@@ -322,3 +322,39 @@ def bucket_pair_cap_from_env() -> int | None:
     except ValueError:
         return None
     return v if v > 0 else None
+
+
+# ---------------------------------------------------------------------------------------------------
+# N1: the refinement the shipped UI runs after a scan (src/ui/dup_refine_parallel.py)
+
+
+def tile_ahash_bits_image(image, grid: int = 4, tile: int = 8) -> int:
+    """src/ui/dup_refine_parallel.py:59-83 after the file is open (exif_transpose is the caller's):
+    convert("L").resize((side, side), BILINEAR), per-tile mean threshold, bits in (gy, gx, ty, tx) order,
+    little-endian packed integer."""
+    from PIL import Image
+
+    side = grid * tile
+    gray = image.convert("L").resize((side, side), Image.Resampling.BILINEAR)
+    arr = np.asarray(gray, dtype=np.uint8)
+    a = arr.reshape(grid, tile, grid, tile).transpose(0, 2, 1, 3)
+    means = a.mean(axis=(2, 3), keepdims=True)
+    bits = (a > means).reshape(-1).astype(np.uint8)
+    return int.from_bytes(np.packbits(bits, bitorder="little").tobytes(), "little")
+
+
+def tile_hamming(a_bits: int, b_bits: int) -> int:
+    """src/ui/dup_refine_parallel.py:86-88."""
+    return (int(a_bits) ^ int(b_bits)).bit_count()
+
+
+def small_gray(image, size: int = 128) -> np.ndarray:
+    """src/ui/dup_refine_parallel.py:203-207 after the file is open."""
+    from PIL import Image
+
+    return np.asarray(image.convert("L").resize((size, size), Image.Resampling.BILINEAR), dtype=np.uint8)
+
+
+def mae01(a: np.ndarray, b: np.ndarray) -> float:
+    """src/ui/dup_refine_parallel.py:210-212."""
+    return float(np.mean(np.abs(a.astype(np.int16) - b.astype(np.int16))) / 255.0)

@@ -10,6 +10,8 @@ Writes
   scanner_golden.json  dup.scanner.DuplicateScanner.build_clusters on seeded hash sets
   ssim_golden.json     oracle.ref_py SSIM restatement values (scikit-image is NOT installable
                        here, so these pin the restatement against drift, not the reference)
+  n1_golden.json       ui.dup_refine_parallel.tile_ahash_bits / _load_small_gray / _mae01 (reference, PIL) on
+                       seeded synthetic PNG files
 plus the library versions they were produced with.
 """
 from __future__ import annotations
@@ -163,7 +165,50 @@ def gen_ssim():
     print("ssim", out)
 
 
+# (h, w, c) of the files behind the N1 vectors, (grid, tile) of the tile aHash, thumb sizes of the pixel pass
+N1_IMAGES = [(512, 512, 3), (300, 200, 3), (33, 47, 3), (100, 33, 1), (480, 640, 4), (64, 64, 3), (32, 32, 1), (31, 29, 3),
+             (128, 128, 1), (700, 45, 3)]
+N1_TILES = [(4, 8), (8, 8), (16, 16), (3, 5), (1, 7)]
+N1_THUMBS = [128, 32, 7]
+
+
+def gen_n1():
+    import hashlib
+    import tempfile
+
+    from PIL import Image
+    from ui import dup_refine_parallel as ref
+
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for k, (h, w, c) in enumerate(N1_IMAGES):
+            arr = synth.synth_image(1000 + k, h, w, c, n_set=1 << 30)
+            path = Path(tmp) / f"n1_{k}.png"
+            Image.fromarray(arr if c > 1 else arr[..., 0] if arr.ndim == 3 else arr, MODES[c]).save(path, format="PNG")
+            paths.append(path)
+            case = {"index": 1000 + k, "h": h, "w": w, "c": c, "tile_bits": {}, "small_gray_sha256": {}}
+            for grid, tile in N1_TILES:
+                v = ref.tile_ahash_bits(path, grid=grid, tile=tile)
+                nbits = (grid * tile) ** 2
+                # long bit strings are stored as the sha256 of their little-endian bytes
+                case["tile_bits"][f"{grid}x{tile}"] = hex(v) if nbits <= 1024 else \
+                    "sha256:" + hashlib.sha256(v.to_bytes((nbits + 7) // 8, "little")).hexdigest()
+            for size in N1_THUMBS:
+                plane = ref._load_small_gray(path, size=size)
+                case["small_gray_sha256"][str(size)] = hashlib.sha256(plane.tobytes()).hexdigest()
+            cases.append(case)
+        mae = []
+        for a, b in ((0, 1), (0, 5), (2, 3), (6, 8), (4, 9)):
+            for size in (128, 32):
+                mae.append({"a": a, "b": b, "size": size,
+                            "mae": ref._mae01(ref._load_small_gray(paths[a], size), ref._load_small_gray(paths[b], size))})
+    (HERE / "n1_golden.json").write_text(json.dumps({"versions": versions(), "cases": cases, "mae": mae}, indent=1))
+    print("n1", len(cases), "files", len(mae), "mae pairs")
+
+
 if __name__ == "__main__":
+    gen_n1()
     gen_phash()
     gen_scanner()
     gen_ssim()
