@@ -20,6 +20,8 @@
 // exchange at all.
 //
 // Algorithmic HBM bytes per pair: 2*h*w*c read + 8 written.
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "ke_common.cuh"
@@ -268,6 +270,236 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2: four output columns per thread.
+//
+// The v1 kernel (thread = one output column) is bound by instruction issue: per pixel it loads six
+// words, realigns them with four PRMT and evaluates the point formula on scalars.  Here a thread owns the
+// outputs x0..x0+3 (x0 = 4 tid): the three words per image and row are loaded ONCE for the four windows
+// (bytes x0..x0+9), the window of output 0 is word aligned (no PRMT), and the point formula runs on
+// output PAIRS with the packed FP32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2).  A unit is still
+// (pair, 256 output columns), now walked by 64 threads; the 7-row ring lives in registers (84 of them).
+
+constexpr int kT4 = 64;
+
+__device__ __forceinline__ HSum hsum7_words(uint32_t ua, uint32_t ub, uint32_t va, uint32_t vb) {
+    const uint32_t ubm = ub & 0x00FFFFFFu, vbm = vb & 0x00FFFFFFu;
+    HSum r;
+    const uint32_t su = dp4a_uu(ua, 0x01010101u, dp4a_uu(ub, 0x00010101u, 0u));
+    const uint32_t sv = dp4a_uu(va, 0x01010101u, dp4a_uu(vb, 0x00010101u, 0u));
+    r.s = su + (sv << 16);
+    r.t = dp4a_uu(ua, ua, dp4a_uu(ub, ubm, dp4a_uu(va, va, dp4a_uu(vb, vbm, 0u))));
+    r.uv = dp4a_uu(ua, va, dp4a_uu(ub, vbm, 0u));
+    return r;
+}
+
+// SSIM of two neighbouring windows from their exact integer sums (same arithmetic as ssim_point)
+__device__ __forceinline__ float2 ssim_point2(uint32_t s0, uint32_t t0, uint32_t uv0, uint32_t s1, uint32_t t1, uint32_t uv1) {
+    constexpr float C1 = 1e-4f * 49.0f * 49.0f * 255.0f * 255.0f;
+    constexpr float C2 = 9e-4f * 48.0f * 49.0f * 255.0f * 255.0f;
+    const int a0 = (int)(s0 & 0xFFFFu), b0 = (int)(s0 >> 16), a1 = (int)(s1 & 0xFFFFu), b1 = (int)(s1 >> 16);
+    const int p0 = a0 * b0, p1 = a1 * b1;
+    const int q0 = a0 * a0 + b0 * b0, q1 = a1 * a1 + b1 * b1;
+    const int x0 = 49 * (int)uv0 - p0, x1 = 49 * (int)uv1 - p1;
+    const int v0 = 49 * (int)t0 - q0, v1 = 49 * (int)t1 - q1;
+    const float2 two = make_float2(2.0f, 2.0f), c1 = make_float2(C1, C1), c2 = make_float2(C2, C2);
+    const float2 A1 = __ffma2_rn(two, make_float2((float)p0, (float)p1), c1);
+    const float2 A2 = __ffma2_rn(two, make_float2((float)x0, (float)x1), c2);
+    const float2 B1 = __fadd2_rn(make_float2((float)q0, (float)q1), c1);
+    const float2 B2 = __fadd2_rn(make_float2((float)v0, (float)v1), c2);
+    const float2 num = __fmul2_rn(A1, A2), den = __fmul2_rn(B1, B2);  // den >= c1*c2 > 0, far from the rcp range limits
+    float rx, ry;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(den.y));
+    return __fmul2_rn(num, make_float2(rx, ry));
+}
+
+template <int C>
+__global__ void __launch_bounds__(kT4) ke_ssim4_kernel(const SsimArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int strip_bytes = (kStripRows * a.pitch + 32 + 127) / 128 * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * strip_bytes);
+    __shared__ double s_red[kT4 / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity[2] = {0u, 0u};
+    const int n_strips = (a.h + kStripRows - 1) / kStripRows;
+    const long long n_units = a.n_pairs * a.n_cblocks;
+
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long pair = unit / a.n_cblocks;
+        const int cb = (int)(unit - pair * a.n_cblocks);
+        const int col0 = cb * kBlockCols;
+        const int out_cols = min(kBlockCols, (a.w - 6) - col0);
+        const int in_cols = out_cols + 6;
+        const uint8_t* img_u = a.bank + a.ia[pair] * a.img_stride;
+        const uint8_t* img_v = a.bank + a.ib[pair] * a.img_stride;
+
+        auto load_strip = [&](int s) {
+            const int buf = s & 1;
+            const int r0 = s * kStripRows;
+            const int rows = min(kStripRows, a.h - r0);
+            uint8_t* du = smem + (2 * buf) * strip_bytes;
+            uint8_t* dv = smem + (2 * buf + 1) * strip_bytes;
+            if (a.use_bulk) {
+                if (tid == 0) {
+                    const uint32_t bytes = (uint32_t)(rows * a.w);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&bars[buf], 2u * bytes);
+                    bulk_g2s(du, img_u + (long long)r0 * a.row_stride, bytes, &bars[buf]);
+                    bulk_g2s(dv, img_v + (long long)r0 * a.row_stride, bytes, &bars[buf]);
+                }
+            } else {
+                int x_done = 0;
+                if (C == 3 && a.rgb_words) {
+                    constexpr uint32_t LO = 0x002F468Bu, HI = 0x001D964Cu;
+                    const int groups = in_cols >> 2;
+                    x_done = groups << 2;
+                    for (int idx = tid; idx < rows * groups; idx += kT4) {
+                        const int r = idx / groups, q = idx - r * groups;
+                        const long long g = (long long)(r0 + r) * a.row_stride + (long long)col0 * 3 + (long long)q * 12;
+#pragma unroll
+                        for (int im = 0; im < 2; ++im) {
+                            const uint32_t* src = reinterpret_cast<const uint32_t*>((im ? img_v : img_u) + g);
+                            const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+                            const uint32_t l0 = dp4a_uu(w0, LO, 0x8000u), h0 = dp4a_uu(w0, HI, 0u);
+                            uint32_t l1 = dp4a_uu(w0, LO << 24, 0x8000u), h1 = dp4a_uu(w0, HI << 24, 0u);
+                            l1 = dp4a_uu(w1, LO >> 8, l1), h1 = dp4a_uu(w1, HI >> 8, h1);
+                            uint32_t l2 = dp4a_uu(w1, LO << 16, 0x8000u), h2 = dp4a_uu(w1, HI << 16, 0u);
+                            l2 = dp4a_uu(w2, LO >> 16, l2), h2 = dp4a_uu(w2, HI >> 16, h2);
+                            const uint32_t l3 = dp4a_uu(w2, LO << 8, 0x8000u), h3 = dp4a_uu(w2, HI << 8, 0u);
+                            const uint32_t s0 = l0 + (h0 << 8), s1 = l1 + (h1 << 8), s2 = l2 + (h2 << 8), s3 = l3 + (h3 << 8);
+                            const uint32_t packed = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+                            *reinterpret_cast<uint32_t*>((im ? dv : du) + r * a.pitch + 4 * q) = packed;
+                        }
+                    }
+                }
+                const int tail = in_cols - x_done;
+                for (int idx = tid; idx < rows * tail; idx += kT4) {
+                    const int r = idx / tail, x = x_done + (idx - r * tail);
+                    const long long g = (long long)(r0 + r) * a.row_stride + (long long)(col0 + x) * C;
+                    du[r * a.pitch + x] = luma_of<C>(img_u + g);
+                    dv[r * a.pitch + x] = luma_of<C>(img_v + g);
+                }
+                __syncthreads();
+                if (tid == 0) mbar_arrive(&bars[buf]);
+            }
+        };
+
+        HSum ring[4][kWin];
+        uint32_t acc_s[4], acc_t[4], acc_uv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc_s[j] = acc_t[j] = acc_uv[j] = 0u;
+#pragma unroll
+            for (int i = 0; i < kWin; ++i) ring[j][i] = HSum{0u, 0u, 0u};
+        }
+        double total = 0.0;
+        const int x0 = 4 * tid;
+        const bool active = x0 < out_cols;
+        // outputs past the last valid column read padding / the next row's bytes: computed, then masked out
+        const float m0 = x0 < out_cols ? 1.f : 0.f, m1 = x0 + 1 < out_cols ? 1.f : 0.f, m2 = x0 + 2 < out_cols ? 1.f : 0.f,
+                    m3 = x0 + 3 < out_cols ? 1.f : 0.f;
+
+        __syncthreads();  // every thread is done with the previous unit's buffers
+        load_strip(0);
+        for (int s = 0; s < n_strips; ++s) {
+            const int buf = s & 1;
+            if (s + 1 < n_strips) load_strip(s + 1);
+            mbar_wait(&bars[buf], parity[buf]);
+            parity[buf] ^= 1u;
+            const int r0 = s * kStripRows;
+            const int rows = min(kStripRows, a.h - r0);
+            const uint32_t* su = reinterpret_cast<const uint32_t*>(smem + (2 * buf) * strip_bytes) + tid;
+            const uint32_t* sv = reinterpret_cast<const uint32_t*>(smem + (2 * buf + 1) * strip_bytes) + tid;
+            const int pw = a.pitch >> 2;
+            float part = 0.f;
+            if (active) {
+                auto group = [&](int rb, auto steady) {
+                    constexpr bool STEADY = decltype(steady)::value;
+#pragma unroll
+                    for (int k = 0; k < kWin; ++k) {
+                        const int r = rb + k;  // (r0 + r) % 7 == k because strips are multiples of 7
+                        if (STEADY || r < rows) {
+                            const uint32_t* pu = su + r * pw;
+                            const uint32_t* pv = sv + r * pw;
+                            const uint32_t u0 = pu[0], u1 = pu[1], u2 = pu[2];
+                            const uint32_t v0 = pv[0], v1 = pv[1], v2 = pv[2];
+                            ring[0][k] = hsum7_words(u0, u1, v0, v1);
+                            ring[1][k] = hsum7_words(__byte_perm(u0, u1, 0x4321), __byte_perm(u1, u2, 0x4321),
+                                                     __byte_perm(v0, v1, 0x4321), __byte_perm(v1, v2, 0x4321));
+                            ring[2][k] = hsum7_words(__byte_perm(u0, u1, 0x5432), __byte_perm(u1, u2, 0x5432),
+                                                     __byte_perm(v0, v1, 0x5432), __byte_perm(v1, v2, 0x5432));
+                            ring[3][k] = hsum7_words(__byte_perm(u0, u1, 0x6543), __byte_perm(u1, u2, 0x6543),
+                                                     __byte_perm(v0, v1, 0x6543), __byte_perm(v1, v2, 0x6543));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc_s[j] += ring[j][k].s;
+                                acc_t[j] += ring[j][k].t;
+                                acc_uv[j] += ring[j][k].uv;
+                            }
+                            if (STEADY || r0 + r >= kWin - 1) {
+                                const float2 e01 = ssim_point2(acc_s[0], acc_t[0], acc_uv[0], acc_s[1], acc_t[1], acc_uv[1]);
+                                const float2 e23 = ssim_point2(acc_s[2], acc_t[2], acc_uv[2], acc_s[3], acc_t[3], acc_uv[3]);
+                                const float2 sm = __ffma2_rn(e23, make_float2(m2, m3), __fmul2_rn(e01, make_float2(m0, m1)));
+                                part += sm.x + sm.y;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc_s[j] -= ring[j][(k + 1) % kWin].s;
+                                acc_t[j] -= ring[j][(k + 1) % kWin].t;
+                                acc_uv[j] -= ring[j][(k + 1) % kWin].uv;
+                            }
+                        }
+                    }
+                };
+                for (int rb = 0; rb < rows; rb += kWin) {
+                    if (r0 + rb >= kWin && rb + kWin <= rows) group(rb, std::true_type{});
+                    else group(rb, std::false_type{});
+                }
+            }
+            total += (double)part;
+            __syncthreads();  // strip buffer `buf` may be refilled
+        }
+
+#pragma unroll
+        for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+        if (lane == 0) s_red[warp] = total;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kT4 / 32; ++i) t += s_red[i];
+            if (a.n_cblocks == 1) a.out[pair] = t * a.inv_count;
+            else atomicAdd(&a.out[pair], t * a.inv_count);
+        }
+    }
+}
+
+template <int C>
+int launch_ssim4(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
+    const int strip_bytes = (kStripRows * a.pitch + 32 + 127) / 128 * 128;
+    const int smem = 4 * strip_bytes + 16;
+    KE_CUDA(cudaFuncSetAttribute(ke_ssim4_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_ssim4_kernel<C>, kT4, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long units = a.n_pairs * a.n_cblocks;
+    if (grid > units) grid = units;
+    ke_ssim4_kernel<C><<<(unsigned)grid, kT4, smem, s>>>(a);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 template <int C>
 int launch_ssim(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
     const int strip_bytes = (kStripRows * a.pitch + 16 + 127) / 128 * 128;
@@ -321,10 +553,20 @@ extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, i
     a.inv_count = 1.0 / ((double)(h - 6) * (double)(w - 6));
     a.out = d_ssim;
     if (a.n_cblocks > 1) KE_CUDA(cudaMemsetAsync(d_ssim, 0, (size_t)n_pairs * sizeof(double), s));
+    const char* which = getenv("KE_SSIM_KERNEL");  // "v1": one output column per thread (the first kernel)
+    if (which && !strcmp(which, "v1")) {
+        switch (c) {
+            case 1: return launch_ssim<1>(ctx, a, s);
+            case 3: return launch_ssim<3>(ctx, a, s);
+            default: return launch_ssim<4>(ctx, a, s);
+        }
+    }
+    // v2 reads up to 11 bytes past a thread's first column: keep the strip rows that much longer than the block
+    if (!a.use_bulk) a.pitch = (std::min(w, kBlockCols + 6) + 3) / 4 * 4 + 12;
     switch (c) {
-        case 1: return launch_ssim<1>(ctx, a, s);
-        case 3: return launch_ssim<3>(ctx, a, s);
-        default: return launch_ssim<4>(ctx, a, s);
+        case 1: return launch_ssim4<1>(ctx, a, s);
+        case 3: return launch_ssim4<3>(ctx, a, s);
+        default: return launch_ssim4<4>(ctx, a, s);
     }
 }
 
