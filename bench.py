@@ -342,7 +342,7 @@ def run_cuda(args) -> dict:
     k3_ms = float(k3.item())
     k3_bytes = n_pairs * (2 * 256 * 256 + 8)
     k3_gbs = k3_bytes / (k3_ms_local * 1e-3) / 1e9
-    roof_k3 = {"kernel": "ke_ssim_kernel<1>", "bound": "hbm", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roof_k3 = {"kernel": "ke_ssim4_kernel<1> (4 output columns per thread, packed FP32)", "bound": "hbm", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k3_gbs / hbm_peak, "pairs_per_s": world * n_pairs / (k3_ms * 1e-3), "shape": "256x256 L",
                "pairs": world * n_pairs, "bank_images": m_bank, "ms": k3_ms, "peak_source": peak_src}
     del crops, bank_l, ia, ib, hashes
