@@ -553,8 +553,12 @@ extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, i
     a.inv_count = 1.0 / ((double)(h - 6) * (double)(w - 6));
     a.out = d_ssim;
     if (a.n_cblocks > 1) KE_CUDA(cudaMemsetAsync(d_ssim, 0, (size_t)n_pairs * sizeof(double), s));
-    const char* which = getenv("KE_SSIM_KERNEL");  // "v1": one output column per thread (the first kernel)
-    if (which && !strcmp(which, "v1")) {
+    // v2 (four output columns per thread) wins where the strips arrive by TMA; on the staged paths (RGB banks, planes
+    // wider than one column block) its 64-thread CTAs hide the global-load latency of the staging loop worse than
+    // v1's 256 threads do (measured: 4.3 vs 3.7 ms on the C2 step's 3.6k pairs of 512x512 RGB), so those stay on v1.
+    const char* which = getenv("KE_SSIM_KERNEL");  // tuning override: "v1" | "v2"
+    const bool use_v1 = which ? !strcmp(which, "v1") : !a.use_bulk;
+    if (use_v1) {
         switch (c) {
             case 1: return launch_ssim<1>(ctx, a, s);
             case 3: return launch_ssim<3>(ctx, a, s);

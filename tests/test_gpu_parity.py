@@ -338,6 +338,30 @@ def test_ssim_scale_properties_at_bench_size():
         assert abs(float(s_ab[k]) - want) <= SSIM_TOL
 
 
+def test_ssim_both_kernels_agree_with_the_oracle():
+    """K3 has two kernels (v1: one output column per thread; v2: four, packed FP32); either may serve any shape."""
+    import os
+
+    torch = _torch()
+    for (h, w, c) in ((256, 256, 1), (64, 80, 1), (7, 7, 1), (300, 520, 1), (96, 128, 3), (512, 512, 3), (40, 271, 4), (33, 1030, 1)):
+        n = 12
+        imgs = synth.synth_images(0, n, h, w, c, n_set=n, planted=0.5)
+        bank = torch.from_numpy(imgs).cuda()
+        ia, ib = list(range(0, n, 2)) + [0], list(range(1, n, 2)) + [0]
+        got = {}
+        for kernel in ("v1", "v2"):
+            os.environ["KE_SSIM_KERNEL"] = kernel
+            try:
+                got[kernel] = ops.ssim_batch(bank, ia, ib).cpu().numpy()
+            finally:
+                os.environ.pop("KE_SSIM_KERNEL", None)
+        assert np.abs(got["v1"] - got["v2"]).max() <= 2e-6, (h, w, c)
+        for k, (i, j) in enumerate(zip(ia, ib)):
+            want = ref_py.ssim_of_planes(oracle.to_l(imgs[i]), oracle.to_l(imgs[j]))
+            assert abs(got["v2"][k] - want) <= SSIM_TOL and abs(got["v1"][k] - want) <= SSIM_TOL, (h, w, c, k)
+        assert abs(got["v2"][-1] - 1.0) < 1e-6
+
+
 def test_phash_fast_and_generic_kernels_agree():
     """K1 has two kernels (fast: aligned contiguous rows; generic: everything else); on geometries both
     accept they must produce identical planes and hashes."""
@@ -355,7 +379,7 @@ def test_phash_fast_and_generic_kernels_agree():
             gen = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
         finally:
             ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
-        for kernel in ("v5", "v4", "v3", "fast"):  # the library falls back by itself when a kernel does not take the shape
+        for kernel in ("v5", "v4", "v3", "fast"):  # the library falls back by itself  # the library falls back by itself when a kernel does not take the shape
             os.environ["KE_PHASH_KERNEL"] = kernel
             try:
                 got = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
