@@ -1735,7 +1735,7 @@ struct V5Layout {
     int raw, luma, bfrag, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
 };
 
-__host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, int n_slots, int mma_words) {
+__host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, int n_slots, int mma_words /* of warps 4..7 */) {
     V5Layout L;
     int off = 0;
     auto take = [&](int bytes, int align) {
@@ -1837,6 +1837,40 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
     }
 }
 
+
+// Wide-target warps keep their B fragments (3 digits x <= kNKP k-steps) in REGISTERS for the whole kernel: no
+// shared-memory table, no LDS per MMA.  One 16-row block at a time keeps the accumulators at 12 registers.
+constexpr int kNKP = 8;
+__device__ __forceinline__ void v5_taps_wide_reg(uint32_t a_addr, const uint2 (&breg)[kNKP][3], int nk, int pitch_bytes,
+                                                 uint8_t* __restrict__ hrow, int out0, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        int32_t c[3][4];
+#pragma unroll
+        for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[tl][i] = tl == 0 ? (1 << (kPrec - 1)) : 0;
+#pragma unroll
+        for (int k = 0; k < kNKP; ++k) {
+            if (k < nk) {
+                uint32_t a0[4];
+                ldmatrix_x4(a0, a_addr + k * 32 + rb * 16 * pitch_bytes);
+#pragma unroll
+                for (int tl = 0; tl < 3; ++tl) mma_u8s8(c[tl], a0, breg[k][tl]);
+            }
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int32_t v0 = c[0][2 * hf] + (c[1][2 * hf] << 8) + (c[2][2 * hf] << 16);
+            const int32_t v1 = c[0][2 * hf + 1] + (c[1][2 * hf + 1] << 8) + (c[2][2 * hf + 1] << 16);
+            const int row = rb * 16 + hf * 8 + g;
+            hrow[(out0 + 2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
+            hrow[(out0 + 2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
+        }
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows,
                                                                    const int slot_shift, const int pitch_bytes,
@@ -1847,7 +1881,8 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     const int sub_bytes = sub_rows * row_bytes;
     const int n_slots = 1 << slot_shift;
     const uint32_t slot_mask = (uint32_t)n_slots - 1u;
-    const V5Layout L = v5_layout(sub_bytes, pitch_bytes, n_slots, a.mma_words);
+    const int b_first = a.mma_boff[4];  // the wide-target warps' fragments live in registers, not here
+    const V5Layout L = v5_layout(sub_bytes, pitch_bytes, n_slots, a.mma_words - b_first);
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
@@ -1878,7 +1913,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < a.mma_words; i += kV5Threads) s_b[i] = __ldg(a.mma_b + i);
+    for (int i = tid; i < a.mma_words - b_first; i += kV5Threads) s_b[i] = __ldg(a.mma_b + b_first + i);
     for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
     for (int i = tid; i < 2 * kHCols * kHP / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_hrow)[i] = 0u;
     __syncthreads();
@@ -1964,20 +1999,47 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     }
 
     // ===== tap warps =====
-    const uint2* bw = s_b + a.mma_boff[warp] + lane;
     const int nk = (dbg & 2) ? 0 : a.mma_nk[warp];
     const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mma_k0[warp] * 32);
+    const uint32_t poll_ns = (uint32_t)dbg >> 8;
+    if (warp < 4) {
+        // ---- wide target (32 outputs): outputs 8 warp .. 8 warp + 7, B fragments in registers
+        uint2 breg[kNKP][3];
+#pragma unroll
+        for (int k = 0; k < kNKP; ++k)
+#pragma unroll
+            for (int tl = 0; tl < 3; ++tl)
+                breg[k][tl] = k < a.mma_nk[warp] ? __ldg(a.mma_b + a.mma_boff[warp] + (k * 3 + tl) * 32 + lane) : make_uint2(0u, 0u);
+        uint32_t chunk = 0;
+        for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
+                const int lb = chunk & 1;
+                mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, poll_ns);
+                v5_taps_wide_reg(smem_u32(s_luma + lb * L.luma_bytes) + a_off, breg, nk, pitch_bytes,
+                                 s_hrow + lb * (kHCols * kHP), 8 * warp, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
+                compute_sync<NW>();                          // the row plane of this chunk is complete
+            }
+            compute_sync<NW>();  // the planes are written (by warps 4..7)
+            dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
+        }
+        return;
+    }
+
+    // ---- narrow target (9 outputs) + the vertical pass of both targets
     // Vertical pass, also on the tensor pipe: out[yy, x] = sum_y V[yy, y] * hrow[y, x] per 32-row chunk is one
     // k-step of mma.m16n8k32.s8.u8 (A = tap digits from the per-height table, B = the transposed row plane).
     // The accumulators live in warps 4..7 for the whole image: (unit, 8-column tile) pairs
     //   warp 4: (0,0) (0,1) (0,2)   warp 5: (0,3) (1,0) (1,1)   warp 6: (1,2) (1,3)   warp 7: (2,0) (2,1)
+    const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
     constexpr int NVP = 3;
     int32_t vc[NVP][3][4];
     int v_unit[NVP], v_nt[NVP];
 #pragma unroll
     for (int p = 0; p < NVP; ++p) {
         const int idx = (warp - 4) * 3 + p;  // warps 4,5: pairs 0..5; warp 6: 6,7; warp 7: unit 2
-        v_unit[p] = warp < 4 ? -1 : (warp == 7 ? (p < 2 ? 2 : -1) : (idx < 8 ? idx >> 2 : -1));
+        v_unit[p] = warp == 7 ? (p < 2 ? 2 : -1) : (idx < 8 ? idx >> 2 : -1);
         v_nt[p] = warp == 7 ? 4 + p : (idx & 3);
     }
     const int g = lane >> 2, t = lane & 3;
@@ -1993,17 +2055,16 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci) {
             const int lb = chunk & 1;
             uint8_t* hrow = s_hrow + lb * (kHCols * kHP);
-            mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, (uint32_t)dbg >> 8);
+            mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, poll_ns);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
-            if (warp < 4) v5_taps<3, true>(a_addr, bw, nk, pitch_bytes, hrow, 8 * warp, lane);
-            else if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
+            if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
             else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 6, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
             compute_sync<NW>();
             // the row plane is double buffered: the next chunk's epilogue writes the other half, and the
             // half read here is rewritten only after the next chunk's barrier
-            if (warp >= 4 && !(dbg & 4)) {
+            if (!(dbg & 4)) {
 #pragma unroll
                 for (int p = 0; p < NVP; ++p) {
                     const int u = v_unit[p];
@@ -2017,23 +2078,21 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             }
         }
         // planes from the vertical accumulators
-        if (warp >= 4) {
 #pragma unroll
-            for (int p = 0; p < NVP; ++p) {
-                const int u = v_unit[p];
-                if (u < 0) continue;
+        for (int p = 0; p < NVP; ++p) {
+            const int u = v_unit[p];
+            if (u < 0) continue;
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int32_t v0 = vc[p][0][2 * hf] + (vc[p][1][2 * hf] << 8) + (vc[p][2][2 * hf] << 16);
-                    const int32_t v1 = vc[p][0][2 * hf + 1] + (vc[p][1][2 * hf + 1] << 8) + (vc[p][2][2 * hf + 1] << 16);
-                    const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
-                    if (u < 2) {
-                        *reinterpret_cast<uint16_t*>(s_x32 + (u * 16 + hf * 8 + g) * 32 + v_nt[p] * 8 + 2 * t) = (uint16_t)pk;
-                    } else if (hf == 0) {  // 8x9 plane: rows g, columns (nt-4)*8 + 2t (+1) < 9
-                        const int x = (v_nt[p] - 4) * 8 + 2 * t;
-                        if (x < kDW) s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
-                        if (x + 1 < kDW) s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
-                    }
+            for (int hf = 0; hf < 2; ++hf) {
+                const int32_t v0 = vc[p][0][2 * hf] + (vc[p][1][2 * hf] << 8) + (vc[p][2][2 * hf] << 16);
+                const int32_t v1 = vc[p][0][2 * hf + 1] + (vc[p][1][2 * hf + 1] << 8) + (vc[p][2][2 * hf + 1] << 16);
+                const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+                if (u < 2) {
+                    *reinterpret_cast<uint16_t*>(s_x32 + (u * 16 + hf * 8 + g) * 32 + v_nt[p] * 8 + 2 * t) = (uint16_t)pk;
+                } else if (hf == 0) {  // 8x9 plane: rows g, columns (nt-4)*8 + 2t (+1) < 9
+                    const int x = (v_nt[p] - 4) * 8 + 2 * t;
+                    if (x < kDW) s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+                    if (x + 1 < kDW) s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
                 }
             }
         }
@@ -2046,6 +2105,8 @@ template <int C>
 bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V5Layout& L) {
     const long long row_bytes = (long long)a.w * C;
     if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.mma_words < 1 || !a.vmma) return false;
+    for (int q = 0; q < 4; ++q)
+        if (a.mma_nk[q] > kNKP) return false;  // wide-target B fragments must fit the register file
     pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
     int want_sub = 8, want_shift = 2;
     if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d", &want_sub, &want_shift);  // tuning override
@@ -2053,7 +2114,7 @@ bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_by
         if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
         for (int shift : {want_shift, 2, 1}) {
             if (shift < 1 || shift > 3) continue;
-            L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words);
+            L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words - a.mma_boff[4]);
             if (L.total <= 113 * 1024 && a.n * ((a.h + sub - 1) / sub) < (1ll << 31)) {
                 sub_rows = sub;
                 slot_shift = shift;
