@@ -2,6 +2,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <algorithm>
+#include <vector>
+
 #include "ke_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -165,5 +168,72 @@ extern "C" int ke_resample_table(int in_size, int out_size, int32_t* kk, int32_t
         bounds[2 * o] = first;
         bounds[2 * o + 1] = count;
     }
+    return KE_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Host union-find over accepted pairs: representative = smallest id of the component.
+
+extern "C" int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int64_t n_pairs, int64_t* h_nodes,
+                                     int64_t* h_node_rep, int64_t* n_nodes) {
+    KE_REQUIRE(n_pairs >= 0 && n_nodes != nullptr, "ke_cluster_pairs_host: bad arguments");
+    *n_nodes = 0;
+    if (n_pairs == 0) return KE_OK;
+    KE_REQUIRE(h_a && h_b && h_nodes && h_node_rep, "ke_cluster_pairs_host: NULL buffer");
+    int64_t lo = h_a[0], hi = h_a[0];
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        lo = std::min(lo, std::min(h_a[k], h_b[k]));
+        hi = std::max(hi, std::max(h_a[k], h_b[k]));
+    }
+    // slot of an id: direct index when the id range is compact (table indices), else rank among the sorted ids
+    const bool direct = (hi - lo) >= 0 && (hi - lo) < 64 * n_pairs + 4096;
+    std::vector<int64_t> ids;
+    std::vector<int32_t> parent;
+    if (direct) {
+        parent.assign((size_t)(hi - lo + 1), -1);
+    } else {
+        ids.reserve((size_t)n_pairs * 2);
+        ids.insert(ids.end(), h_a, h_a + n_pairs);
+        ids.insert(ids.end(), h_b, h_b + n_pairs);
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        parent.resize(ids.size());
+        for (size_t i = 0; i < parent.size(); ++i) parent[i] = (int32_t)i;
+    }
+    auto slot = [&](int64_t v) -> int32_t {
+        if (direct) {
+            const int32_t s = (int32_t)(v - lo);
+            if (parent[(size_t)s] < 0) parent[(size_t)s] = s;  // first sight of this id
+            return s;
+        }
+        return (int32_t)(std::lower_bound(ids.begin(), ids.end(), v) - ids.begin());
+    };
+    auto find = [&](int32_t x) {
+        int32_t r = x;
+        while (parent[(size_t)r] != r) r = parent[(size_t)r];
+        while (parent[(size_t)x] != r) {
+            const int32_t nx = parent[(size_t)x];
+            parent[(size_t)x] = r;
+            x = nx;
+        }
+        return r;
+    };
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        const int32_t rx = find(slot(h_a[k])), ry = find(slot(h_b[k]));
+        if (rx != ry) {  // slots are ordered like the ids: the smaller one stays the root
+            if (rx < ry) parent[(size_t)ry] = rx;
+            else parent[(size_t)rx] = ry;
+        }
+    }
+    int64_t n = 0;
+    for (size_t sidx = 0; sidx < parent.size(); ++sidx) {
+        if (parent[sidx] < 0) continue;
+        const int32_t r = find((int32_t)sidx);
+        h_nodes[n] = direct ? lo + (int64_t)sidx : ids[sidx];
+        h_node_rep[n] = direct ? lo + (int64_t)r : ids[(size_t)r];
+        ++n;
+    }
+    *n_nodes = n;
     return KE_OK;
 }

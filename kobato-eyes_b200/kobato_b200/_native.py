@@ -69,6 +69,7 @@ _SIGNATURES = {
                                         C.c_void_p]),
     "ke_plane_sad_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p]),
+    "ke_cluster_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "ke_synth_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
                                   C.c_uint64, C.c_int, C.c_void_p]),
     "ke_microbench_popc": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -389,6 +389,28 @@ def plane_sad_pairs(planes, ia, ib):
     return out
 
 
+def cluster_pairs(a, b):
+    """Connected components of the pairs (a[k], b[k]): returns ``[(representative, [members])]`` sorted by
+    representative, members ascending, representative = smallest id ("smaller root wins", reference
+    src/dup/cluster.py:22-70).  Host union-find inside the library (no Python loop, no SciPy)."""
+    a = np.ascontiguousarray(a, np.int64)
+    b = np.ascontiguousarray(b, np.int64)
+    if a.shape != b.shape or a.ndim != 1:
+        raise ValueError("a and b must be 1-D and of equal length")
+    if a.size == 0:
+        return []
+    nodes = np.empty(2 * a.size, np.int64)
+    reps = np.empty(2 * a.size, np.int64)
+    count = C.c_int64(0)
+    nat.check(nat.load().ke_cluster_pairs_host(_np_ptr(a), _np_ptr(b), a.size, _np_ptr(nodes), _np_ptr(reps), C.byref(count)),
+              "ke_cluster_pairs_host")
+    nodes, reps = nodes[: count.value], reps[: count.value]
+    order = np.lexsort((nodes, reps))
+    members = nodes[order].tolist()
+    cuts = (np.flatnonzero(np.diff(reps[order])) + 1).tolist()
+    return [(members[s], members[s:e]) for s, e in zip([0] + cuts, cuts + [len(members)])]
+
+
 def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n_set: int = 1 << 30,
                         seed: int | None = None, planted: float = 0.05, device=None, out=None):
     """CUDA twin of ``synth.synth_image`` (identical bytes) -> uint8 CUDA tensor [count,h,w,c]."""

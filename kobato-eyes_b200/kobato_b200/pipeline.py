@@ -46,20 +46,7 @@ def _torch():
 def _components(i, j, keep):
     """Connected components of the accepted pairs -> sorted [(representative, [members])]
     (the reference's ClusterBuilder semantics, src/dup/cluster.py:22-70)."""
-    a, b = i[keep], j[keep]
-    if a.size == 0:
-        return []
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
-
-    nodes, inv = np.unique(np.concatenate([a, b]), return_inverse=True)
-    m = nodes.size
-    graph = coo_matrix((np.ones(a.size, np.int8), (inv[: a.size], inv[a.size:])), shape=(m, m))
-    _, labels = connected_components(graph, directed=False)
-    order = np.lexsort((nodes, labels))
-    cuts = np.flatnonzero(np.diff(labels[order])) + 1
-    groups = np.split(nodes[order], cuts)
-    return sorted((int(g[0]), g.tolist()) for g in groups)
+    return ops.cluster_pairs(i[keep], j[keep])
 
 
 class Timer:

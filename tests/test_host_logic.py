@@ -327,3 +327,19 @@ def test_cluster_builder():
     assert len(clusters[0].matches) == 2 and kcluster.ClusterBuilder().build([]) == []
     assert [(r, m) for r, m in ref_py.cluster_matches([(m.file_id_a, m.file_id_b, m.is_duplicate) for m in ms])] == \
         [(c.representative, c.members) for c in clusters]
+
+
+def test_cluster_pairs_host_union_find_matches_the_oracle():
+    """ke_cluster_pairs_host (host code of the library, no GPU): components with the reference's "smaller root
+    wins" representative (src/dup/cluster.py:22-70), for compact and for sparse id ranges."""
+    from kobato_b200 import ops
+
+    rng = np.random.default_rng(11)
+    for lo, hi, n in ((0, 3000, 2000), (0, 70000, 1200), (-5, 5, 40), (10 ** 12, 10 ** 12 + 10 ** 9, 500), (0, 2, 1), (7, 8, 3)):
+        a, b = rng.integers(lo, hi, n), rng.integers(lo, hi, n)
+        want = ref_py.cluster_matches((int(x), int(y), True) for x, y in zip(a, b))
+        assert ops.cluster_pairs(a, b) == want, (lo, hi, n)
+    assert ops.cluster_pairs([], []) == []
+    assert ops.cluster_pairs([5], [5]) == [(5, [5])]
+    with pytest.raises(ValueError):
+        ops.cluster_pairs([1, 2], [3])
