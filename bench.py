@@ -260,6 +260,8 @@ def run_cuda(args) -> dict:
 
     # ---- per-kernel timings (CUDA events around single launches, inputs >> L2 or L2-flushed) ---
     def timed(fn, reps=3):
+        fn()  # one untimed launch: the first one after a different kernel runs ~10 % long (cold instruction / L2 state)
+        torch.cuda.synchronize(dev)
         ts = []
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -416,6 +418,11 @@ def main():
     ap.add_argument("--ref-unique", type=int, default=256, help="unique synthetic images behind the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.impl == "cuda" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU (rank 0 of the children prints the JSON line)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", *sys.argv]
+        raise SystemExit(subprocess.call(cmd))
     # Only the JSON line may reach stdout (NCCL / libraries print banners there): park the real stdout.
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -425,11 +432,6 @@ def main():
     if args.impl == "reference":
         res = run_reference(args)
     else:
-        if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
-            # convenience: re-launch under torchrun, one rank per GPU
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-                   "--master-addr", "127.0.0.1", "--master-port", "29533", *sys.argv]
-            raise SystemExit(subprocess.call(cmd))
         res = run_cuda(args)
     if res:
         sys.stdout.flush()
