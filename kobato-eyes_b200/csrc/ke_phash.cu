@@ -1731,11 +1731,14 @@ constexpr int kV5Threads = (kV5Tap + kV5Luma) * 32;
 constexpr int kHP = 48;   // horizontal-pass output plane, stored TRANSPOSED: [column 0..47][row 0..31], column pitch 48 B
 constexpr int kHCols = 48;
 
+constexpr int kMaxLumaBufs = 4;
+
 struct V5Layout {
     int raw, luma, bfrag, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
 };
 
-__host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, int n_slots, int mma_words /* of warps 4..7 */) {
+__host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, int n_slots, int mma_words /* of warps 4..7 */,
+                                                  int nlb /* luma chunk buffers */) {
     V5Layout L;
     int off = 0;
     auto take = [&](int bytes, int align) {
@@ -1746,14 +1749,14 @@ __host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, in
     };
     L.luma_bytes = (32 * pitch_bytes + 127) / 128 * 128;
     L.raw = take(n_slots * sub_bytes, 128);
-    L.luma = take(2 * L.luma_bytes, 128);
+    L.luma = take(nlb * L.luma_bytes, 128);
     L.bfrag = take(mma_words * 8, 16);
     L.hrow = take(2 * kHCols * kHP, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
     L.ymat = take(64 * 8, 16);
-    L.bar = take((2 * kMaxSlots + 4) * 8 + kMaxSlots * 4, 8);
+    L.bar = take((2 * kMaxSlots + 2 * kMaxLumaBufs) * 8 + kMaxSlots * 4, 8);
     L.total = off;
     return L;
 }
@@ -1874,7 +1877,7 @@ __device__ __forceinline__ void v5_taps_wide_reg(uint32_t a_addr, const uint2 (&
 template <int C>
 __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows,
                                                                    const int slot_shift, const int pitch_bytes,
-                                                                   const int dbg) {
+                                                                   const int nlb, const int dbg) {
     constexpr int CR = 32, NW = kV5Tap;
     extern __shared__ __align__(128) uint8_t smem[];
     const int row_bytes = a.w * C;
@@ -1882,7 +1885,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     const int n_slots = 1 << slot_shift;
     const uint32_t slot_mask = (uint32_t)n_slots - 1u;
     const int b_first = a.mma_boff[4];  // the wide-target warps' fragments live in registers, not here
-    const V5Layout L = v5_layout(sub_bytes, pitch_bytes, n_slots, a.mma_words - b_first);
+    const V5Layout L = v5_layout(sub_bytes, pitch_bytes, n_slots, a.mma_words - b_first, nlb);
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
@@ -1893,9 +1896,9 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     double* s_y = reinterpret_cast<double*>(smem + L.ymat);
     uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // raw ring
     uint64_t* s_empty = s_full + kMaxSlots;
-    uint64_t* l_full = s_empty + kMaxSlots;  // luma chunk ring [2]
-    uint64_t* l_empty = l_full + 2;
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(l_empty + 2);  // readers done with a raw slot (mod kV5Luma)
+    uint64_t* l_full = s_empty + kMaxSlots;  // luma chunk ring [nlb]
+    uint64_t* l_empty = l_full + kMaxLumaBufs;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(l_empty + kMaxLumaBufs);  // readers done with a raw slot (mod kV5Luma)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_sub = (a.h + sub_rows - 1) / sub_rows;
@@ -1907,14 +1910,14 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             mbar_init(&s_full[b], 1);
             s_cnt[b] = 0u;
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < nlb; ++b) {
             mbar_init(&l_full[b], kV5Luma);
             mbar_init(&l_empty[b], kV5Tap);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < a.mma_words - b_first; i += kV5Threads) s_b[i] = __ldg(a.mma_b + b_first + i);
-    for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
+    for (int i = tid; i < nlb * L.luma_bytes / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
     for (int i = tid; i < 2 * kHCols * kHP / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_hrow)[i] = 0u;
     __syncthreads();
 
@@ -1951,11 +1954,11 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         const bool act = lane < ng;
         const int src_off = lw * row_bytes + 48 * lane, dst_off = lw * pitch_bytes + 16 * lane;
         uint32_t seq = 0;
-        uint32_t chunk = 0;
+        uint32_t chunk = 0, lph = 0;  // luma ring: buffer lb, phase lph
+        int lb = 0;
         for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
-                const int lb = chunk & 1;
-                mbar_wait(&l_empty[lb], ((chunk >> 1) & 1u) ^ 1u);  // tap warps are done with this buffer
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
+                mbar_wait(&l_empty[lb], lph ^ 1u);  // tap warps are done with this buffer
                 uint8_t* dst8 = s_luma + lb * L.luma_bytes;
                 for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
                     const int b = (int)(seq & slot_mask);
@@ -2010,13 +2013,13 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 #pragma unroll
             for (int tl = 0; tl < 3; ++tl)
                 breg[k][tl] = k < a.mma_nk[warp] ? __ldg(a.mma_b + a.mma_boff[warp] + (k * 3 + tl) * 32 + lane) : make_uint2(0u, 0u);
-        uint32_t chunk = 0;
+        uint32_t chunk = 0, lph = 0;
+        int lb = 0;
         for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
-                const int lb = chunk & 1;
-                mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, poll_ns);
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
+                mbar_wait_sleep(&l_full[lb], lph, poll_ns);
                 v5_taps_wide_reg(smem_u32(s_luma + lb * L.luma_bytes) + a_off, breg, nk, pitch_bytes,
-                                 s_hrow + lb * (kHCols * kHP), 8 * warp, lane);
+                                 s_hrow + (chunk & 1) * (kHCols * kHP), 8 * warp, lane);
                 __syncwarp();
                 if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
                 compute_sync<NW>();                          // the row plane of this chunk is complete
@@ -2043,7 +2046,8 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         v_nt[p] = warp == 7 ? 4 + p : (idx & 3);
     }
     const int g = lane >> 2, t = lane & 3;
-    uint32_t chunk = 0;
+    uint32_t chunk = 0, lph = 0;
+    int lb = 0;
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
 #pragma unroll
         for (int p = 0; p < NVP; ++p)
@@ -2052,10 +2056,9 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 #pragma unroll
                 for (int i = 0; i < 4; ++i) vc[p][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
         int ci = 0;
-        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci) {
-            const int lb = chunk & 1;
-            uint8_t* hrow = s_hrow + lb * (kHCols * kHP);
-            mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, poll_ns);
+        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
+            uint8_t* hrow = s_hrow + (chunk & 1) * (kHCols * kHP);
+            mbar_wait_sleep(&l_full[lb], lph, poll_ns);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
             if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
             else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 6, lane);
@@ -2102,23 +2105,27 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 }
 
 template <int C>
-bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V5Layout& L) {
+bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, int& nlb, V5Layout& L) {
     const long long row_bytes = (long long)a.w * C;
     if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.mma_words < 1 || !a.vmma) return false;
     for (int q = 0; q < 4; ++q)
         if (a.mma_nk[q] > kNKP) return false;  // wide-target B fragments must fit the register file
     pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
-    int want_sub = 8, want_shift = 2;
-    if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d", &want_sub, &want_shift);  // tuning override
+    int want_sub = 8, want_shift = 1, want_nlb = 3;
+    if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d,%d", &want_sub, &want_shift, &want_nlb);  // tuning override
+    if (want_nlb < 2 || want_nlb > kMaxLumaBufs) want_nlb = 2;
     for (int sub : {want_sub, 8, 4, 2, 1}) {
         if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
         for (int shift : {want_shift, 2, 1}) {
             if (shift < 1 || shift > 3) continue;
-            L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words - a.mma_boff[4]);
-            if (L.total <= 113 * 1024 && a.n * ((a.h + sub - 1) / sub) < (1ll << 31)) {
-                sub_rows = sub;
-                slot_shift = shift;
-                return true;
+            for (int bufs : {want_nlb, 2}) {
+                L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words - a.mma_boff[4], bufs);
+                if (L.total <= 113 * 1024 && a.n * ((a.h + sub - 1) / sub) < (1ll << 31)) {
+                    sub_rows = sub;
+                    slot_shift = shift;
+                    nlb = bufs;
+                    return true;
+                }
             }
         }
     }
@@ -2126,7 +2133,7 @@ bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_by
 }
 
 template <int C>
-int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, const V5Layout& L,
+int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, int nlb, const V5Layout& L,
               cudaStream_t s) {
     KE_CUDA(cudaFuncSetAttribute(ke_phash_v5_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int per_sm = 0;
@@ -2137,7 +2144,7 @@ int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
     const char* dbg_env = getenv("KE_PHASH_DBG");
     const char* ns_env = getenv("KE_PHASH_SLEEP");  // tuning override: consumer poll interval in ns
     const int ns = ns_env ? atoi(ns_env) : 200;
-    ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes,
+    ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes, nlb,
                                                                       ((dbg_env ? atoi(dbg_env) : 0) & 0xFF) | (ns << 8));
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
@@ -2168,10 +2175,10 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // 2.0 M images/s.
     const char* which = getenv("KE_PHASH_KERNEL");
     if (!ctx->force_generic_phash && (!which || !strcmp(which, "v5"))) {
-        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
+        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0, nlb = 2;
         V5Layout VL;
-        if (v5_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
-            return launch_v5<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
+        if (v5_config<C>(a, sub_rows, slot_shift, pitch_bytes, nlb, VL))
+            return launch_v5<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, nlb, VL, s);
     }
     if (!ctx->force_generic_phash && !(which && (!strcmp(which, "v3") || !strcmp(which, "fast")))) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
