@@ -500,6 +500,231 @@ int launch_ssim4(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
     return KE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2, staged feed (RGB / RGBA banks, 'L' planes wider than one column block): the strips cannot come as one
+// contiguous bulk copy, so every thread streams 16-byte pieces of the raw rows into shared memory with cp.async
+// (no registers held, the copy of strip s+1 runs under the arithmetic of strip s), and the raw strip is turned into
+// the luma strip shared memory to shared memory (dp2a, 16 pixels per step).  Same 4-columns-per-thread arithmetic.
+
+constexpr int kSR2 = 14;  // rows per staged strip (multiple of 7)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// 4 RGB pixels (12 bytes) -> 4 luma bytes, two dp2a per pixel (see ke_phash.cu luma4_rgb)
+__device__ __forceinline__ uint32_t ssim_luma4_rgb(uint32_t w0, uint32_t w1, uint32_t w2) {
+    constexpr uint32_t cR = 19595u, cG = 38470u, cB = 7471u;
+    constexpr uint32_t RG = cR | (cG << 16), B_ = cB, _R = cR << 16, GB = cG | (cB << 16);
+    const uint32_t s0 = dp2a_hi(B_, w0, dp2a_lo(RG, w0, 0x8000u));
+    const uint32_t s1 = dp2a_lo(GB, w1, dp2a_hi(_R, w0, 0x8000u));
+    const uint32_t s2 = dp2a_lo(B_, w2, dp2a_hi(RG, w1, 0x8000u));
+    const uint32_t s3 = dp2a_hi(GB, w2, dp2a_lo(_R, w2, 0x8000u));
+    return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+}
+__device__ __forceinline__ uint32_t ssim_luma4_rgba(uint4 px) {
+    constexpr uint32_t RG = 19595u | (38470u << 16), B_ = 7471u;
+    const uint32_t s0 = dp2a_hi(B_, px.x, dp2a_lo(RG, px.x, 0x8000u)), s1 = dp2a_hi(B_, px.y, dp2a_lo(RG, px.y, 0x8000u));
+    const uint32_t s2 = dp2a_hi(B_, px.z, dp2a_lo(RG, px.z, 0x8000u)), s3 = dp2a_hi(B_, px.w, dp2a_lo(RG, px.w, 0x8000u));
+    return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+}
+
+struct Ssim4State {  // the register state a thread carries down the rows of one unit
+    HSum ring[4][kWin];
+    uint32_t acc_s[4], acc_t[4], acc_uv[4];
+};
+
+// rows [0, rows) of a luma strip pair (word pointers already offset by the thread's first word) -> partial sum
+__device__ __forceinline__ float ssim4_strip(Ssim4State& st, const uint32_t* su, const uint32_t* sv, int pw, int rows, int r0,
+                                             float m0, float m1, float m2, float m3) {
+    float part = 0.f;
+    auto group = [&](int rb, auto steady) {
+        constexpr bool STEADY = decltype(steady)::value;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const int r = rb + k;  // (r0 + r) % 7 == k because strips are multiples of 7
+            if (STEADY || r < rows) {
+                const uint32_t* pu = su + r * pw;
+                const uint32_t* pv = sv + r * pw;
+                const uint32_t u0 = pu[0], u1 = pu[1], u2 = pu[2];
+                const uint32_t v0 = pv[0], v1 = pv[1], v2 = pv[2];
+                st.ring[0][k] = hsum7_words(u0, u1, v0, v1);
+                st.ring[1][k] = hsum7_words(__byte_perm(u0, u1, 0x4321), __byte_perm(u1, u2, 0x4321),
+                                            __byte_perm(v0, v1, 0x4321), __byte_perm(v1, v2, 0x4321));
+                st.ring[2][k] = hsum7_words(__byte_perm(u0, u1, 0x5432), __byte_perm(u1, u2, 0x5432),
+                                            __byte_perm(v0, v1, 0x5432), __byte_perm(v1, v2, 0x5432));
+                st.ring[3][k] = hsum7_words(__byte_perm(u0, u1, 0x6543), __byte_perm(u1, u2, 0x6543),
+                                            __byte_perm(v0, v1, 0x6543), __byte_perm(v1, v2, 0x6543));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st.acc_s[j] += st.ring[j][k].s;
+                    st.acc_t[j] += st.ring[j][k].t;
+                    st.acc_uv[j] += st.ring[j][k].uv;
+                }
+                if (STEADY || r0 + r >= kWin - 1) {
+                    const float2 e01 = ssim_point2(st.acc_s[0], st.acc_t[0], st.acc_uv[0], st.acc_s[1], st.acc_t[1], st.acc_uv[1]);
+                    const float2 e23 = ssim_point2(st.acc_s[2], st.acc_t[2], st.acc_uv[2], st.acc_s[3], st.acc_t[3], st.acc_uv[3]);
+                    const float2 sm = __ffma2_rn(e23, make_float2(m2, m3), __fmul2_rn(e01, make_float2(m0, m1)));
+                    part += sm.x + sm.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st.acc_s[j] -= st.ring[j][(k + 1) % kWin].s;
+                    st.acc_t[j] -= st.ring[j][(k + 1) % kWin].t;
+                    st.acc_uv[j] -= st.ring[j][(k + 1) % kWin].uv;
+                }
+            }
+        }
+    };
+    for (int rb = 0; rb < rows; rb += kWin) {
+        if (r0 + rb >= kWin && rb + kWin <= rows) group(rb, std::true_type{});
+        else group(rb, std::false_type{});
+    }
+    return part;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kT4) ke_ssim4s_kernel(const SsimArgs a, const int raw_pitch) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // C > 1: [raw u | raw v] (one strip, refilled under the arithmetic) + [luma u | luma v];  C == 1: 2 x [luma u | luma v]
+    const int luma_bytes = (kSR2 * a.pitch + 32 + 127) / 128 * 128;
+    const int raw_bytes = C == 1 ? 0 : (kSR2 * raw_pitch + 64 + 127) / 128 * 128;
+    uint8_t* s_rawbuf = smem;
+    uint8_t* s_lum = smem + 2 * raw_bytes;
+    __shared__ double s_red[kT4 / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_strips = (a.h + kSR2 - 1) / kSR2;
+    const long long n_units = a.n_pairs * a.n_cblocks;
+    const int row_bytes_img = a.w * C;
+
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long pair = unit / a.n_cblocks;
+        const int cb = (int)(unit - pair * a.n_cblocks);
+        const int col0 = cb * kBlockCols;
+        const int out_cols = min(kBlockCols, (a.w - 6) - col0);
+        const int in_cols = out_cols + 6;
+        const uint8_t* img_u = a.bank + a.ia[pair] * a.img_stride + (long long)col0 * C;
+        const uint8_t* img_v = a.bank + a.ib[pair] * a.img_stride + (long long)col0 * C;
+        // 16-byte pieces per row: everything the block needs, never past the end of the image row
+        const int piece_bytes = min((in_cols * C + 15) / 16 * 16, row_bytes_img - col0 * C);
+        const int pieces = piece_bytes >> 4;
+
+        auto fetch = [&](int s, int buf) {  // raw rows of strip s -> shared memory, asynchronously
+            const int r0 = s * kSR2;
+            const int rows = min(kSR2, a.h - r0);
+            uint8_t* du = C == 1 ? s_lum + (2 * buf) * luma_bytes : s_rawbuf;
+            uint8_t* dv = C == 1 ? s_lum + (2 * buf + 1) * luma_bytes : s_rawbuf + raw_bytes;
+            const int pitch = C == 1 ? a.pitch : raw_pitch;
+            for (int idx = tid; idx < rows * pieces; idx += kT4) {
+                const int r = idx / pieces, q = idx - r * pieces;
+                const long long g = (long long)(r0 + r) * a.row_stride + 16 * q;
+                cp_async16(du + r * pitch + 16 * q, img_u + g);
+                cp_async16(dv + r * pitch + 16 * q, img_v + g);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto convert = [&](int s) {  // raw strip -> luma strip (C > 1)
+            const int rows = min(kSR2, a.h - s * kSR2);
+            if (C == 3) {
+                const int groups = (in_cols + 15) >> 4;  // 16 pixels = 48 raw bytes per step
+                for (int idx = tid; idx < 2 * rows * groups; idx += kT4) {
+                    const int im = idx / (rows * groups), rem = idx - im * rows * groups;
+                    const int r = rem / groups, q = rem - r * groups;
+                    const uint4* src = reinterpret_cast<const uint4*>(s_rawbuf + im * raw_bytes + r * raw_pitch + 48 * q);
+                    const uint4 x = src[0], y = src[1], z = src[2];
+                    *reinterpret_cast<uint4*>(s_lum + im * luma_bytes + r * a.pitch + 16 * q) =
+                        make_uint4(ssim_luma4_rgb(x.x, x.y, x.z), ssim_luma4_rgb(x.w, y.x, y.y), ssim_luma4_rgb(y.z, y.w, z.x),
+                                   ssim_luma4_rgb(z.y, z.z, z.w));
+                }
+            } else if (C == 4) {
+                const int groups = (in_cols + 3) >> 2;
+                for (int idx = tid; idx < 2 * rows * groups; idx += kT4) {
+                    const int im = idx / (rows * groups), rem = idx - im * rows * groups;
+                    const int r = rem / groups, q = rem - r * groups;
+                    const uint4 px = *reinterpret_cast<const uint4*>(s_rawbuf + im * raw_bytes + r * raw_pitch + 16 * q);
+                    *reinterpret_cast<uint32_t*>(s_lum + im * luma_bytes + r * a.pitch + 4 * q) = ssim_luma4_rgba(px);
+                }
+            }
+        };
+
+        Ssim4State st;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            st.acc_s[j] = st.acc_t[j] = st.acc_uv[j] = 0u;
+#pragma unroll
+            for (int i = 0; i < kWin; ++i) st.ring[j][i] = HSum{0u, 0u, 0u};
+        }
+        double total = 0.0;
+        const int x0 = 4 * tid;
+        const bool active = x0 < out_cols;
+        const float m0 = x0 < out_cols ? 1.f : 0.f, m1 = x0 + 1 < out_cols ? 1.f : 0.f, m2 = x0 + 2 < out_cols ? 1.f : 0.f,
+                    m3 = x0 + 3 < out_cols ? 1.f : 0.f;
+        const int pw = a.pitch >> 2;
+
+        __syncthreads();  // every thread is done with the previous unit's buffers
+        fetch(0, 0);
+        for (int s = 0; s < n_strips; ++s) {
+            const int buf = C == 1 ? (s & 1) : 0;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();  // strip s has landed for every thread
+            if (C > 1) {
+                convert(s);
+                __syncthreads();  // luma strip complete, raw strip free
+            }
+            if (s + 1 < n_strips) fetch(s + 1, (s + 1) & 1);  // runs under the arithmetic below
+            const int r0 = s * kSR2;
+            const int rows = min(kSR2, a.h - r0);
+            const uint32_t* su = reinterpret_cast<const uint32_t*>(s_lum + (2 * buf) * luma_bytes) + tid;
+            const uint32_t* sv = reinterpret_cast<const uint32_t*>(s_lum + (C == 1 ? (2 * buf + 1) : 1) * luma_bytes) + tid;
+            if (active) total += (double)ssim4_strip(st, su, sv, pw, rows, r0, m0, m1, m2, m3);
+            if (C > 1) __syncthreads();  // the luma strip is rewritten by the next convert
+        }
+
+#pragma unroll
+        for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+        if (lane == 0) s_red[warp] = total;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kT4 / 32; ++i) t += s_red[i];
+            if (a.n_cblocks == 1) a.out[pair] = t * a.inv_count;
+            else atomicAdd(&a.out[pair], t * a.inv_count);
+        }
+    }
+}
+
+template <int C>
+int launch_ssim4s(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
+    const int in_max = std::min(a.w, kBlockCols + 6);
+    const int raw_pitch = (in_max * C + 15) / 16 * 16 + 16;
+    const int luma_bytes = (kSR2 * a.pitch + 32 + 127) / 128 * 128;
+    const int raw_bytes = C == 1 ? 0 : (kSR2 * raw_pitch + 64 + 127) / 128 * 128;
+    const int smem = 2 * raw_bytes + (C == 1 ? 4 : 2) * luma_bytes;
+    KE_CUDA(cudaFuncSetAttribute(ke_ssim4s_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_ssim4s_kernel<C>, kT4, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long units = a.n_pairs * a.n_cblocks;
+    if (grid > units) grid = units;
+    ke_ssim4s_kernel<C><<<(unsigned)grid, kT4, smem, s>>>(a, raw_pitch);
+    ctx->launches++;
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 template <int C>
 int launch_ssim(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
     const int strip_bytes = (kStripRows * a.pitch + 16 + 127) / 128 * 128;
@@ -553,24 +778,26 @@ extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, i
     a.inv_count = 1.0 / ((double)(h - 6) * (double)(w - 6));
     a.out = d_ssim;
     if (a.n_cblocks > 1) KE_CUDA(cudaMemsetAsync(d_ssim, 0, (size_t)n_pairs * sizeof(double), s));
-    // v2 (four output columns per thread) wins where the strips arrive by TMA; on the staged paths (RGB banks, planes
-    // wider than one column block) its 64-thread CTAs hide the global-load latency of the staging loop worse than
-    // v1's 256 threads do (measured: 4.3 vs 3.7 ms on the C2 step's 3.6k pairs of 512x512 RGB), so those stay on v1.
+    // v2 (four output columns per thread): strips by one bulk copy per image when the plane is a contiguous 'L' block,
+    // else by cp.async pieces (needs 16-byte aligned rows); v1 (one column per thread, plain loads) takes the rest.
     const char* which = getenv("KE_SSIM_KERNEL");  // tuning override: "v1" | "v2"
-    const bool use_v1 = which ? !strcmp(which, "v1") : !a.use_bulk;
-    if (use_v1) {
+    const bool can_stage = (row_stride % 16) == 0 && (img_stride % 16) == 0 && ((int64_t)w * c) % 16 == 0 &&
+                           (reinterpret_cast<uintptr_t>(d_bank) & 15) == 0;
+    const bool use_v1 = which ? !strcmp(which, "v1") : !(a.use_bulk || can_stage);
+    if (use_v1 || !(a.use_bulk || can_stage)) {
         switch (c) {
             case 1: return launch_ssim<1>(ctx, a, s);
             case 3: return launch_ssim<3>(ctx, a, s);
             default: return launch_ssim<4>(ctx, a, s);
         }
     }
-    // v2 reads up to 11 bytes past a thread's first column: keep the strip rows that much longer than the block
-    if (!a.use_bulk) a.pitch = (std::min(w, kBlockCols + 6) + 3) / 4 * 4 + 12;
+    if (a.use_bulk) return launch_ssim4<1>(ctx, a, s);
+    // staged v2 reads up to 11 bytes past a thread's first column and converts 16 pixels per step
+    a.pitch = (std::min(w, kBlockCols + 6) + 15) / 16 * 16 + 16;
     switch (c) {
-        case 1: return launch_ssim4<1>(ctx, a, s);
-        case 3: return launch_ssim4<3>(ctx, a, s);
-        default: return launch_ssim4<4>(ctx, a, s);
+        case 1: return launch_ssim4s<1>(ctx, a, s);
+        case 3: return launch_ssim4s<3>(ctx, a, s);
+        default: return launch_ssim4s<4>(ctx, a, s);
     }
 }
 
