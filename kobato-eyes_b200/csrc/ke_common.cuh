@@ -33,6 +33,9 @@ void ke_set_error(const char* fmt, ...);
 // Device-resident Pillow coefficient tables, cached per image geometry (ke_phash.cu).
 struct KeTableCache;
 void ke_tables_free(KeTableCache* cache);
+// Device-resident tap tables of the generic gray resize (ke_refine.cu), cached per (in, out, filter).
+struct KeResizeCache;
+void ke_resize_tables_free(KeResizeCache* cache);
 
 struct ke_ctx {
     int device = 0;
@@ -47,6 +50,7 @@ struct ke_ctx {
     void* h_pinned[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_pinned_bytes[4] = {0, 0, 0, 0};
     KeTableCache* tables = nullptr;
+    KeResizeCache* resize_tables = nullptr;
     int force_generic_phash = 0;
     int join_mode = 0;  // KE_OPT_JOIN_MODE: 0 auto, 1 POPC kernel only, 2 hybrid (POPC + bit-sliced), 3 bit-sliced only  // KE_OPT_PHASH_GENERIC: route every geometry through the generic K1 kernel
 };

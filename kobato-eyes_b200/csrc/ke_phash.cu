@@ -1075,6 +1075,12 @@ __device__ __forceinline__ uint32_t luma4_rgb(uint32_t w0, uint32_t w1, uint32_t
     const uint32_t s3 = dp2a_hi(GB, w2, dp2a_lo(_R, w2, 0x8000u));
     return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);  // byte 2 of each sum
 }
+__device__ __forceinline__ uint32_t luma4_rgba(const uint4 px) {  // 4 RGBA pixels -> 4 luma bytes (alpha ignored, as Pillow does)
+    constexpr uint32_t RG = 19595u | (38470u << 16), B_ = 7471u;
+    const uint32_t s0 = dp2a_hi(B_, px.x, dp2a_lo(RG, px.x, 0x8000u)), s1 = dp2a_hi(B_, px.y, dp2a_lo(RG, px.y, 0x8000u));
+    const uint32_t s2 = dp2a_hi(B_, px.z, dp2a_lo(RG, px.z, 0x8000u)), s3 = dp2a_hi(B_, px.w, dp2a_lo(RG, px.w, 0x8000u));
+    return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+}
 __device__ __forceinline__ uint4 luma16_rgb(const uint4 a, const uint4 b, const uint4 c) {
     return make_uint4(luma4_rgb(a.x, a.y, a.z), luma4_rgb(a.w, b.x, b.y), luma4_rgb(b.z, b.w, c.x), luma4_rgb(c.y, c.z, c.w));
 }
@@ -1949,10 +1955,9 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             for (uint32_t q = 0; q < (uint32_t)n_slots && q < total_seq; ++q) issue(q);
         // early release: when a warp's share of a sub-chunk (<= 2 rows of <= 512 pixels) fits its registers the
         // raw slot is handed back right after the loads, before the arithmetic
-        const bool early = (C == 3) && sub_rows <= 2 * kV5Luma && a.w <= 512;
+        const bool early = sub_rows <= 2 * kV5Luma && a.w <= 512 && !(dbg & 16);
         const int ng = a.w >> 4;
         const bool act = lane < ng;
-        const int src_off = lw * row_bytes + 48 * lane, dst_off = lw * pitch_bytes + 16 * lane;
         uint32_t seq = 0;
         uint32_t chunk = 0, lph = 0;  // luma ring: buffer lb, phase lph
         int lb = 0;
@@ -1968,20 +1973,49 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                         __syncwarp();
                         if (lane == 0) release(seq, b);
                     } else if (early) {
-                        const bool one = act && lw < srows, two = act && lw + kV5Luma < srows;
-                        const uint4* p0 = reinterpret_cast<const uint4*>(s_raw + b * sub_bytes + src_off);
-                        const uint4* p1 = reinterpret_cast<const uint4*>(s_raw + b * sub_bytes + src_off + kV5Luma * row_bytes);
-                        uint4 x0[3], x1[3];
+                        const bool r_one = lw < srows, r_two = lw + kV5Luma < srows;
+                        const uint8_t* s0 = s_raw + b * sub_bytes + lw * row_bytes;
+                        const uint8_t* s1 = s0 + kV5Luma * row_bytes;
+                        uint8_t* d0 = dst8 + (s * sub_rows + lw) * pitch_bytes;
+                        uint8_t* d1 = d0 + kV5Luma * pitch_bytes;
+                        if (C == 3) {  // 16 pixels = 48 bytes per lane (lane stride 48 B: conflict-free LDS.128)
+                            const bool one = act && r_one, two = act && r_two;
+                            uint4 x0[3], x1[3];
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            x0[i] = one ? p0[i] : make_uint4(0, 0, 0, 0);
-                            x1[i] = two ? p1[i] : make_uint4(0, 0, 0, 0);
+                            for (int i = 0; i < 3; ++i) {
+                                x0[i] = one ? reinterpret_cast<const uint4*>(s0 + 48 * lane)[i] : make_uint4(0, 0, 0, 0);
+                                x1[i] = two ? reinterpret_cast<const uint4*>(s1 + 48 * lane)[i] : make_uint4(0, 0, 0, 0);
+                            }
+                            __syncwarp();
+                            if (lane == 0) release(seq, b);
+                            if (one) *reinterpret_cast<uint4*>(d0 + 16 * lane) = luma16_rgb(x0[0], x0[1], x0[2]);
+                            if (two) *reinterpret_cast<uint4*>(d1 + 16 * lane) = luma16_rgb(x1[0], x1[1], x1[2]);
+                        } else if (C == 4) {  // 4 pixels per 16-byte piece, piece 32 i + lane: consecutive lanes, no conflicts
+                            const int pieces = a.w >> 2;
+                            uint4 x0[4], x1[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const bool in = 32 * i + lane < pieces;
+                                x0[i] = in && r_one ? reinterpret_cast<const uint4*>(s0)[32 * i + lane] : make_uint4(0, 0, 0, 0);
+                                x1[i] = in && r_two ? reinterpret_cast<const uint4*>(s1)[32 * i + lane] : make_uint4(0, 0, 0, 0);
+                            }
+                            __syncwarp();
+                            if (lane == 0) release(seq, b);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const bool in = 32 * i + lane < pieces;
+                                if (in && r_one) reinterpret_cast<uint32_t*>(d0)[32 * i + lane] = luma4_rgba(x0[i]);
+                                if (in && r_two) reinterpret_cast<uint32_t*>(d1)[32 * i + lane] = luma4_rgba(x1[i]);
+                            }
+                        } else {  // 'L': the rows are the luma rows already
+                            const bool one = act && r_one, two = act && r_two;
+                            const uint4 x0 = one ? reinterpret_cast<const uint4*>(s0)[lane] : make_uint4(0, 0, 0, 0);
+                            const uint4 x1 = two ? reinterpret_cast<const uint4*>(s1)[lane] : make_uint4(0, 0, 0, 0);
+                            __syncwarp();
+                            if (lane == 0) release(seq, b);
+                            if (one) reinterpret_cast<uint4*>(d0)[lane] = x0;
+                            if (two) reinterpret_cast<uint4*>(d1)[lane] = x1;
                         }
-                        __syncwarp();
-                        if (lane == 0) release(seq, b);
-                        uint8_t* d0 = dst8 + s * sub_rows * pitch_bytes + dst_off;
-                        if (one) *reinterpret_cast<uint4*>(d0) = luma16_rgb(x0[0], x0[1], x0[2]);
-                        if (two) *reinterpret_cast<uint4*>(d0 + kV5Luma * pitch_bytes) = luma16_rgb(x1[0], x1[1], x1[2]);
                     } else {
                         if (C == 3)
                             luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, dst8 + s * sub_rows * pitch_bytes, srows, a.w,

@@ -15,6 +15,7 @@
 // The intermediate [n,h,ow] plane costs ow/(w*c) of the input traffic (8 % at 512x512x3 -> 128).
 #include <cmath>
 #include <map>
+#include <tuple>
 #include <vector>
 
 #include "ke_common.cuh"
@@ -220,12 +221,29 @@ int build_table(int in_size, int out_size, int filter, std::vector<int32_t>& kk,
     return KE_OK;
 }
 
-std::map<std::tuple<int, int, int, int>, RTable> g_tables;  // (device, in, out, filter)
+}  // namespace
+
+struct KeResizeCache {
+    std::map<std::tuple<int, int, int>, RTable> tables;  // (in, out, filter)
+};
+
+void ke_resize_tables_free(KeResizeCache* cache) {
+    if (!cache) return;
+    for (auto& kv : cache->tables) {
+        cudaFree(kv.second.d_kk);
+        cudaFree(kv.second.d_bounds);
+    }
+    delete cache;
+}
+
+namespace {
 
 int get_table(ke_ctx* ctx, int in_size, int out_size, int filter, const RTable** out) {
-    auto key = std::make_tuple(ctx->device, in_size, out_size, filter);
-    auto it = g_tables.find(key);
-    if (it == g_tables.end()) {
+    if (!ctx->resize_tables) ctx->resize_tables = new KeResizeCache();
+    auto& tables = ctx->resize_tables->tables;
+    auto key = std::make_tuple(in_size, out_size, filter);
+    auto it = tables.find(key);
+    if (it == tables.end()) {
         std::vector<int32_t> kk, bd;
         RTable t;
         build_table(in_size, out_size, filter, kk, bd, t.ksize);
@@ -233,7 +251,7 @@ int get_table(ke_ctx* ctx, int in_size, int out_size, int filter, const RTable**
         KE_CUDA(cudaMalloc((void**)&t.d_bounds, bd.size() * 4));
         KE_CUDA(cudaMemcpy(t.d_kk, kk.data(), kk.size() * 4, cudaMemcpyHostToDevice));
         KE_CUDA(cudaMemcpy(t.d_bounds, bd.data(), bd.size() * 4, cudaMemcpyHostToDevice));
-        it = g_tables.emplace(key, t).first;
+        it = tables.emplace(key, t).first;
     }
     *out = &it->second;
     return KE_OK;
