@@ -1944,12 +1944,9 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                      (uint32_t)(rows * row_bytes), &s_full[b]);
         };
         auto release = [&](uint32_t seq_, int b) {  // lane 0, after the warp's reads of slot b (ordered by __syncwarp)
-            __threadfence_block();
-            const uint32_t old = atomicAdd(&s_cnt[b], 1u);
-            if ((old & (kV5Luma - 1)) == kV5Luma - 1) {
-                __threadfence_block();
-                if (seq_ + (uint32_t)n_slots < total_seq) issue(seq_ + (uint32_t)n_slots);
-            }
+            uint32_t old;  // acq_rel: the warp's reads are ordered before the count, the refill after the last count
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&s_cnt[b])) : "memory");
+            if ((old & (kV5Luma - 1)) == kV5Luma - 1 && seq_ + (uint32_t)n_slots < total_seq) issue(seq_ + (uint32_t)n_slots);
         };
         if (lw == 0 && lane == 0)
             for (uint32_t q = 0; q < (uint32_t)n_slots && q < total_seq; ++q) issue(q);
