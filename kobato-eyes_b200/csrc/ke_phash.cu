@@ -1733,6 +1733,10 @@ int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
 //     warps 8..11  luma warps (warp 8 / lane 0 issues the TMA copies)
 
 constexpr int kV5Tap = 8, kV5Luma = 4;
+// Registers per role (setmaxnreg per 4-warp group; the CTA launches with 80 per thread): the wide-target warps hold their
+// B fragments and the vertical accumulators in registers and take what the other two groups hand back.
+constexpr int kV5WideRegs = 104, kV5NarrowRegs = 72, kV5LumaRegs = 64;
+static_assert(kV5WideRegs + kV5NarrowRegs + kV5LumaRegs == 3 * 80, "register pool of the 3 warp groups");
 constexpr int kV5Threads = (kV5Tap + kV5Luma) * 32;
 constexpr int kHP = 48;   // horizontal-pass output plane, stored TRANSPOSED: [column 0..47][row 0..31], column pitch 48 B
 constexpr int kHCols = 48;
@@ -1928,6 +1932,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     __syncthreads();
 
     if (warp >= kV5Tap) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5LumaRegs));
         // ===== luma warps: raw rows -> (TMA) raw ring -> luma chunk ring =====
         // A raw slot is refilled by whichever luma warp finishes reading it LAST (a shared-memory counter
         // per slot tells): no issuer warp, no "slot empty" barrier to wait on, the copy of sub-chunk
@@ -2036,56 +2041,78 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     const int nk = (dbg & 2) ? 0 : a.mma_nk[warp];
     const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mma_k0[warp] * 32);
     const uint32_t poll_ns = (uint32_t)dbg >> 8;
+    const int g = lane >> 2, t = lane & 3;
+    // Vertical pass, also on the tensor pipe: out[yy, x] = sum_y V[yy, y] * hrow[y, x]; a 32-row chunk is one k-step of
+    // mma.m16n8k32.s8.u8 (A = tap digits from the per-height table, B = the transposed row plane).  Accumulators live
+    // in registers for the whole image.
     if (warp < 4) {
-        // ---- wide target (32 outputs): outputs 8 warp .. 8 warp + 7, B fragments in registers
+        // ---- wide target: warp q owns outputs 8q..8q+7 END TO END — horizontal taps (B fragments in registers), then
+        // the vertical pass of exactly those eight columns (both 16-row halves of the 32x32 plane).  It reads back only
+        // what it wrote itself, so it never meets another tap warp before the image is finished.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kV5WideRegs));
         uint2 breg[kNKP][3];
 #pragma unroll
         for (int k = 0; k < kNKP; ++k)
 #pragma unroll
             for (int tl = 0; tl < 3; ++tl)
                 breg[k][tl] = k < a.mma_nk[warp] ? __ldg(a.mma_b + a.mma_boff[warp] + (k * 3 + tl) * 32 + lane) : make_uint2(0u, 0u);
-        uint32_t chunk = 0, lph = 0;
+        uint8_t* hrow = s_hrow;  // columns 8q..8q+7 of plane 0 are this warp's private scratch
+        const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + (8 * warp + g) * kHP);
+        int32_t vc[2][3][4];
+        uint32_t lph = 0;
         int lb = 0;
         for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vc[u][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+            int ci = 0;
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
                 mbar_wait_sleep(&l_full[lb], lph, poll_ns);
-                v5_taps_wide_reg(smem_u32(s_luma + lb * L.luma_bytes) + a_off, breg, nk, pitch_bytes,
-                                 s_hrow + (chunk & 1) * (kHCols * kHP), 8 * warp, lane);
-                __syncwarp();
+                v5_taps_wide_reg(smem_u32(s_luma + lb * L.luma_bytes) + a_off, breg, nk, pitch_bytes, hrow, 8 * warp, lane);
+                __syncwarp();  // the eight columns are written
                 if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
-                compute_sync<NW>();                          // the row plane of this chunk is complete
+                if (!(dbg & 4)) {
+                    const uint32_t b0 = col[t], b1 = col[4 + t];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (ci < a.v_lo[u] || ci > a.v_hi[u]) continue;
+                        const uint4* af = a.vmma + ((size_t)(ci * 3 + u) * 3) * 32 + lane;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) mma_s8u8(vc[u][d], __ldg(af + d * 32), b0, b1);
+                    }
+                }
+                __syncwarp();  // every lane has read the columns before the next chunk overwrites them
             }
-            compute_sync<NW>();  // the planes are written (by warps 4..7)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int32_t v0 = vc[u][0][2 * hf] + (vc[u][1][2 * hf] << 8) + (vc[u][2][2 * hf] << 16);
+                    const int32_t v1 = vc[u][0][2 * hf + 1] + (vc[u][1][2 * hf + 1] << 8) + (vc[u][2][2 * hf + 1] << 16);
+                    *reinterpret_cast<uint16_t*>(s_x32 + (u * 16 + hf * 8 + g) * 32 + 8 * warp + 2 * t) =
+                        (uint16_t)pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+                }
+            compute_sync<NW>();  // both planes are complete
             dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
         }
         return;
     }
 
-    // ---- narrow target (9 outputs) + the vertical pass of both targets
-    // Vertical pass, also on the tensor pipe: out[yy, x] = sum_y V[yy, y] * hrow[y, x] per 32-row chunk is one
-    // k-step of mma.m16n8k32.s8.u8 (A = tap digits from the per-height table, B = the transposed row plane).
-    // The accumulators live in warps 4..7 for the whole image: (unit, 8-column tile) pairs
-    //   warp 4: (0,0) (0,1) (0,2)   warp 5: (0,3) (1,0) (1,1)   warp 6: (1,2) (1,3)   warp 7: (2,0) (2,1)
+    // ---- narrow target: warps 4..7 own output pairs of the 9-wide target; after their own barrier warps 4 and 5 run
+    // the vertical pass of its two 8-column tiles (columns 32..39, 40..47 of the row plane, double buffered).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5NarrowRegs));
     const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
-    constexpr int NVP = 3;
-    int32_t vc[NVP][3][4];
-    int v_unit[NVP], v_nt[NVP];
-#pragma unroll
-    for (int p = 0; p < NVP; ++p) {
-        const int idx = (warp - 4) * 3 + p;  // warps 4,5: pairs 0..5; warp 6: 6,7; warp 7: unit 2
-        v_unit[p] = warp == 7 ? (p < 2 ? 2 : -1) : (idx < 8 ? idx >> 2 : -1);
-        v_nt[p] = warp == 7 ? 4 + p : (idx & 3);
-    }
-    const int g = lane >> 2, t = lane & 3;
+    int32_t vc[3][4];
     uint32_t chunk = 0, lph = 0;
     int lb = 0;
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
 #pragma unroll
-        for (int p = 0; p < NVP; ++p)
+        for (int d = 0; d < 3; ++d)
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) vc[p][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+            for (int i = 0; i < 4; ++i) vc[d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
         int ci = 0;
         for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
             uint8_t* hrow = s_hrow + (chunk & 1) * (kHCols * kHP);
@@ -2095,40 +2122,24 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 6, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
-            compute_sync<NW>();
-            // the row plane is double buffered: the next chunk's epilogue writes the other half, and the
-            // half read here is rewritten only after the next chunk's barrier
-            if (!(dbg & 4)) {
+            asm volatile("bar.sync 2, 128;" ::: "memory");  // the narrow columns of this chunk are complete
+            // the plane is double buffered: the next chunk writes the other half, this half is rewritten after the
+            // next chunk's barrier
+            if (warp < 6 && !(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
+                const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + ((4 + warp - 4) * 8 + g) * kHP);
+                const uint32_t b0 = col[t], b1 = col[4 + t];
+                const uint4* af = a.vmma + ((size_t)(ci * 3 + 2) * 3) * 32 + lane;
 #pragma unroll
-                for (int p = 0; p < NVP; ++p) {
-                    const int u = v_unit[p];
-                    if (u < 0 || ci < a.v_lo[u] || ci > a.v_hi[u]) continue;
-                    const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + (v_nt[p] * 8 + g) * kHP);
-                    const uint32_t b0 = col[t], b1 = col[4 + t];
-                    const uint4* af = a.vmma + ((size_t)(ci * 3 + u) * 3) * 32 + lane;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) mma_s8u8(vc[p][d], __ldg(af + d * 32), b0, b1);
-                }
+                for (int d = 0; d < 3; ++d) mma_s8u8(vc[d], __ldg(af + d * 32), b0, b1);
             }
         }
-        // planes from the vertical accumulators
-#pragma unroll
-        for (int p = 0; p < NVP; ++p) {
-            const int u = v_unit[p];
-            if (u < 0) continue;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int32_t v0 = vc[p][0][2 * hf] + (vc[p][1][2 * hf] << 8) + (vc[p][2][2 * hf] << 16);
-                const int32_t v1 = vc[p][0][2 * hf + 1] + (vc[p][1][2 * hf + 1] << 8) + (vc[p][2][2 * hf + 1] << 16);
-                const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
-                if (u < 2) {
-                    *reinterpret_cast<uint16_t*>(s_x32 + (u * 16 + hf * 8 + g) * 32 + v_nt[p] * 8 + 2 * t) = (uint16_t)pk;
-                } else if (hf == 0) {  // 8x9 plane: rows g, columns (nt-4)*8 + 2t (+1) < 9
-                    const int x = (v_nt[p] - 4) * 8 + 2 * t;
-                    if (x < kDW) s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
-                    if (x + 1 < kDW) s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
-                }
-            }
+        if (warp < 6) {  // 8x9 plane: rows g, columns (warp-4)*8 + 2t (+1) < 9
+            const int32_t v0 = vc[0][0] + (vc[1][0] << 8) + (vc[2][0] << 16);
+            const int32_t v1 = vc[0][1] + (vc[1][1] << 8) + (vc[2][1] << 16);
+            const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+            const int x = (warp - 4) * 8 + 2 * t;
+            if (x < kDW) s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+            if (x + 1 < kDW) s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
         }
         compute_sync<NW>();
         dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
