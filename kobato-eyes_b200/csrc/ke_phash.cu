@@ -2153,7 +2153,7 @@ bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_by
     for (int q = 0; q < 4; ++q)
         if (a.mma_nk[q] > kNKP) return false;  // wide-target B fragments must fit the register file
     pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
-    int want_sub = 8, want_shift = 1, want_nlb = 3;
+    int want_sub = 16, want_shift = 1, want_nlb = 2;
     if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d,%d", &want_sub, &want_shift, &want_nlb);  // tuning override
     if (want_nlb < 2 || want_nlb > kMaxLumaBufs) want_nlb = 2;
     for (int sub : {want_sub, 8, 4, 2, 1}) {
