@@ -1957,7 +1957,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             for (uint32_t q = 0; q < (uint32_t)n_slots && q < total_seq; ++q) issue(q);
         // early release: when a warp's share of a sub-chunk (<= 2 rows of <= 512 pixels) fits its registers the
         // raw slot is handed back right after the loads, before the arithmetic
-        const bool early = sub_rows <= 2 * kV5Luma && a.w <= 512 && !(dbg & 16);
+        const bool early = a.w <= 512 && !(dbg & 16);  // 16 pixels (RGB, L) or 4 x 4 pixels (RGBA) per lane cover a row
         const int ng = a.w >> 4;
         const bool act = lane < ng;
         uint32_t seq = 0;
@@ -1975,49 +1975,50 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                         __syncwarp();
                         if (lane == 0) release(seq, b);
                     } else if (early) {
-                        const bool r_one = lw < srows, r_two = lw + kV5Luma < srows;
-                        const uint8_t* s0 = s_raw + b * sub_bytes + lw * row_bytes;
-                        const uint8_t* s1 = s0 + kV5Luma * row_bytes;
-                        uint8_t* d0 = dst8 + (s * sub_rows + lw) * pitch_bytes;
-                        uint8_t* d1 = d0 + kV5Luma * pitch_bytes;
-                        if (C == 3) {  // 16 pixels = 48 bytes per lane (lane stride 48 B: conflict-free LDS.128)
-                            const bool one = act && r_one, two = act && r_two;
-                            uint4 x0[3], x1[3];
+                        // rows lw, lw+NL, lw+2NL, ... of the sub-chunk, two at a time through registers.  The slot is handed back
+                        // after the warp's last row (measured: with 16-row sub-chunks handing it back before the arithmetic
+                        // of the last pair costs more in the luma warps than the earlier refill gains)
+                        for (int rr = lw; rr < srows; rr += 2 * kV5Luma) {
+                            const bool r_two = rr + kV5Luma < srows;
+                            const uint8_t* s0 = s_raw + b * sub_bytes + rr * row_bytes;
+                            const uint8_t* s1 = s0 + kV5Luma * row_bytes;
+                            uint8_t* d0 = dst8 + (s * sub_rows + rr) * pitch_bytes;
+                            uint8_t* d1 = d0 + kV5Luma * pitch_bytes;
+                            if (C == 3) {  // 16 pixels = 48 bytes per lane (lane stride 48 B: conflict-free LDS.128)
+                                const bool one = act, two = act && r_two;
+                                uint4 x0[3], x1[3];
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                x0[i] = one ? reinterpret_cast<const uint4*>(s0 + 48 * lane)[i] : make_uint4(0, 0, 0, 0);
-                                x1[i] = two ? reinterpret_cast<const uint4*>(s1 + 48 * lane)[i] : make_uint4(0, 0, 0, 0);
-                            }
-                            __syncwarp();
-                            if (lane == 0) release(seq, b);
-                            if (one) *reinterpret_cast<uint4*>(d0 + 16 * lane) = luma16_rgb(x0[0], x0[1], x0[2]);
-                            if (two) *reinterpret_cast<uint4*>(d1 + 16 * lane) = luma16_rgb(x1[0], x1[1], x1[2]);
-                        } else if (C == 4) {  // 4 pixels per 16-byte piece, piece 32 i + lane: consecutive lanes, no conflicts
-                            const int pieces = a.w >> 2;
-                            uint4 x0[4], x1[4];
+                                for (int i = 0; i < 3; ++i) {
+                                    x0[i] = one ? reinterpret_cast<const uint4*>(s0 + 48 * lane)[i] : make_uint4(0, 0, 0, 0);
+                                    x1[i] = two ? reinterpret_cast<const uint4*>(s1 + 48 * lane)[i] : make_uint4(0, 0, 0, 0);
+                                }
+                                if (one) *reinterpret_cast<uint4*>(d0 + 16 * lane) = luma16_rgb(x0[0], x0[1], x0[2]);
+                                if (two) *reinterpret_cast<uint4*>(d1 + 16 * lane) = luma16_rgb(x1[0], x1[1], x1[2]);
+                            } else if (C == 4) {  // 4 pixels per 16-byte piece, piece 32 i + lane: consecutive lanes, no conflicts
+                                const int pieces = a.w >> 2;
+                                uint4 x0[4], x1[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const bool in = 32 * i + lane < pieces;
-                                x0[i] = in && r_one ? reinterpret_cast<const uint4*>(s0)[32 * i + lane] : make_uint4(0, 0, 0, 0);
-                                x1[i] = in && r_two ? reinterpret_cast<const uint4*>(s1)[32 * i + lane] : make_uint4(0, 0, 0, 0);
-                            }
-                            __syncwarp();
-                            if (lane == 0) release(seq, b);
+                                for (int i = 0; i < 4; ++i) {
+                                    const bool in = 32 * i + lane < pieces;
+                                    x0[i] = in ? reinterpret_cast<const uint4*>(s0)[32 * i + lane] : make_uint4(0, 0, 0, 0);
+                                    x1[i] = in && r_two ? reinterpret_cast<const uint4*>(s1)[32 * i + lane] : make_uint4(0, 0, 0, 0);
+                                }
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const bool in = 32 * i + lane < pieces;
-                                if (in && r_one) reinterpret_cast<uint32_t*>(d0)[32 * i + lane] = luma4_rgba(x0[i]);
-                                if (in && r_two) reinterpret_cast<uint32_t*>(d1)[32 * i + lane] = luma4_rgba(x1[i]);
+                                for (int i = 0; i < 4; ++i) {
+                                    const bool in = 32 * i + lane < pieces;
+                                    if (in) reinterpret_cast<uint32_t*>(d0)[32 * i + lane] = luma4_rgba(x0[i]);
+                                    if (in && r_two) reinterpret_cast<uint32_t*>(d1)[32 * i + lane] = luma4_rgba(x1[i]);
+                                }
+                            } else {  // 'L': the rows are the luma rows already
+                                const bool one = act, two = act && r_two;
+                                const uint4 x0 = one ? reinterpret_cast<const uint4*>(s0)[lane] : make_uint4(0, 0, 0, 0);
+                                const uint4 x1 = two ? reinterpret_cast<const uint4*>(s1)[lane] : make_uint4(0, 0, 0, 0);
+                                if (one) reinterpret_cast<uint4*>(d0)[lane] = x0;
+                                if (two) reinterpret_cast<uint4*>(d1)[lane] = x1;
                             }
-                        } else {  // 'L': the rows are the luma rows already
-                            const bool one = act && r_one, two = act && r_two;
-                            const uint4 x0 = one ? reinterpret_cast<const uint4*>(s0)[lane] : make_uint4(0, 0, 0, 0);
-                            const uint4 x1 = two ? reinterpret_cast<const uint4*>(s1)[lane] : make_uint4(0, 0, 0, 0);
-                            __syncwarp();
-                            if (lane == 0) release(seq, b);
-                            if (one) reinterpret_cast<uint4*>(d0)[lane] = x0;
-                            if (two) reinterpret_cast<uint4*>(d1)[lane] = x1;
                         }
+                        __syncwarp();  // (a warp without rows in a short last sub-chunk still counts as a reader)
+                        if (lane == 0) release(seq, b);
                     } else {
                         if (C == 3)
                             luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, dst8 + s * sub_rows * pitch_bytes, srows, a.w,
