@@ -277,9 +277,9 @@ def run_cuda(args) -> dict:
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
     roof_k1 = {"kernel": "ke_phash_v5_kernel<3> (512x512x3; TMA ring + dp2a luma + mma.sync u8xs8 resample)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k1_gbs / hbm_peak,
-               # dram read+write per launch: 795 543 B/image measured by `ncu --set full` on an 8192-image launch of
+               # dram read+write per launch: 787 156 B/image measured by `ncu --set full` on an 8192-image launch of
                # the same kernel (profiles/r1_ncu_k1v5_summary.txt), scaled to this launch's image count
-               "traffic": int(n * 795543), "peak_source": peak_src,
+               "traffic": int(n * 787156), "peak_source": peak_src,
                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                "images_per_s": n / (k1_ms * 1e-3)}
 
