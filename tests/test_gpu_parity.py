@@ -372,7 +372,8 @@ def test_phash_fast_and_generic_kernels_agree():
 
     ctx = nat.context(torch.cuda.current_device())
     for (h, w, c, n) in ((512, 512, 3, 300), (96, 160, 3, 40), (200, 64, 4, 20), (130, 256, 1, 20), (1100, 1024, 3, 6),
-                         (70, 100, 3, 9), (512, 512, 1, 64), (512, 512, 4, 64), (300, 256, 3, 40), (31, 48, 3, 17), (640, 480, 3, 20)):
+                         (70, 100, 3, 9), (512, 512, 1, 64), (512, 512, 4, 64), (300, 256, 3, 40), (31, 48, 3, 17), (640, 480, 3, 20), (8, 16, 3, 5), (17, 512, 3, 300), (33, 512, 1, 40), (512, 16, 4, 33), (100, 496, 3, 7),
+                         (1, 32, 3, 3), (47, 512, 4, 1), (2048, 32, 3, 3)):
         imgs = ops.synth_images_device(0, n, h, w, c, n_set=n)
         ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
         try:
