@@ -14,7 +14,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
 OUT = HERE.parent / "kobato_b200" / "libkobato_b200.so"
-SOURCES = ["ke_capi.cu", "ke_join.cu", "ke_phash.cu", "ke_ssim.cu", "ke_synth.cu", "ke_refine.cu"]
+SOURCES = ["ke_capi.cu", "ke_join.cu", "ke_phash.cu", "ke_ssim.cu", "ke_synth.cu", "ke_refine.cu", "ke_resize_mma.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -55,6 +55,7 @@ extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
     cudaDeviceSynchronize();
     ke_tables_free(ctx->tables);
     ke_resize_tables_free(ctx->resize_tables);
+    ke_resize_mma_tables_free(ctx->resize_mma);
     for (auto p : ctx->d_scratch) cudaFree(p);
     for (auto p : ctx->h_pinned) cudaFreeHost(p);
     for (auto s : ctx->copy_stream)

@@ -36,6 +36,12 @@ void ke_tables_free(KeTableCache* cache);
 // Device-resident tap tables of the generic gray resize (ke_refine.cu), cached per (in, out, filter).
 struct KeResizeCache;
 void ke_resize_tables_free(KeResizeCache* cache);
+// Tables and entry of the streaming tensor-pipe resize (ke_resize_mma.cu); *taken = 0 when the shape is not its.
+struct ke_ctx;
+struct KeResizeMmaCache;
+void ke_resize_mma_tables_free(KeResizeMmaCache* cache);
+int ke_gray_resize_mma(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int w, int c, int64_t img_stride,
+                       int64_t row_stride, int out_w, int out_h, int filter, uint8_t* d_out, cudaStream_t s, int* taken);
 
 struct ke_ctx {
     int device = 0;
@@ -51,6 +57,7 @@ struct ke_ctx {
     size_t h_pinned_bytes[4] = {0, 0, 0, 0};
     KeTableCache* tables = nullptr;
     KeResizeCache* resize_tables = nullptr;
+    KeResizeMmaCache* resize_mma = nullptr;
     int force_generic_phash = 0;
     int join_mode = 0;  // KE_OPT_JOIN_MODE: 0 auto, 1 POPC kernel only, 2 hybrid (POPC + bit-sliced), 3 bit-sliced only  // KE_OPT_PHASH_GENERIC: route every geometry through the generic K1 kernel
 };

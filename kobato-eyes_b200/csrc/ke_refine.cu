@@ -14,6 +14,7 @@
 //   ke_bits_hamming_kernel / ke_plane_sad_kernel   pair (ia, ib) -> popcount(xor) / sum |a-b|
 // The intermediate [n,h,ow] plane costs ow/(w*c) of the input traffic (8 % at 512x512x3 -> 128).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -257,6 +258,14 @@ int get_table(ke_ctx* ctx, int in_size, int out_size, int filter, const RTable**
     return KE_OK;
 }
 
+}  // namespace
+
+int ke_pillow_table(int in_size, int out_size, int filter, std::vector<int32_t>& kk, std::vector<int32_t>& bd, int& ksize) {
+    return build_table(in_size, out_size, filter, kk, bd, ksize);
+}
+
+namespace {
+
 unsigned grid_for(long long work_items, int per_block, const ke_ctx* ctx) {
     long long blocks = (work_items + per_block - 1) / per_block;
     const long long cap = (long long)ctx->sm_count * 16;
@@ -281,8 +290,14 @@ extern "C" int ke_gray_resize_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n
                "ke_gray_resize_batch: strides smaller than the image");
     KeDeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const RTable *th, *tv;
     int rc;
+    if (!getenv("KE_RESIZE_GENERIC")) {  // streaming tensor-pipe kernel for the shapes it takes (ke_resize_mma.cu)
+        int taken = 0;
+        if ((rc = ke_gray_resize_mma(ctx, d_img, n, h, w, c, img_stride, row_stride, out_w, out_h, filter, d_out, s, &taken)))
+            return rc;
+        if (taken) return KE_OK;
+    }
+    const RTable *th, *tv;
     if ((rc = get_table(ctx, w, out_w, filter, &th))) return rc;
     if ((rc = get_table(ctx, h, out_h, filter, &tv))) return rc;
     const unsigned gh = grid_for(n * h * out_w, 256, ctx), gv = grid_for(n * out_h * out_w, 256, ctx);

@@ -303,11 +303,13 @@ def test_dropin_decisions_equal_the_live_reference(tmp_path, oracle_ops):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(512, 512, 3), (300, 200, 3), (33, 47, 3), (100, 33, 1), (480, 640, 4), (32, 32, 1), (31, 29, 3),
-                                   (128, 128, 1), (700, 45, 3), (5, 3, 3)])
+                                   (128, 128, 1), (700, 45, 3), (5, 3, 3), (256, 512, 4), (512, 256, 3), (96, 160, 3), (300, 256, 3),
+                                   (130, 144, 1), (48, 80, 4), (512, 512, 1)])
 def test_gray_resize_is_byte_identical_to_pillow(shape):
     h, w, c = shape
     imgs = synth.synth_images(0, 5, h, w, c, n_set=5)
     for (ow, oh), flt in (((128, 128), "bilinear"), ((32, 32), "bilinear"), ((64, 64), "bilinear"), ((w, 17), "bilinear"),
+                          ((64, 32), "bilinear"), ((24, 48), "bilinear"), ((64, 64), "lanczos"), ((128, 16), "lanczos"),
                           ((9, h), "bilinear"), ((32, 32), "lanczos"), ((9, 8), "lanczos"), ((w, h), "bilinear"),
                           ((2 * w + 1, 3 * h), "bilinear")):
         got = ops.gray_resize_batch(imgs, ow, oh, flt).cpu().numpy()

@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     torch.cuda.set_device(0)
-    only = set(args.only.split(",")) if args.only else {"phash", "join", "ssim"}
+    only = set(args.only.split(",")) if args.only else {"phash", "join", "ssim", "n1"}
     if "phash" in only:
         bank = ops.synth_images_device(0, args.images, 512, 512, 3, n_set=args.images)
         ops.phash_dhash_batch(bank[:64])
@@ -48,6 +48,25 @@ def main():
         gbs = args.images * 786448 / (min(t) * 1e-3) / 1e9
         print(f"phash: {args.images} images 512x512x3: ms={t} -> {args.images / (min(t) * 1e-3):.3e} img/s, {gbs:.1f} GB/s")
         del bank
+    if "n1" in only:
+        bank = ops.synth_images_device(0, args.images, 512, 512, 3, n_set=args.images)
+        for side, grid, tile in ((64, 8, 8), (32, 4, 8), (128, 16, 8)):
+            def run():
+                planes = ops.gray_resize_batch(bank, side, side, "bilinear")
+                return ops.tile_ahash_bits(planes, grid, tile)
+            run()
+            t = timed(run, args.reps)
+            gbs = args.images * 786432 / (min(t) * 1e-3) / 1e9
+            print(f"n1 tile-aHash {grid}x{tile} ({side}x{side}): {args.images} images 512x512x3: ms={t} -> "
+                  f"{args.images / (min(t) * 1e-3):.3e} img/s, {gbs:.1f} GB/s")
+        planes = ops.gray_resize_batch(bank, 128, 128, "bilinear")
+        g = torch.Generator().manual_seed(2)
+        ia = torch.randint(0, args.images, (200000,), generator=g).cuda()
+        ib = torch.randint(0, args.images, (200000,), generator=g).cuda()
+        t = timed(lambda: ops.plane_sad_pairs(planes, ia, ib), args.reps)
+        print(f"n1 pixel SAD 128x128: 200000 pairs: ms={t} -> {200000 / (min(t) * 1e-3):.3e} pairs/s, "
+              f"{200000 * 32768 / (min(t) * 1e-3) / 1e9:.1f} GB/s")
+        del bank, planes
     if "join" in only:
         h = torch.from_numpy(synth.synth_hashes(args.hashes).view(np.int64)).cuda()
         ops.hamming_join(h[:4096], 8)
