@@ -349,6 +349,19 @@ def run_cuda(args) -> dict:
                "pairs": world * n_pairs, "bank_images": m_bank, "ms": k3_ms, "peak_source": peak_src}
     del crops, bank_l, ia, ib, hashes
 
+    # N1 (the refinement the UI runs after a scan): tile aHash at the UI default (grid 8 x tile 8 -> 64x64
+    # BILINEAR planes -> 4096 bits) over the resident bank; HBM bound like K1 (bytes/image = h*w*c + 64*64 + 512)
+    def run_n1():
+        planes = ops.gray_resize_batch(bank, 64, 64, "bilinear")
+        return ops.tile_ahash_bits(planes, 8, 8)
+
+    n1_ms = timed(run_n1)
+    n1_bytes = n * (IMG_BYTES + 64 * 64 + 512)
+    n1_gbs = n1_bytes / (n1_ms * 1e-3) / 1e9
+    roof_n1 = {"kernel": "ke_resize_mma_kernel<3> + ke_tile_bits_kernel (tile aHash 8x8, 64x64 BILINEAR planes)", "bound": "hbm",
+               "achieved": n1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": n1_gbs / hbm_peak,
+               "images_per_s": n / (n1_ms * 1e-3), "ms": n1_ms, "peak_source": peak_src}
+
     # ---- end to end from pinned host memory ---------------------------------------------------
     import psutil
 
@@ -392,7 +405,7 @@ def run_cuda(args) -> dict:
                    "parallelism": f"image shards x{world}; join tiles t%{world}; SSIM pairs by owner"},
         "counts": counts,
         "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-        "roofline": roof_k1, "roofline_join": roof_k2, "roofline_ssim": roof_k3,
+        "roofline": roof_k1, "roofline_join": roof_k2, "roofline_ssim": roof_k3, "roofline_n1": roof_n1,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
