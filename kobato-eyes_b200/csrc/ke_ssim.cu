@@ -282,6 +282,12 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
 // (pair, 256 output columns), now walked by 64 threads; the 7-row ring lives in registers (84 of them).
 
 constexpr int kT4 = 64;
+#ifndef KE_SSIM4_CTAS
+#define KE_SSIM4_CTAS 6
+#endif
+#ifndef KE_SSIM4S_CTAS
+#define KE_SSIM4S_CTAS 6
+#endif
 
 __device__ __forceinline__ HSum hsum7_words(uint32_t ua, uint32_t ub, uint32_t va, uint32_t vb) {
     const uint32_t ubm = ub & 0x00FFFFFFu, vbm = vb & 0x00FFFFFFu;
@@ -316,7 +322,7 @@ __device__ __forceinline__ float2 ssim_point2(uint32_t s0, uint32_t t0, uint32_t
 }
 
 template <int C>
-__global__ void __launch_bounds__(kT4) ke_ssim4_kernel(const SsimArgs a) {
+__global__ void __launch_bounds__(kT4, KE_SSIM4_CTAS) ke_ssim4_kernel(const SsimArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int strip_bytes = (kStripRows * a.pitch + 32 + 127) / 128 * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * strip_bytes);
@@ -594,7 +600,7 @@ __device__ __forceinline__ float ssim4_strip(Ssim4State& st, const uint32_t* su,
 }
 
 template <int C>
-__global__ void __launch_bounds__(kT4) ke_ssim4s_kernel(const SsimArgs a, const int raw_pitch) {
+__global__ void __launch_bounds__(kT4, KE_SSIM4S_CTAS) ke_ssim4s_kernel(const SsimArgs a, const int raw_pitch) {
     extern __shared__ __align__(128) uint8_t smem[];
     // C > 1: [raw u | raw v] (one strip, refilled under the arithmetic) + [luma u | luma v];  C == 1: 2 x [luma u | luma v]
     const int luma_bytes = (kSR2 * a.pitch + 32 + 127) / 128 * 128;
