@@ -11,8 +11,7 @@
 //                   digits).  Output rows come in units of 16; a unit's support spans a few 32-row chunks and at most
 //                   two units (of different parity) are live at a time, so the vertical accumulators are two register
 //                   slots that are flushed to the output plane when their unit's last chunk has passed.
-// One launch covers up to 64 output columns and 128 output rows; wider targets are covered by two launches over
-// column halves.  Shapes it does not take (w % 16, w > 512, out sizes not multiples of 8 / 16, nearly 1:1 scales) stay
+// One launch covers up to 128 output columns (tap warp q owns the 8-column groups q and q + 8) and 128 output rows.  Shapes it does not take (w % 16, w > 512, out sizes not multiples of 8 / 16, nearly 1:1 scales) stay
 // on the generic kernels of ke_refine.cu.
 //
 // Algorithmic HBM bytes per image: h*w*c read + out_w*out_h written.
@@ -31,7 +30,7 @@ namespace {
 constexpr int kTap = 8, kLuma = 4, kThreads = (kTap + kLuma) * 32;
 constexpr int kTapRegs = 88, kLumaRegs = 64;  // setmaxnreg per 4-warp group; the CTA launches with 80 per thread
 static_assert(2 * kTapRegs + kLumaRegs == 3 * 80, "register pool of the 3 warp groups");
-constexpr int kPrec = 22, kCR = 32, kHP = 48, kSlots = 2, kMaxUnits = 8, kMaxGroups = 8;
+constexpr int kPrec = 22, kCR = 32, kHP = 48, kSlots = 2, kMaxUnits = 8, kMaxGroups = 16;  // groups per launch: 8 tap warps x <= 2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -130,7 +129,7 @@ struct ResizeArgs {
     long long n, img_stride;
     int h, w;
     int sub_rows, pitch_bytes;
-    int n_groups;                 // 8-column output groups in this launch (<= 8), warp q owns group q
+    int n_groups;                 // 8-column output groups in this launch (<= 16), warp q owns groups q and q + 8
     int col_begin;                // first output column of this launch
     int out_w, out_h, n_units;    // full output plane geometry; n_units = out_h / 16
     const uint2* hb;              // horizontal B fragments [group][k][digit][lane]
@@ -164,7 +163,7 @@ __host__ __device__ inline Layout make_layout(int sub_bytes, int pitch_bytes, in
     return L;
 }
 
-template <int C>
+template <int C, int GP>
 __global__ void __launch_bounds__(kThreads, 2) ke_resize_mma_kernel(const ResizeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int row_bytes = a.w * C;
@@ -271,90 +270,121 @@ __global__ void __launch_bounds__(kThreads, 2) ke_resize_mma_kernel(const Resize
         return;
     }
 
-    // ===== tap warps: warp q owns output columns col_begin + 8q .. + 7 end to end =====
+    // ===== tap warps: warp q owns output column groups q (and q + 8 when GP == 2) end to end =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTapRegs));
-    const bool mine = warp < a.n_groups;  // idle tap warps still take part in the luma ring hand-shake
     const int g = lane >> 2, t = lane & 3;
-    const int nk = mine ? a.h_nk[warp] : 0;
-    const uint2* bw = s_b + (mine ? a.h_off[warp] : 0) + lane;
-    const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + (mine ? a.h_k0[warp] : 0) * 32);
+    const uint32_t row_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16);
     uint8_t* scr = s_scr + warp * (8 * kHP);
     const uint32_t* col = reinterpret_cast<const uint32_t*>(scr + g * kHP);
-    const int out_col = a.col_begin + 8 * warp + 2 * t;
-    int32_t vc[2][3][4];  // two live units (slot = unit & 1), three digits
+    int32_t vc[GP][2][3][4];  // per group: two live units (slot = unit & 1), three digits
     uint32_t chunk = 0;
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
+        for (int gp = 0; gp < GP; ++gp)
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
+            for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) vc[sl][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vc[gp][sl][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
         uint8_t* out_img = a.out + im * (long long)a.out_h * a.out_w;
         int ci = 0;
         for (int r0 = 0; r0 < a.h; r0 += kCR, ++chunk, ++ci) {
             const int lb = chunk & 1;
             mbar_wait_sleep(&l_full[lb], (chunk >> 1) & 1u, 200);
-            if (mine) {
-                // horizontal: two 16-row blocks x three digit tiles over the group's band
-                const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
-                int32_t c[2][3][4];
+            const uint32_t luma_addr = smem_u32(s_luma + lb * L.luma_bytes) + row_off;
 #pragma unroll
-                for (int rb = 0; rb < 2; ++rb)
+            for (int gp = 0; gp < GP; ++gp) {
+                const int grp = warp + kTap * gp;
+                if (grp >= a.n_groups) continue;  // idle tap warps still take part in the luma ring hand-shake below
+                const int nk = a.h_nk[grp];
+                const uint2* bw = s_b + a.h_off[grp] + lane;
+                const uint32_t a_addr = luma_addr + a.h_k0[grp] * 32;
+                if (GP == 1) {
+                    // horizontal: two 16-row blocks x three digit tiles over the group's band, one B load per two MMAs
+                    int32_t c[2][3][4];
 #pragma unroll
-                    for (int tl = 0; tl < 3; ++tl)
+                    for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) c[rb][tl][i] = tl == 0 ? (1 << (kPrec - 1)) : 0;
+                        for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) c[rb][tl][i] = tl == 0 ? (1 << (kPrec - 1)) : 0;
 #pragma unroll 2
-                for (int k = 0; k < nk; ++k) {
-                    uint32_t a0[4], a1[4];
-                    ldmatrix_x4(a0, a_addr + k * 32);
-                    ldmatrix_x4(a1, a_addr + k * 32 + 16 * pitch_bytes);
+                    for (int k = 0; k < nk; ++k) {
+                        uint32_t a0[4], a1[4];
+                        ldmatrix_x4(a0, a_addr + k * 32);
+                        ldmatrix_x4(a1, a_addr + k * 32 + 16 * pitch_bytes);
 #pragma unroll
-                    for (int tl = 0; tl < 3; ++tl) {
-                        const uint2 b = bw[(k * 3 + tl) * 32];
-                        mma_u8s8(c[0][tl], a0, b);
-                        mma_u8s8(c[1][tl], a1, b);
+                        for (int tl = 0; tl < 3; ++tl) {
+                            const uint2 b = bw[(k * 3 + tl) * 32];
+                            mma_u8s8(c[0][tl], a0, b);
+                            mma_u8s8(c[1][tl], a1, b);
+                        }
+                    }
+#pragma unroll
+                    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int32_t v0 = c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
+                            const int32_t v1 = c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
+                            const int row = rb * 16 + hf * 8 + g;
+                            scr[(2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
+                            scr[(2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
+                        }
+                } else {
+                    // two groups per warp: one 16-row block at a time keeps the horizontal accumulators at 12 registers
+#pragma unroll
+                    for (int rb = 0; rb < 2; ++rb) {
+                        int32_t c[3][4];
+#pragma unroll
+                        for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) c[tl][i] = tl == 0 ? (1 << (kPrec - 1)) : 0;
+                        for (int k = 0; k < nk; ++k) {
+                            uint32_t a0[4];
+                            ldmatrix_x4(a0, a_addr + k * 32 + rb * 16 * pitch_bytes);
+#pragma unroll
+                            for (int tl = 0; tl < 3; ++tl) mma_u8s8(c[tl], a0, bw[(k * 3 + tl) * 32]);
+                        }
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int32_t v0 = c[0][2 * hf] + (c[1][2 * hf] << 8) + (c[2][2 * hf] << 16);
+                            const int32_t v1 = c[0][2 * hf + 1] + (c[1][2 * hf + 1] << 8) + (c[2][2 * hf + 1] << 16);
+                            const int row = rb * 16 + hf * 8 + g;
+                            scr[(2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
+                            scr[(2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
+                        }
                     }
                 }
-#pragma unroll
-                for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int32_t v0 = c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
-                        const int32_t v1 = c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
-                        const int row = rb * 16 + hf * 8 + g;
-                        scr[(2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
-                        scr[(2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
-                    }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&l_empty[lb]);  // this warp no longer reads the luma buffer
-            if (mine) {
+                __syncwarp();  // the eight columns of this chunk are in the scratch
                 // vertical: this chunk is one k-step for every live unit; a unit is flushed after its last chunk
                 const uint32_t b0 = col[t], b1 = col[4 + t];
+                const int out_col = a.col_begin + 8 * grp + 2 * t;
 #pragma unroll
                 for (int u = 0; u < kMaxUnits; ++u) {
                     if (u >= a.n_units || ci < a.v_lo[u] || ci > a.v_hi[u]) continue;
                     const uint4* af = a.va + ((size_t)(ci * a.n_units + u) * 3) * 32 + lane;
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) mma_s8u8(vc[u & 1][d], __ldg(af + d * 32), b0, b1);
+                    for (int d = 0; d < 3; ++d) mma_s8u8(vc[gp][u & 1][d], __ldg(af + d * 32), b0, b1);
                     if (ci == a.v_hi[u]) {
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
-                            const int32_t v0 = vc[u & 1][0][2 * hf] + (vc[u & 1][1][2 * hf] << 8) + (vc[u & 1][2][2 * hf] << 16);
-                            const int32_t v1 = vc[u & 1][0][2 * hf + 1] + (vc[u & 1][1][2 * hf + 1] << 8) + (vc[u & 1][2][2 * hf + 1] << 16);
+                            const int32_t v0 = vc[gp][u & 1][0][2 * hf] + (vc[gp][u & 1][1][2 * hf] << 8) + (vc[gp][u & 1][2][2 * hf] << 16);
+                            const int32_t v1 = vc[gp][u & 1][0][2 * hf + 1] + (vc[gp][u & 1][1][2 * hf + 1] << 8) +
+                                               (vc[gp][u & 1][2][2 * hf + 1] << 16);
                             *reinterpret_cast<uint16_t*>(out_img + (long long)(16 * u + hf * 8 + g) * a.out_w + out_col) =
                                 (uint16_t)pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
                         }
 #pragma unroll
                         for (int d = 0; d < 3; ++d)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) vc[u & 1][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+                            for (int i = 0; i < 4; ++i) vc[gp][u & 1][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
                     }
                 }
+                __syncwarp();  // every lane has read the scratch columns before they are overwritten
             }
-            __syncwarp();  // every lane has read the scratch columns before the next chunk overwrites them
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&l_empty[lb]);  // this warp no longer reads the luma buffer
         }
     }
 }
@@ -472,15 +502,15 @@ int build_tables(int w, int h, int out_w, int out_h, int filter, MmaTables& T) {
     return KE_OK;
 }
 
-template <int C>
+template <int C, int GP>
 int launch(ke_ctx* ctx, const ResizeArgs& a, int smem, cudaStream_t s) {
-    KE_CUDA(cudaFuncSetAttribute(ke_resize_mma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KE_CUDA(cudaFuncSetAttribute(ke_resize_mma_kernel<C, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
-    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_resize_mma_kernel<C>, kThreads, smem));
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_resize_mma_kernel<C, GP>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > a.n) grid = a.n;
-    ke_resize_mma_kernel<C><<<(unsigned)grid, kThreads, smem, s>>>(a);
+    ke_resize_mma_kernel<C, GP><<<(unsigned)grid, kThreads, smem, s>>>(a);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;
@@ -524,7 +554,7 @@ int ke_gray_resize_mma(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int 
             }
     }
     if (!sub_rows) return KE_OK;
-    for (int g0 = 0; g0 < T.n_groups; g0 += kMaxGroups) {  // up to 64 output columns per launch
+    for (int g0 = 0; g0 < T.n_groups; g0 += kMaxGroups) {  // up to 128 output columns per launch
         ResizeArgs a;
         a.img = d_img;
         a.n = n;
@@ -551,10 +581,11 @@ int ke_gray_resize_mma(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int 
         a.sub_rows = sub_rows;
         const int smem = make_layout((int)(sub_rows * row_bytes), pitch_bytes, a.hb_words).total;
         int rc;
+        const bool two = a.n_groups > kTap;
         switch (c) {
-            case 1: rc = launch<1>(ctx, a, smem, s); break;
-            case 3: rc = launch<3>(ctx, a, smem, s); break;
-            default: rc = launch<4>(ctx, a, smem, s); break;
+            case 1: rc = two ? launch<1, 2>(ctx, a, smem, s) : launch<1, 1>(ctx, a, smem, s); break;
+            case 3: rc = two ? launch<3, 2>(ctx, a, smem, s) : launch<3, 1>(ctx, a, smem, s); break;
+            default: rc = two ? launch<4, 2>(ctx, a, smem, s) : launch<4, 1>(ctx, a, smem, s); break;
         }
         if (rc) return rc;
     }
