@@ -76,6 +76,28 @@ def all_gather_varlen(local):
     return torch.cat([p[:c] for p, c in zip(parts, counts)])
 
 
+def all_gather_rows(local):
+    """Concatenate ``[m_r, k]`` tensors (per-rank m_r) along dim 0 on every rank with TWO collectives: the row counts,
+    then one padded all_gather of the rows."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    if size == 1:
+        return local
+    local = local.contiguous()
+    k = local.shape[1]
+    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(size)]
+    dist.all_gather(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device))
+    counts = torch.cat(counts).tolist()
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap, k), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts = [torch.empty((cap, k), dtype=local.dtype, device=local.device) for _ in range(size)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
 def broadcast_table(table, src: int = 0):
     """Rank `src` holds the table (int64 tensor); every rank returns its own copy."""
     import torch

@@ -117,13 +117,14 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
     li, lj, ld = ops.hamming_join_device(table, threshold, require_band=require_band, part_index=rank,
                                          part_count=size, capacity=max(1 << 16, 2 * total))
     tm.mark("join")
-    # every rank gets every candidate (three small NCCL all_gathers), sorted by (i, j) on the device
-    gi, gj, gd = kdist.all_gather_varlen(li), kdist.all_gather_varlen(lj), kdist.all_gather_varlen(ld)
-    key = (gi.to(torch.int64) & 0xFFFFFFFF) << 32 | (gj.to(torch.int64) & 0xFFFFFFFF)
-    order = torch.argsort(key)
-    ci = (gi[order].to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
-    cj = (gj[order].to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
-    cd = gd[order].cpu().numpy()
+    # every rank gets every candidate: one packed gather of (i << 32 | j, dist) rows, sorted by (i, j) on the device,
+    # one device->host copy
+    key = (li.to(torch.int64) & 0xFFFFFFFF) << 32 | (lj.to(torch.int64) & 0xFFFFFFFF)
+    rows = kdist.all_gather_rows(torch.stack([key, ld.to(torch.int64)], dim=1))
+    rows = rows[torch.argsort(rows[:, 0])].cpu().numpy()
+    ci = (rows[:, 0] >> 32) & 0xFFFFFFFF
+    cj = rows[:, 0] & 0xFFFFFFFF
+    cd = rows[:, 1].astype(np.uint8)
     out.bytes_d2h += 9 * len(ci)
     out.counts.update(images_local=int(n), images_total=int(total), candidates=int(len(ci)))
 

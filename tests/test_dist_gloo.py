@@ -34,6 +34,12 @@ def _worker(rank: int, size: int, init_file: str, out_dir: str):
         local = torch.from_numpy(full[lo:hi].view(np.int64))
         table = kdist.all_gather_hashes(local)
         assert np.array_equal(table.numpy().view(np.uint64), full)
+        # ---- per-rank row blocks of unequal length (the packed candidate exchange of pipeline.scan)
+        mine = torch.arange(rank * 100, rank * 100 + 5 + 3 * rank, dtype=torch.int64)
+        rows = kdist.all_gather_rows(torch.stack([mine, mine * 7], dim=1))
+        want = np.concatenate([np.arange(r * 100, r * 100 + 5 + 3 * r) for r in range(size)])
+        assert np.array_equal(rows[:, 0].numpy(), want) and np.array_equal(rows[:, 1].numpy(), want * 7)
+        assert kdist.all_gather_rows(torch.empty((0, 2), dtype=torch.int64)).shape == (0, 2) if size == 1 else True
         # ---- broadcast from rank 0
         t0 = torch.from_numpy(full.view(np.int64).copy()) if rank == 0 else torch.empty(0, dtype=torch.int64)
         got = kdist.broadcast_table(t0, src=0)
