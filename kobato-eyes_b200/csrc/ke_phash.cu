@@ -1720,17 +1720,22 @@ int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
 
 // ------------------------------------------------------------------ tensor-core kernel (v5)
 //
-// The horizontal resample IS a matrix product (luma rows x banded tap matrix), and with the taps in
-// balanced base-256 digits it is an exact u8 x s8 -> s32 one.  v5 keeps v4's rings (1-D TMA raw ring ->
-// luma warps -> 2 x 32-row luma ring) and replaces the dp4a tap phase by mma.sync.m16n8k32 on the tensor
-// pipe, which otherwise idles: per 32-row chunk a tap warp loads A fragments with ldmatrix.x4 (luma pitch
-// = w rounded to 32, + 16: conflict free), B fragments (constant per width, staged once in shared
-// memory, lane-major 8 bytes -> conflict-free LDS.64) and keeps two 16-row blocks of accumulators in
-// registers.  Digits are recombined in the epilogue: (2^21 + d0 + 256 d1 + 65536 d2) >> 22, clip, and the
-// bytes go to a double-buffered [32][48] row plane for the (unchanged) streamed vertical pass.
-//     warps 0..3   outputs 8q..8q+7 of the 32-wide target: 3 tiles (digits) x <= 8 k-steps
-//     warps 4..7   output pairs of the 9-wide target: 1 tile (2 for warp 7) x <= 16 k-steps
-//     warps 8..11  luma warps (warp 8 / lane 0 issues the TMA copies)
+// Both resamples ARE matrix products (rows x banded tap matrix), and with the 22-bit taps in balanced base-256
+// digits they are exact u8 x s8 -> s32 ones: v5 keeps v4's rings (1-D TMA raw slots -> luma warps -> 2 x 32-row
+// luma ring) and runs them on the tensor pipe, which otherwise idles (mma.sync.m16n8k32, IMMA.16832).
+//     warps 0..3   "wide target": warp q owns outputs 8q..8q+7 of the 32-wide plane END TO END.  Per 32-row chunk:
+//                  A fragments by ldmatrix.x4 from the luma ring (pitch = w rounded to 32, + 16: conflict free), B
+//                  fragments (3 digits x <= 8 k-steps, constant per width) in registers, epilogue
+//                  (2^21 + d0 + 256 d1 + 65536 d2) >> 22 -> cvt.pack.sat -> its eight columns TRANSPOSED into a
+//                  private scratch -> read back as the B fragment of the vertical pass (A = vertical tap digits of
+//                  this chunk, accumulators for both 16-row halves of the 32x32 plane in registers all image long).
+//                  No barrier with any other warp before the image is finished.
+//     warps 4..7   "narrow target": output pairs of the 9-wide plane (B fragments in shared memory), their own
+//                  128-thread barrier per chunk, then warps 4 and 5 run the vertical pass of the 8x9 plane.
+//     warps 8..11  luma warps: wait for a 16-row raw slot, 16 pixels per lane through registers (2 dp2a per pixel),
+//                  the LAST reader of a slot (shared-memory counter) issues the next TMA copy into it.
+// Image end: all eight tap warps meet for the FP64 DCT and the bits.  setmaxnreg gives the three 4-warp groups
+// 104 / 72 / 64 registers out of the 80 per thread the CTA launches with.
 
 constexpr int kV5Tap = 8, kV5Luma = 4;
 // Registers per role (setmaxnreg per 4-warp group; the CTA launches with 80 per thread): the wide-target warps hold their
@@ -1791,10 +1796,6 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int32_t hi, int32_t lo) {  // sa
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(0));
     return d;
 }
-__device__ __forceinline__ uint32_t clip8u(int32_t v) {
-    v >>= kPrec;
-    return (uint32_t)min(max(v, 0), 255);
-}
 
 // One 32-row luma chunk -> this warp's columns of the row plane.  NT tiles share the k range.
 // WIDE: tiles are the three digits of outputs out0..out0+7; else tile tl is the output pair (out0 + 2 tl, +1).
@@ -1822,18 +1823,7 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
         }
     }
     const int g = lane >> 2, t = lane & 3;
-    if (WIDE) {
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int32_t v0 = c[rb][0][2 * hf] + (c[rb][1][2 * hf] << 8) + (c[rb][2][2 * hf] << 16);
-                const int32_t v1 = c[rb][0][2 * hf + 1] + (c[rb][1][2 * hf + 1] << 8) + (c[rb][2][2 * hf + 1] << 16);
-                const int row = rb * 16 + hf * 8 + g;
-                hrow[(out0 + 2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
-                hrow[(out0 + 2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
-            }
-    } else {
+    {
         const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb)
