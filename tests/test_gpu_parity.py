@@ -449,3 +449,36 @@ def test_join_config_c5_ten_million_hashes():
     want = set(zip(src[dist <= 8].tolist(), (np.flatnonzero(dist <= 8) + n_base).tolist()))
     got = set(zip(i.tolist(), j.tolist()))
     assert want <= got and len(want) > 300_000
+
+
+def test_streaming_kernels_random_batches_match_the_generic_kernels():
+    """K1 v5 and the N1 streaming resize on random batch sizes (ring / slot hand-off paths with n below, at and
+    above the persistent grid) against the generic kernels: hashes, planes and resized planes identical."""
+    import os
+
+    torch = _torch()
+    from kobato_b200 import _native as nat
+
+    ctx = nat.context(torch.cuda.current_device())
+    rng = np.random.default_rng(77)
+    shapes = [(512, 512, 3), (512, 512, 1), (512, 512, 4), (96, 160, 3), (300, 256, 3), (47, 512, 4), (33, 512, 1)]
+    for it in range(21):
+        h, w, c = shapes[it % len(shapes)]
+        n = int(rng.integers(1, 700))
+        imgs = ops.synth_images_device(int(rng.integers(0, 1 << 20)), n, h, w, c, n_set=1 << 30)
+        got = ops.phash_dhash_batch(imgs, want_planes=True)
+        ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
+        try:
+            ref = ops.phash_dhash_batch(imgs, want_planes=True)
+        finally:
+            ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), (it, h, w, c, n)
+        assert torch.equal(got[2][0], ref[2][0]) and torch.equal(got[2][1], ref[2][1]), (it, h, w, c, n)
+        side = (32, 64, 128)[it % 3]
+        fast = ops.gray_resize_batch(imgs, side, side, "bilinear")
+        os.environ["KE_RESIZE_GENERIC"] = "1"
+        try:
+            slow = ops.gray_resize_batch(imgs, side, side, "bilinear")
+        finally:
+            os.environ.pop("KE_RESIZE_GENERIC", None)
+        assert torch.equal(fast, slow), (it, h, w, c, n, side)
