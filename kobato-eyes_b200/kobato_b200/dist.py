@@ -15,7 +15,11 @@ from __future__ import annotations
 
 from typing import Callable
 
+import os
+
 import numpy as np
+
+_LEGACY = bool(os.environ.get("KE_DIST_LIST_COLLECTIVES"))  # tuning probe: list-based all_gather instead of the flat one
 
 
 def _dist():
@@ -38,42 +42,78 @@ def shard_range(n: int, rank: int, size: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def all_gather_hashes(local):
-    """Concatenate per-rank int64 hash shards (possibly of different lengths) on every rank."""
+def _gather_counts(n_local: int, device) -> list[int]:
+    """Row counts of every rank: one collective into one tensor, one device->host read."""
     import torch
 
     dist = _dist()
+    _, size = world()
+    mine = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    out = torch.empty(size, dtype=torch.int64, device=device)
+    try:
+        if _LEGACY:
+            raise NotImplementedError
+        dist.all_gather_into_tensor(out, mine)
+    except (RuntimeError, NotImplementedError, AttributeError):  # backends without the flat variant
+        parts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(size)]
+        dist.all_gather(parts, mine)
+        out = torch.cat(parts)
+    return out.tolist()
+
+
+def _gather_padded(padded):
+    """[cap, ...] from every rank -> [size, cap, ...] with one collective."""
+    import torch
+
+    dist = _dist()
+    _, size = world()
+    out = torch.empty((size,) + tuple(padded.shape), dtype=padded.dtype, device=padded.device)
+    try:
+        if _LEGACY:
+            raise NotImplementedError
+        dist.all_gather_into_tensor(out.view(-1), padded.reshape(-1))
+    except (RuntimeError, NotImplementedError, AttributeError):
+        parts = [torch.empty_like(padded) for _ in range(size)]
+        dist.all_gather(parts, padded)
+        out = torch.stack(parts)
+    return out
+
+
+def all_gather_hashes(local):
+    """Concatenate per-rank int64 hash shards (possibly of different lengths) on every rank: the counts, then ONE
+    all_gather of the (padded) shards; equal shards (the weak-scaling case) need no padding and no re-packing."""
+    import torch
+
     rank, size = world()
     if size == 1:
         return local
-    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(size)]
-    dist.all_gather(counts, torch.tensor([local.numel()], dtype=torch.int64, device=local.device))
-    counts = [int(c.item()) for c in counts]
-    cap = max(counts)
-    padded = torch.zeros(cap, dtype=torch.int64, device=local.device)
-    padded[: local.numel()] = local
-    parts = [torch.empty(cap, dtype=torch.int64, device=local.device) for _ in range(size)]
-    dist.all_gather(parts, padded)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    local = local.contiguous().view(-1)
+    counts = _gather_counts(local.numel(), local.device)
+    cap = max(max(counts), 1)
+    if local.numel() == cap:
+        padded = local
+    else:
+        padded = torch.zeros(cap, dtype=local.dtype, device=local.device)
+        padded[: local.numel()] = local
+    out = _gather_padded(padded)
+    if all(c == cap for c in counts):
+        return out.view(-1)
+    return torch.cat([out[r, :c] for r, c in enumerate(counts)])
 
 
 def all_gather_varlen(local):
     """Concatenate 1-D tensors of any dtype and per-rank length on every rank (padded all_gather)."""
     import torch
 
-    dist = _dist()
     rank, size = world()
     if size == 1:
         return local
-    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(size)]
-    dist.all_gather(counts, torch.tensor([local.numel()], dtype=torch.int64, device=local.device))
-    counts = [int(c.item()) for c in counts]
+    counts = _gather_counts(local.numel(), local.device)
     cap = max(max(counts), 1)
     padded = torch.zeros(cap, dtype=local.dtype, device=local.device)
     padded[: local.numel()] = local
-    parts = [torch.empty(cap, dtype=local.dtype, device=local.device) for _ in range(size)]
-    dist.all_gather(parts, padded)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    out = _gather_padded(padded)
+    return torch.cat([out[r, :c] for r, c in enumerate(counts)])
 
 
 def all_gather_rows(local):
@@ -81,21 +121,17 @@ def all_gather_rows(local):
     then one padded all_gather of the rows."""
     import torch
 
-    dist = _dist()
     rank, size = world()
     if size == 1:
         return local
     local = local.contiguous()
     k = local.shape[1]
-    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(size)]
-    dist.all_gather(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device))
-    counts = torch.cat(counts).tolist()
+    counts = _gather_counts(local.shape[0], local.device)
     cap = max(max(counts), 1)
     padded = torch.zeros((cap, k), dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
-    parts = [torch.empty((cap, k), dtype=local.dtype, device=local.device) for _ in range(size)]
-    dist.all_gather(parts, padded)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    out = _gather_padded(padded)
+    return torch.cat([out[r, :c] for r, c in enumerate(counts)])
 
 
 def broadcast_table(table, src: int = 0):

@@ -12,6 +12,7 @@ Per rank (one process per GPU):
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 
@@ -141,16 +142,27 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
     tm.mark("ssim")
     cross = np.flatnonzero(own_i != own_j)
     if size > 1 and len(cross):
+        # the rare cross-shard pairs: rank a (owner of i) scores the pair, rank b ships image j; all transfers are posted
+        # before the first wait
         dist = kdist._dist()
         tmp = torch.empty((2 * len(cross), h, w, c), dtype=torch.uint8, device=dev)
+        p2p, sel = [], []
         for k, q in enumerate(cross.tolist()):
-            a, b = int(own_i[q]), int(own_j[q])  # rank a scores the pair, rank b ships image j
+            a, b = int(own_i[q]), int(own_j[q])
             if rank == a:
                 tmp[2 * k].copy_(bank[int(ci[q]) - a * n_loc])
-                dist.recv(tmp[2 * k + 1], src=b)
+                p2p.append(dist.P2POp(dist.irecv, tmp[2 * k + 1], b))
+                sel.append(k)
             elif rank == b:
-                dist.send(bank[int(cj[q]) - b * n_loc].contiguous(), dst=a)
-        sel = [k for k, q in enumerate(cross.tolist()) if int(own_i[q]) == rank]
+                p2p.append(dist.P2POp(dist.isend, bank[int(cj[q]) - b * n_loc].contiguous(), a))
+        # plain isend/irecv: batch_isend_irecv measured ~10 ms slower per step here (2 x B200, NCCL 2.28: the grouped
+        # point-to-point launch stalls the step's next collective)
+        if p2p and os.environ.get("KE_P2P_BATCHED"):  # tuning probe
+            for req in dist.batch_isend_irecv(p2p):
+                req.wait()
+        else:
+            for req in [op.op(op.tensor, op.peer) for op in p2p]:
+                req.wait()
         if sel:
             s = ops.ssim_batch(tmp, [2 * k for k in sel], [2 * k + 1 for k in sel])
             scores_dev[torch.from_numpy(cross[sel]).to(dev)] = s
