@@ -153,8 +153,9 @@ int ke_plane_sad_pairs(ke_ctx* ctx, const uint8_t* d_planes, int64_t plane_bytes
 /* ---------------------------------------------------------------------------------------
  * Cluster assembly (host).  Union-find over accepted pairs with the reference's "smaller root wins" rule
  * (ClusterBuilder.build, src/dup/cluster.py:22-70; DisjointSet of dup.scanner, src/dup/scanner.py:176-200):
- * h_nodes[0..*n_nodes) receives the distinct ids that occur in the pairs, ascending, and h_node_rep[i] the
- * representative (= smallest id) of the component of h_nodes[i]; both buffers hold 2*n_pairs entries.
+ * h_nodes[0..*n_nodes) receives the distinct ids that occur in the pairs GROUPED BY COMPONENT (components by ascending
+ * representative, members ascending inside each) and h_node_rep[i] the representative (= smallest id) of the component
+ * of h_nodes[i]; both buffers hold 2*n_pairs entries.
  * Ids are arbitrary int64 values (file ids or table indices). */
 int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int64_t n_pairs, int64_t* h_nodes,
                           int64_t* h_node_rep, int64_t* n_nodes);

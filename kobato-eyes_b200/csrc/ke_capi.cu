@@ -189,7 +189,7 @@ extern "C" int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int
         hi = std::max(hi, std::max(h_a[k], h_b[k]));
     }
     // slot of an id: direct index when the id range is compact (table indices), else rank among the sorted ids
-    const bool direct = (hi - lo) >= 0 && (hi - lo) < 64 * n_pairs + 4096;
+    const bool direct = (hi - lo) >= 0 && (hi - lo) < 8 * n_pairs + 4096;  // else O(range) passes would dominate
     std::vector<int64_t> ids;
     std::vector<int32_t> parent;
     if (direct) {
@@ -228,13 +228,21 @@ extern "C" int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int
             else parent[(size_t)rx] = ry;
         }
     }
+    // output grouped by component: components by ascending representative, members ascending inside each
+    std::vector<int32_t> place(parent.size() + 1, 0);
     int64_t n = 0;
     for (size_t sidx = 0; sidx < parent.size(); ++sidx) {
         if (parent[sidx] < 0) continue;
-        const int32_t r = find((int32_t)sidx);
-        h_nodes[n] = direct ? lo + (int64_t)sidx : ids[sidx];
-        h_node_rep[n] = direct ? lo + (int64_t)r : ids[(size_t)r];
+        ++place[(size_t)find((int32_t)sidx) + 1];  // size of the component, counted at its root
         ++n;
+    }
+    for (size_t i = 1; i < place.size(); ++i) place[i] += place[i - 1];  // first output position of root i-1 at place[i-1]
+    for (size_t sidx = 0; sidx < parent.size(); ++sidx) {
+        if (parent[sidx] < 0) continue;
+        const int32_t r = parent[sidx];  // fully compressed by the find above
+        const int64_t at = place[(size_t)r]++;
+        h_nodes[at] = direct ? lo + (int64_t)sidx : ids[sidx];
+        h_node_rep[at] = direct ? lo + (int64_t)r : ids[(size_t)r];
     }
     *n_nodes = n;
     return KE_OK;

@@ -389,26 +389,32 @@ def plane_sad_pairs(planes, ia, ib):
     return out
 
 
-def cluster_pairs(a, b):
-    """Connected components of the pairs (a[k], b[k]): returns ``[(representative, [members])]`` sorted by
-    representative, members ascending, representative = smallest id ("smaller root wins", reference
-    src/dup/cluster.py:22-70).  Host union-find inside the library (no Python loop, no SciPy)."""
+def cluster_pairs_csr(a, b):
+    """Connected components of the pairs (a[k], b[k]) in CSR form: ``(members, offsets)`` with component c =
+    ``members[offsets[c]:offsets[c+1]]``, components by ascending representative (= smallest id, "smaller root wins",
+    reference src/dup/cluster.py:22-70), members ascending.  Host union-find inside the library."""
     a = np.ascontiguousarray(a, np.int64)
     b = np.ascontiguousarray(b, np.int64)
     if a.shape != b.shape or a.ndim != 1:
         raise ValueError("a and b must be 1-D and of equal length")
     if a.size == 0:
-        return []
+        return np.empty(0, np.int64), np.zeros(1, np.int64)
     nodes = np.empty(2 * a.size, np.int64)
     reps = np.empty(2 * a.size, np.int64)
     count = C.c_int64(0)
     nat.check(nat.load().ke_cluster_pairs_host(_np_ptr(a), _np_ptr(b), a.size, _np_ptr(nodes), _np_ptr(reps), C.byref(count)),
               "ke_cluster_pairs_host")
     nodes, reps = nodes[: count.value], reps[: count.value]
-    order = np.lexsort((nodes, reps))
-    members = nodes[order].tolist()
-    cuts = (np.flatnonzero(np.diff(reps[order])) + 1).tolist()
-    return [(members[s], members[s:e]) for s, e in zip([0] + cuts, cuts + [len(members)])]
+    cuts = np.flatnonzero(np.diff(reps)) + 1
+    offsets = np.concatenate([[0], cuts, [nodes.size]]).astype(np.int64)
+    return nodes, offsets
+
+
+def cluster_pairs(a, b):
+    """``cluster_pairs_csr`` as ``[(representative, [members])]`` sorted by representative."""
+    members, offsets = cluster_pairs_csr(a, b)
+    flat, offs = members.tolist(), offsets.tolist()
+    return [(flat[s], flat[s:e]) for s, e in zip(offs[:-1], offs[1:])]
 
 
 def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n_set: int = 1 << 30,

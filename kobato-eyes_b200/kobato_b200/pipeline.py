@@ -44,10 +44,34 @@ def _torch():
     return torch
 
 
-def _components(i, j, keep):
-    """Connected components of the accepted pairs -> sorted [(representative, [members])]
-    (the reference's ClusterBuilder semantics, src/dup/cluster.py:22-70)."""
-    return ops.cluster_pairs(i[keep], j[keep])
+class ClusterSet:
+    """Components of the accepted pairs in CSR form (arrays, no per-cluster Python objects until asked for):
+    ``len()``, indexing and iteration yield ``(representative, [members])`` sorted by representative — the reference's
+    ClusterBuilder semantics (src/dup/cluster.py:22-70)."""
+
+    def __init__(self, members: np.ndarray, offsets: np.ndarray):
+        self.members, self.offsets = members, offsets
+
+    def __len__(self) -> int:
+        return len(self.offsets) - 1
+
+    def __getitem__(self, c: int):
+        if c < 0:
+            c += len(self)
+        if not 0 <= c < len(self):
+            raise IndexError(c)
+        m = self.members[self.offsets[c]:self.offsets[c + 1]]
+        return int(m[0]), m.tolist()
+
+    def __iter__(self):
+        return (self[c] for c in range(len(self)))
+
+    def as_list(self):
+        return list(self)
+
+
+def _components(i, j, keep) -> ClusterSet:
+    return ClusterSet(*ops.cluster_pairs_csr(i[keep], j[keep]))
 
 
 class Timer:

@@ -193,5 +193,5 @@ def test_pipeline_scan_matches_oracle_end_to_end():
     assert np.all(np.abs(a.ssim - want) <= 1e-5)
     safe = np.abs(want - 0.9) > 1e-5
     assert np.array_equal(a.accepted[safe], (want >= 0.9)[safe])
-    assert a.clusters == ref_py.cluster_matches(zip(wi.tolist(), wj.tolist(), a.accepted.tolist()))
+    assert a.clusters.as_list() == ref_py.cluster_matches(zip(wi.tolist(), wj.tolist(), a.accepted.tolist()))
     assert b.bytes_h2d == host.nbytes and b.bytes_d2h > 16 * n
