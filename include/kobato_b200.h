@@ -135,7 +135,8 @@ int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int6
  * ke_gray_resize_batch: `convert("L").resize((out_w, out_h), filter)` for a batch of decoded images
  * (filter 1 = LANCZOS, 2 = BILINEAR; Pillow's 8bpc fixed-point arithmetic, byte-identical) —
  * replaces the resize in tile_ahash_bits (:66-69) and _load_small_gray (:203-207).
- * d_mid is caller scratch of n*h*out_w bytes, d_out receives n*out_h*out_w bytes.
+ * d_mid is caller scratch of n*h*out_w bytes (untouched when the streaming kernel serves the shape), d_out receives
+ * n*out_h*out_w bytes.
  * ke_tile_ahash_bits: planes n x (grid*tile)^2 -> bit strings of ceil((grid*tile)^2/32) uint32 words per
  * image, bit order (gy, gx, ty, tx), little endian (:71-83), bit = pixel > mean of its tile.
  * ke_bits_hamming_pairs: popcount(bits[ia] ^ bits[ib]) per pair (tile_hamming :86-88).

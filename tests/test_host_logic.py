@@ -343,3 +343,20 @@ def test_cluster_pairs_host_union_find_matches_the_oracle():
     assert ops.cluster_pairs([5], [5]) == [(5, [5])]
     with pytest.raises(ValueError):
         ops.cluster_pairs([1, 2], [3])
+
+
+def test_cluster_set_is_the_csr_view_of_the_same_components():
+    from kobato_b200 import ops, pipeline
+
+    rng = np.random.default_rng(4)
+    a, b = rng.integers(0, 500, 300), rng.integers(0, 500, 300)
+    keep = rng.random(300) < 0.7
+    cs = pipeline._components(a.astype(np.int64), b.astype(np.int64), keep)
+    want = ref_py.cluster_matches((int(x), int(y), bool(k)) for x, y, k in zip(a, b, keep))
+    assert len(cs) == len(want) and cs.as_list() == want and cs[0] == want[0] and cs[-1] == want[-1]
+    members, offsets = ops.cluster_pairs_csr(a[keep], b[keep])
+    assert offsets[0] == 0 and offsets[-1] == len(members) and np.all(np.diff(offsets) >= 2)
+    with pytest.raises(IndexError):
+        cs[len(want)]
+    empty = pipeline._components(a.astype(np.int64), b.astype(np.int64), np.zeros(300, bool))
+    assert len(empty) == 0 and empty.as_list() == []
