@@ -12,10 +12,15 @@ Two layers:
   libraries restated in plain C so that intermediate planes can be compared byte-for-byte
   and large cases finish in seconds.
 
-Parity status: pHash/dHash/Hamming/scanner are pinned against the live reference (run in the
-build container, vectors in ``tests/golden/``).  SSIM is **parity unpinned**: scikit-image is
-not installable here, so the SSIM restatement is pinned only by the reference's behavioural
-tests (``tests/dup/test_refine.py:24-46``).
+* ``oracle/skimage_shim`` — a stand-in ``skimage.metrics`` (one function, forwarding to ``oracle.ref_py``) that lets
+  the LIVE reference's ``dup.refine`` / ``dup.cluster`` import unmodified in the build container, so that the
+  reference's own tests for that half of the path and a field-by-field comparison with the drop-ins can run.
+
+Parity status: pHash/dHash/Hamming/scanner and the N1 refinement (tile aHash, small gray, MAE) are pinned against the
+live reference (run in the build container, vectors in ``tests/golden/``).  SSIM is **parity unpinned against
+scikit-image itself**: it is not installable here, so the restatement of its algorithm is pinned by the reference's
+behavioural tests (``tests/dup/test_refine.py`` and ``tests/dup/test_cluster.py`` run through the shim) and by the
+equality of ``refine_pair`` / ``ClusterBuilder`` with the live reference, not by scikit-image's own output.
 """
 from __future__ import annotations
 

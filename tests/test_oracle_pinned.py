@@ -8,7 +8,9 @@ from pathlib import Path
 
 import numpy as np
 import pytest
-from conftest import normalise_clusters
+import sys
+
+from conftest import REFERENCE_SRC, ROOT, normalise_clusters
 
 import oracle
 from kobato_b200 import synth
@@ -226,3 +228,87 @@ def test_ssim_exact_vs_float32_noise_over_varied_pairs():
 def test_cluster_matches_restatement():
     ms = [(1, 2, True), (2, 3, True), (4, 5, True), (3, 5, False)]
     assert ref_py.cluster_matches(ms) == [(1, [1, 2, 3]), (4, [4, 5])]
+
+
+# ------------------------------------------------------------------ the live reference's dup.refine / dup.cluster
+# (importable only through oracle/skimage_shim: scikit-image is absent from this image)
+
+
+@pytest.mark.reference
+def test_reference_refine_and_cluster_tests_run_through_the_skimage_shim():
+    """The reference's OWN tests for the SSIM / clustering half of the path (tests/dup/test_refine.py,
+    tests/dup/test_cluster.py) pass with ``skimage.metrics.structural_similarity`` answered by the oracle restatement."""
+    import os
+    import subprocess
+
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([str(ROOT / "oracle" / "skimage_shim"), str(ROOT), str(REFERENCE_SRC)])
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider",
+                          str(REFERENCE_SRC.parent / "tests" / "dup" / "test_refine.py"),
+                          str(REFERENCE_SRC.parent / "tests" / "dup" / "test_cluster.py")],
+                         capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout and "failed" not in res.stdout
+
+
+@pytest.mark.reference
+def test_dropin_refine_and_cluster_equal_the_live_reference(tmp_path, monkeypatch):
+    """Same files through the live ``dup.refine.refine_pair`` / ``dup.cluster.ClusterBuilder`` and through the drop-ins
+    (SSIM arithmetic of the drop-in stubbed by the oracle here; the CUDA kernel is compared with it in the GPU tests):
+    identical RefinedMatch fields, reasons and clusters."""
+    from PIL import Image, ImageEnhance
+
+    from kobato_b200.dup import cluster as kcluster
+    from kobato_b200.dup import refine as krefine
+
+    shim = str(ROOT / "oracle" / "skimage_shim")
+    for p in (shim, str(REFERENCE_SRC)):
+        if p not in sys.path:
+            sys.path.append(p)
+    import importlib
+
+    ref_refine = importlib.import_module("dup.refine")
+    ref_cluster = importlib.import_module("dup.cluster")
+    monkeypatch.setattr(krefine, "_compute_ssim", lambda a, b: ref_py.compute_ssim(a, b))
+
+    rng = np.random.default_rng(9)
+    paths = []
+    base = (rng.random((72, 96, 3)) * 255).astype(np.uint8)
+    for k in range(8):
+        arr = base.copy() if k % 2 == 0 else (rng.random((72, 96, 3)) * 255).astype(np.uint8)
+        img = Image.fromarray(arr)
+        if k in (2, 4):
+            img = ImageEnhance.Brightness(img).enhance(1.0 + 0.01 * k)
+        if k == 6:
+            img = img.resize((80, 60))
+        p = tmp_path / f"f{k}.png"
+        img.save(p)
+        paths.append(p)
+    broken = tmp_path / "broken.png"
+    broken.write_bytes(b"nope")
+    tiny = tmp_path / "tiny.png"
+    Image.new("RGB", (5, 5), (9, 9, 9)).save(tiny)
+    cases = [(0, 2), (0, 4), (0, 1), (1, 3), (2, 4), (0, 6), (3, 5)]
+    got_all, want_all = [], []
+    for thr in (ref_refine.RefinementThresholds(), ref_refine.RefinementThresholds(ssim=0.5, orb=0.9)):
+        kthr = krefine.RefinementThresholds(ssim=thr.ssim, orb=thr.orb)
+        for a, b in cases:
+            want = ref_refine.refine_pair(a, b, paths[a], paths[b], thresholds=thr)
+            got = krefine.refine_pair(a, b, paths[a], paths[b], thresholds=kthr)
+            assert (got.file_id_a, got.file_id_b, got.is_duplicate, got.reason) == \
+                (want.file_id_a, want.file_id_b, want.is_duplicate, want.reason), (a, b)
+            assert (got.ssim is None) == (want.ssim is None) and (got.orb_ratio is None) == (want.orb_ratio is None)
+            if want.ssim is not None:
+                assert abs(got.ssim - want.ssim) <= 1e-9
+            if want.orb_ratio is not None:
+                assert got.orb_ratio == want.orb_ratio
+            got_all.append(got)
+            want_all.append(want)
+    assert ref_refine.refine_pair(1, 2, paths[0], broken) is None and krefine.refine_pair(1, 2, paths[0], broken) is None
+    w, g = ref_refine.refine_pair(1, 2, tiny, tiny), krefine.refine_pair(1, 2, tiny, tiny)
+    assert (g.ssim, g.is_duplicate, g.reason) == (w.ssim, w.is_duplicate, w.reason)  # side < 7: "ssim unavailable, ..."
+    want_c = ref_cluster.ClusterBuilder().build(want_all)
+    got_c = kcluster.ClusterBuilder().build(got_all)
+    assert [(c.representative, c.members) for c in got_c] == [(c.representative, c.members) for c in want_c]
+    assert [(c.representative, c.members) for c in want_c] == \
+        ref_py.cluster_matches((m.file_id_a, m.file_id_b, m.is_duplicate) for m in want_all)
