@@ -1291,39 +1291,12 @@ int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, c
 }
 
 
-// ------------------------------------------------------------------ lanes = outputs kernel (v3)
+// ------------------------------------------------------------------ lanes = outputs tap pass (used by v4)
 //
 // Horizontal taps with the tap words in REGISTERS: lane = (output, segment of <= 8 sixteen-pixel
 // groups), warps walk rows.  Per row and pass of P <= 4 groups a lane issues P LDS.128 of pixels
 // (consecutive lanes read consecutive 16-byte groups: conflict free) and 12*P dp4a; no tap word
-// ever crosses shared memory, which was the limiter of the lanes=rows layout.  Everything else
-// (TMA ring, luma, clip, streamed vertical taps, DCT, bits) is shared with the fast kernel.
-
-struct V3Layout {
-    int raw, luma, acc, hrow, x32, x98, tmat, ymat, bar, total;
-};
-
-__host__ __device__ inline V3Layout v3_layout(int sub_bytes, int pitch_bytes, int n_slots) {
-    V3Layout L;
-    int off = 0;
-    auto take = [&](int bytes, int align) {
-        off = (off + align - 1) / align * align;
-        int at = off;
-        off += bytes;
-        return at;
-    };
-    L.raw = take(n_slots * sub_bytes, 128);
-    L.luma = take(32 * pitch_bytes + 8 * 16 + 64, 128);  // + slack: padded groups may run past the last row
-    L.acc = take(32 * kOuts * 4, 16);
-    L.hrow = take(32 * kOuts, 16);
-    L.x32 = take(1024, 16);
-    L.x98 = take(80, 16);
-    L.tmat = take(8 * 32 * 8, 16);
-    L.ymat = take(64 * 8, 16);
-    L.bar = take(2 * kMaxSlots * 8, 8);
-    L.total = off;
-    return L;
-}
+// ever crosses shared memory, which was the limiter of the lanes=rows layout.
 
 template <int P>
 __device__ __forceinline__ void v3_pass(const PhashArgs& a, int task, int g, int2 lm, int lane, const uint8_t* s_luma,
@@ -1361,159 +1334,11 @@ __device__ __forceinline__ void v3_pass(const PhashArgs& a, int task, int g, int
     }
 }
 
-template <int C, int NW>
-__global__ void __launch_bounds__(NW * 32 + 32, NW == 4 ? 4 : 2) ke_phash_v3_kernel(const PhashArgs a, const int sub_rows,
-                                                                     const int slot_shift, const int pitch_bytes,
-                                                                     const int dbg) {
-    constexpr int CR = 32;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int row_bytes = a.w * C;
-    const int sub_bytes = sub_rows * row_bytes;
-    const int n_slots = 1 << slot_shift;
-    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
-    const V3Layout L = v3_layout(sub_bytes, pitch_bytes, n_slots);
-    uint8_t* s_raw = smem + L.raw;
-    uint8_t* s_luma = smem + L.luma;
-    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
-    uint8_t* s_hrow = smem + L.hrow;
-    uint8_t* s_x32 = smem + L.x32;
-    uint8_t* s_x98 = smem + L.x98;
-    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
-    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);
-    uint64_t* s_empty = s_full + kMaxSlots;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_sub = (a.h + sub_rows - 1) / sub_rows;
-    const int subs_per_chunk = CR / sub_rows;
-    const int pitch_words = pitch_bytes >> 2;
-
-    if (tid == 0) {
-        for (int b = 0; b < n_slots; ++b) {
-            mbar_init(&s_full[b], 1);
-            mbar_init(&s_empty[b], NW);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < CR * kOuts; i += NW * 32 + 32) s_acc[i] = 1u << (kPrec - 1);
-    for (int i = tid; i < (8 * 16 + 64) / 4; i += NW * 32 + 32)
-        reinterpret_cast<uint32_t*>(s_luma + 32 * pitch_bytes)[i] = 0u;
-    __syncthreads();
-
-    if (warp == NW) {
-        if (lane == 0) {
-            uint32_t seq = 0;
-            for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-                const uint8_t* src = a.img + im * a.img_stride;
-                for (int s = 0; s < n_sub; ++s, ++seq) {
-                    const int b = seq & slot_mask;
-                    const int rows = min(sub_rows, a.h - s * sub_rows);
-                    mbar_wait_backoff(&s_empty[b], ((seq >> slot_shift) & 1u) ^ 1u);
-                    mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
-                    bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
-                             &s_full[b]);
-                }
-            }
-        }
-        return;
-    }
-
-    uint32_t seq = 0;
-    VertState<NW> vs;
-    vertical_init(a, vs, lane, warp);
-    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-        vertical_reset(vs, lane);
-
-        for (int r0 = 0; r0 < a.h; r0 += CR) {
-            const int rows = min(CR, a.h - r0);
-            for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
-                const int b = seq & slot_mask;
-                const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
-                mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
-                luma_rows_fast<C, NW>(s_raw + b * sub_bytes, reinterpret_cast<uint32_t*>(s_luma) + s * sub_rows * pitch_words,
-                                  srows, a.w, pitch_words, warp, lane);
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[b])) : "memory");
-            }
-            compute_sync<NW>();
-            if (dbg & 2) continue;  // tuning probe: loads + luma only
-
-            // ---- horizontal taps: item = (warp-task, 8-row group); tap words live in registers
-            for (int item = warp; item < ((dbg & 4) ? 0 : a.n_wtasks * 4); item += NW) {
-                const int task = item >> 2, rg = item & 3;
-                const int row_lo = rg * 8, row_hi = min(row_lo + 8, rows);
-                if (row_lo >= row_hi) continue;
-                const int2 lm = __ldg(a.lt_meta + task * 32 + lane);
-                const int ng = __ldg(a.lt_ng + task);
-                for (int g = 0; g < ng; g += 4) {
-                    switch (min(4, ng - g)) {
-                        case 4: v3_pass<4>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                        case 3: v3_pass<3>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                        case 2: v3_pass<2>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                        default: v3_pass<1>(a, task, g, lm, lane, s_luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                    }
-                }
-            }
-            compute_sync<NW>();
-            if (dbg & 8) continue;  // tuning probe: no clip / vertical taps
-
-            for (int i = tid; i < rows * kOuts; i += NW * 32) {
-                s_hrow[i] = clip8((int32_t)s_acc[i]);
-                s_acc[i] = 1u << (kPrec - 1);
-            }
-            compute_sync<NW>();
-            if (dbg & 16) continue;  // tuning probe: no vertical taps
-
-            vertical_chunk(a, vs, s_hrow, r0, rows, lane, warp);
-        }
-        if (dbg & 32) continue;  // tuning probe: no DCT / bits
-
-        vertical_finish(vs, s_x32, s_x98, lane, warp);
-        compute_sync<NW>();
-        dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
-    }
-}
-
-template <int C>
-bool v3_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V3Layout& L) {
-    const long long row_bytes = (long long)a.w * C;
-    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.n_wtasks < 1) return false;
-    pitch_bytes = a.w;  // rows 16-byte aligned; a warp reads one row at a time, so no padding is needed
-    for (int sub : {8, 4, 2, 1}) {
-        if (sub * row_bytes > (1 << 20)) continue;
-        L = v3_layout((int)(sub * row_bytes), pitch_bytes, 2);
-        if (L.total <= 100 * 1024) {
-            sub_rows = sub;
-            slot_shift = 1;
-            return true;
-        }
-    }
-    return false;
-}
-
-template <int C, int NW>
-int launch_v3(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, const V3Layout& L,
-              cudaStream_t s) {
-    constexpr int kBlock = NW * 32 + 32;
-    KE_CUDA(cudaFuncSetAttribute(ke_phash_v3_kernel<C, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int per_sm = 0;
-    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_v3_kernel<C, NW>, kBlock, L.total));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > a.n) grid = a.n;
-    const char* dbg_env = getenv("KE_PHASH_DBG");
-    ke_phash_v3_kernel<C, NW><<<(unsigned)grid, kBlock, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes,
-                                                                        dbg_env ? atoi(dbg_env) : 0);
-    ctx->launches++;
-    KE_CUDA(cudaGetLastError());
-    return KE_OK;
-}
-
 // ------------------------------------------------------------------ warp-specialised kernel (v4)
 //
-// The v3 kernel runs load+luma (HBM bound on its own: 5 TB/s) and the tap phases (dp4a bound)
-// one after the other; two CTAs per SM overlap them only by accident.  Here the roles are split
-// inside the CTA and decoupled through shared-memory rings:
+// The CUDA-core fallback of v5 (dp4a taps instead of tensor-pipe MMAs) for the widths v5 does not take.  Running
+// load+luma (HBM bound on its own) and the tap phases (dp4a bound) one after the other overlaps them only by
+// accident, so the roles are split inside the CTA and decoupled through shared-memory rings:
 //     warps 8..9   luma warps        raw rows -> raw ring (1-D TMA issued by warp 8 / lane 0, a few
 //                                    sub-chunks ahead) -> luma chunk ring (2 x 32 rows)
 //     warps 0..7   tap warps         luma ring -> horizontal taps (v3 layout) -> clip -> vertical -> DCT
@@ -2203,9 +2028,10 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
-    // "v4" (default: luma warps + tap warps decoupled through shared-memory rings) | "v3" (same tap layout,
-    // all warps walk the phases together) | "fast" (lanes = rows).  Measured on B200, 512x512x3: 2.19 / 2.05 /
-    // 2.0 M images/s.
+    // Kernel ladder, fastest first; each config function says whether its kernel takes the shape:
+    //   v5 (tensor-pipe resamples, 7.5 M img/s at 512x512x3) -> v4 (same rings, dp4a taps: 2.2 M) -> fast (lanes = rows,
+    //   widths that are not a multiple of 16: 2.0 M) -> generic (strided / unaligned / very wide rows).
+    // KE_PHASH_KERNEL=v4|fast starts the ladder lower (tests, comparisons).
     const char* which = getenv("KE_PHASH_KERNEL");
     if (!ctx->force_generic_phash && (!which || !strcmp(which, "v5"))) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0, nlb = 2;
@@ -2213,20 +2039,11 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
         if (v5_config<C>(a, sub_rows, slot_shift, pitch_bytes, nlb, VL))
             return launch_v5<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, nlb, VL, s);
     }
-    if (!ctx->force_generic_phash && !(which && (!strcmp(which, "v3") || !strcmp(which, "fast")))) {
+    if (!ctx->force_generic_phash && !(which && !strcmp(which, "fast"))) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
         V4Layout VL;
         if (v4_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
             return launch_v4<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
-    }
-    if (!ctx->force_generic_phash && !(which && !strcmp(which, "fast"))) {
-        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
-        V3Layout VL;
-        if (v3_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL)) {
-            const char* nw = getenv("KE_PHASH_NW");  // tuning override: compute warps per CTA (4 | 8)
-            if (nw && atoi(nw) == 4) return launch_v3<C, 4>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
-            return launch_v3<C, 8>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);  // measured: 8x2 CTAs > 4x4 CTAs
-        }
     }
     {
         int rpl = 0, sub_rows = 0, slot_shift = 1;
