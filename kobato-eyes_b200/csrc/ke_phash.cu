@@ -1555,8 +1555,9 @@ int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
 //                  private scratch -> read back as the B fragment of the vertical pass (A = vertical tap digits of
 //                  this chunk, accumulators for both 16-row halves of the 32x32 plane in registers all image long).
 //                  No barrier with any other warp before the image is finished.
-//     warps 4..7   "narrow target": output pairs of the 9-wide plane (B fragments in shared memory), their own
-//                  128-thread barrier per chunk, then warps 4 and 5 run the vertical pass of the 8x9 plane.
+//     warps 4..7   "narrow target": output pairs of the 9-wide plane (B fragments in shared memory), the same way end to
+//                  end: the pair's columns through a private scratch into the vertical pass of the 8x9 plane (an
+//                  8-column tile with 2-3 live columns: three cheap MMAs per chunk buy the absence of any barrier).
 //     warps 8..11  luma warps: wait for a 16-row raw slot, 16 pixels per lane through registers (2 dp2a per pixel),
 //                  the LAST reader of a slot (shared-memory counter) issues the next TMA copy into it.
 // Image end: all eight tap warps meet for the FP64 DCT and the bits.  setmaxnreg gives the three 4-warp groups
@@ -1917,12 +1918,17 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         return;
     }
 
-    // ---- narrow target: warps 4..7 own output pairs of the 9-wide target; after their own barrier warps 4 and 5 run
-    // the vertical pass of its two 8-column tiles (columns 32..39, 40..47 of the row plane, double buffered).
+    // ---- narrow target: warps 4..7 own output pairs of the 9-wide target (warp 7: outputs 6, 7 and 8), also END TO END:
+    // the pair's columns go into a private 8-column scratch (plane 1 of the row plane) and come straight back as the B
+    // fragment of the 8x9 plane's vertical pass — six of the tile's eight columns are padding, three MMAs per chunk
+    // are cheap, and no tap warp waits for another before the image is finished.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5NarrowRegs));
     const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
+    uint8_t* scr = s_hrow + kHCols * kHP;                 // plane 1
+    const int scr_col = 8 * (warp - 4);                   // this warp's private columns scr_col .. scr_col + 7
+    const uint32_t* col = reinterpret_cast<const uint32_t*>(scr + (scr_col + g) * kHP);
     int32_t vc[3][4];
-    uint32_t chunk = 0, lph = 0;
+    uint32_t lph = 0;
     int lb = 0;
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
 #pragma unroll
@@ -1930,32 +1936,32 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 #pragma unroll
             for (int i = 0; i < 4; ++i) vc[d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
         int ci = 0;
-        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
-            uint8_t* hrow = s_hrow + (chunk & 1) * (kHCols * kHP);
+        for (int r0 = 0; r0 < a.h; r0 += CR, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
             mbar_wait_sleep(&l_full[lb], lph, poll_ns);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
-            if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 2 * (warp - 4), lane);
-            else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, hrow, kOutW + 6, lane);
-            __syncwarp();
+            if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, scr, scr_col, lane);
+            else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, scr, scr_col, lane);
+            __syncwarp();  // the pair's columns are written
             if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
-            asm volatile("bar.sync 2, 128;" ::: "memory");  // the narrow columns of this chunk are complete
-            // the plane is double buffered: the next chunk writes the other half, this half is rewritten after the
-            // next chunk's barrier
-            if (warp < 6 && !(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
-                const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + ((4 + warp - 4) * 8 + g) * kHP);
+            if (!(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
                 const uint32_t b0 = col[t], b1 = col[4 + t];
                 const uint4* af = a.vmma + ((size_t)(ci * 3 + 2) * 3) * 32 + lane;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) mma_s8u8(vc[d], __ldg(af + d * 32), b0, b1);
             }
+            __syncwarp();  // every lane has read the columns before the next chunk overwrites them
         }
-        if (warp < 6) {  // 8x9 plane: rows g, columns (warp-4)*8 + 2t (+1) < 9
+        {   // 8x9 plane: rows g; tile columns 0, 1 (warp 7: 0, 1, 2) are outputs 2 (warp - 4) + 0, 1 (, 2)
             const int32_t v0 = vc[0][0] + (vc[1][0] << 8) + (vc[2][0] << 16);
             const int32_t v1 = vc[0][1] + (vc[1][1] << 8) + (vc[2][1] << 16);
             const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
-            const int x = (warp - 4) * 8 + 2 * t;
-            if (x < kDW) s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
-            if (x + 1 < kDW) s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
+            const int x = 2 * (warp - 4) + 2 * t;
+            if (t == 0) {
+                s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+                s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
+            } else if (t == 1 && warp == 7) {
+                s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+            }
         }
         compute_sync<NW>();
         dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
