@@ -190,8 +190,13 @@ extern "C" int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int
     }
     // slot of an id: direct index when the id range is compact (table indices), else rank among the sorted ids
     const bool direct = (hi - lo) >= 0 && (hi - lo) < 8 * n_pairs + 4096;  // else O(range) passes would dominate
-    std::vector<int64_t> ids;
-    std::vector<int32_t> parent;
+    std::vector<int64_t> ids, hkey;
+    std::vector<int32_t> parent, hval;
+    size_t hmask = 0;
+    auto hash_of = [](int64_t v) -> size_t {
+        uint64_t x = (uint64_t)v * 0x9E3779B97F4A7C15ull;
+        return (size_t)(x ^ (x >> 29));
+    };
     if (direct) {
         parent.assign((size_t)(hi - lo + 1), -1);
     } else {
@@ -202,6 +207,18 @@ extern "C" int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
         parent.resize(ids.size());
         for (size_t i = 0; i < parent.size(); ++i) parent[i] = (int32_t)i;
+        // id -> rank among the sorted ids through an open-addressing table (a binary search per lookup was the hot spot)
+        size_t cap = 16;
+        while (cap < 4 * ids.size()) cap <<= 1;
+        hkey.assign(cap, 0);
+        hval.assign(cap, -1);
+        hmask = cap - 1;
+        for (size_t i = 0; i < ids.size(); ++i) {
+            size_t at = hash_of(ids[i]) & hmask;
+            while (hval[at] >= 0) at = (at + 1) & hmask;
+            hkey[at] = ids[i];
+            hval[at] = (int32_t)i;
+        }
     }
     auto slot = [&](int64_t v) -> int32_t {
         if (direct) {
@@ -209,7 +226,9 @@ extern "C" int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int
             if (parent[(size_t)s] < 0) parent[(size_t)s] = s;  // first sight of this id
             return s;
         }
-        return (int32_t)(std::lower_bound(ids.begin(), ids.end(), v) - ids.begin());
+        size_t at = hash_of(v) & hmask;
+        while (hkey[at] != v || hval[at] < 0) at = (at + 1) & hmask;  // every id of the pairs is in the table
+        return hval[at];
     };
     auto find = [&](int32_t x) {
         int32_t r = x;
