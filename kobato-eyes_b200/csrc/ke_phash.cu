@@ -929,18 +929,28 @@ __device__ __forceinline__ void dct_and_bits(const PhashArgs& a, long long im, c
     if (a.plane98 && tid < kDW * kDH) a.plane98[im * 72 + tid] = s_x98[tid];
     for (int idx = tid; idx < 256; idx += NW * 32) {
         const int k = idx >> 5, x = idx & 31;
-        double s = 0.0;
-#pragma unroll 8
-        for (int nn = 0; nn < 32; ++nn) s = fma(c_dct[k * 32 + nn], (double)s_x32[nn * 32 + x], s);
-        s_t[k * 32 + x] = s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four independent chains: the DFMA latency, not its rate, bounds this
+#pragma unroll
+        for (int nn = 0; nn < 32; nn += 4) {
+            s0 = fma(c_dct[k * 32 + nn], (double)s_x32[nn * 32 + x], s0);
+            s1 = fma(c_dct[k * 32 + nn + 1], (double)s_x32[(nn + 1) * 32 + x], s1);
+            s2 = fma(c_dct[k * 32 + nn + 2], (double)s_x32[(nn + 2) * 32 + x], s2);
+            s3 = fma(c_dct[k * 32 + nn + 3], (double)s_x32[(nn + 3) * 32 + x], s3);
+        }
+        s_t[k * 32 + x] = (s0 + s1) + (s2 + s3);
     }
     compute_sync<NW>();
     if (tid < 64) {
         const int k = tid >> 3, l = tid & 7;
-        double s = 0.0;
-#pragma unroll 8
-        for (int nn = 0; nn < 32; ++nn) s = fma(s_t[k * 32 + nn], c_dct[l * 32 + nn], s);
-        s_y[tid] = s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int nn = 0; nn < 32; nn += 4) {
+            s0 = fma(s_t[k * 32 + nn], c_dct[l * 32 + nn], s0);
+            s1 = fma(s_t[k * 32 + nn + 1], c_dct[l * 32 + nn + 1], s1);
+            s2 = fma(s_t[k * 32 + nn + 2], c_dct[l * 32 + nn + 2], s2);
+            s3 = fma(s_t[k * 32 + nn + 3], c_dct[l * 32 + nn + 3], s3);
+        }
+        s_y[tid] = (s0 + s1) + (s2 + s3);
     }
     compute_sync<NW>();
     if (warp == 0) {
