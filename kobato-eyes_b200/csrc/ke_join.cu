@@ -448,12 +448,11 @@ extern "C" int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n,
     a.sliced = nullptr;
     const int rpt = pick_rpt(ctx, n, part_count);
     const int mode = ctx->join_mode;
-    // hybrid (POPC role + bit-sliced LOP3 role) as soon as every CTA of the fused kernel gets a 2048-hash tile or more:
-    // measured on B200 it is at least as fast as the POPC kernel from 70 k hashes on (1.21 vs 1.27 ms) and 28 % faster
-    // at 140 k
-    const long long bt = (n + kBTile - 1) / kBTile, btiles = bt * (bt + 1) / 2 / part_count;
-    const bool hybrid_auto = rpt == 8 || btiles >= 2ll * ctx->sm_count;
-    if (threshold <= 15 && mode != 1 && (mode >= 2 || hybrid_auto)) return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode);
+    // hybrid (POPC role + bit-sliced LOP3 role) only for large tables.  On uniformly random hashes it also wins from
+    // ~70 k hashes on (140 k: 3.6 vs 4.7 ms), but on the pHashes of real scans — many near pairs that the band predicate
+    // then rejects in the slow path — the same switch made the 70 k-image step's join 8x slower (9.8 vs 1.2 ms), so the
+    // threshold stays where the tile queue is long.
+    if (threshold <= 15 && mode != 1 && (mode >= 2 || rpt == 8)) return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode);
     switch (rpt) {
         case 8: return launch_join<8>(ctx, a, s);
         case 4: return launch_join<4>(ctx, a, s);
