@@ -70,9 +70,10 @@ __device__ __forceinline__ bool band_match(uint64_t x, const JoinArgs& a, uint64
 }
 
 __device__ __noinline__ void emit_hits(const JoinArgs& a, const uint64_t* rows, long long row0, const uint64_t* cols,
-                                       long long col0, int jbase, int rpt) {
-    // Re-evaluate rpt x kColBatch pairs of this thread with every filter.
+                                       long long col0, int jbase, int rpt, uint32_t rowmask) {
+    // Re-evaluate the kColBatch pairs of every flagged row of this thread with every filter.
     for (int k = 0; k < rpt; ++k) {
+        if (!((rowmask >> k) & 1u)) continue;
         const long long i = row0 + threadIdx.x + (long long)k * kThreads;
         if (i >= a.n) continue;
         for (int jj = 0; jj < kColBatch; ++jj) {
@@ -141,17 +142,30 @@ __device__ __forceinline__ void popc_role(const JoinArgs& a, uint64_t* cols, lon
         const int jend = (int)((col_valid + kColBatch - 1) / kColBatch) * kColBatch;
 #pragma unroll 1
         for (int j = 0; j < jend; j += kColBatch) {
-            int acc = 0;
+            // one sign accumulator per ROW (same LOP3 count as a single one: each 3-input OR folds two pairs), so that
+            // the slow path re-checks only the flagged rows' 4 pairs instead of all RPT x 4 — on tables with many near
+            // pairs (real pHashes) the slow path otherwise dominates
+            int acc[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) acc[k] = 0;
 #pragma unroll
             for (int jj = 0; jj < kColBatch; ++jj) {
                 const uint2 b = *reinterpret_cast<const uint2*>(&cols[j + jj]);
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) {
                     // sign bit of (popc_lo + popc_hi - (T+1)) is set iff the pair is within T
-                    acc |= __popc(al[k] ^ b.x) + __popc(ah[k] ^ b.y) + neg_t1;
+                    acc[k] |= __popc(al[k] ^ b.x) + __popc(ah[k] ^ b.y) + neg_t1;
                 }
             }
-            if (acc < 0) emit_hits(a, rows, row0, cols, col0, j, RPT);
+            int any = 0;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) any |= acc[k];
+            if (any < 0) {
+                uint32_t rowmask = 0u;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) rowmask |= ((uint32_t)acc[k] >> 31) << k;
+                emit_hits(a, rows, row0, cols, col0, j, RPT, rowmask);
+            }
         }
     }
 }
@@ -448,11 +462,13 @@ extern "C" int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n,
     a.sliced = nullptr;
     const int rpt = pick_rpt(ctx, n, part_count);
     const int mode = ctx->join_mode;
-    // hybrid (POPC role + bit-sliced LOP3 role) only for large tables.  On uniformly random hashes it also wins from
-    // ~70 k hashes on (140 k: 3.6 vs 4.7 ms), but on the pHashes of real scans — many near pairs that the band predicate
-    // then rejects in the slow path — the same switch made the 70 k-image step's join 8x slower (9.8 vs 1.2 ms), so the
-    // threshold stays where the tile queue is long.
-    if (threshold <= 15 && mode != 1 && (mode >= 2 || rpt == 8)) return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode);
+    // hybrid (POPC role + bit-sliced LOP3 role) as soon as every CTA of the fused kernel gets a 2048-hash tile or more:
+    // measured on B200 it is at least as fast as the POPC kernel from 70 k hashes on (1.14 vs 1.23 ms) and 28 % faster at
+    // 140 k.  (Before the slow path re-checked flagged ROWS only, the pHashes of a real scan — many near pairs that the band
+    // predicate rejects — made this switch 8x slower at 70 k; `tools/probe_join70k.py` is the regression probe.)
+    const long long bt = (n + kBTile - 1) / kBTile, btiles = bt * (bt + 1) / 2 / part_count;
+    const bool hybrid_auto = rpt == 8 || btiles >= 2ll * ctx->sm_count;
+    if (threshold <= 15 && mode != 1 && (mode >= 2 || hybrid_auto)) return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode);
     switch (rpt) {
         case 8: return launch_join<8>(ctx, a, s);
         case 4: return launch_join<4>(ctx, a, s);

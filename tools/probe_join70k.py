@@ -1,5 +1,5 @@
 """Time the 70k-hash join (the C2 step's K2) alone and right after a K1 launch."""
-import sys, time
+import os, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "kobato-eyes_b200"))
@@ -28,7 +28,9 @@ for rep in range(3):
     a0 = ev(); p, d = ops.phash_dhash_batch(bank); a = ev()
     r = ops.hamming_join_device(p, 8, require_band=True, capacity=140000); b = ev(); b.synchronize()
     print("k1 ms", a0.elapsed_time(a), "join of k1 hashes ms", a.elapsed_time(b), "hits", r[0].numel())
-from kobato_b200 import pipeline
+from kobato_b200 import pipeline, _native as nat
+mode = int(os.environ.get('KE_PROBE_JOIN_MODE', '0'))
+nat.context(0).set_option(nat.KE_OPT_JOIN_MODE, mode)
 for rep in range(4):
     t0 = time.perf_counter(); out = pipeline.scan(bank, threshold=8, ssim_threshold=0.9); t1 = time.perf_counter()
     print("scan wall ms", (t1 - t0) * 1e3, {k: round(v, 2) for k, v in out.stage_ms.items()})
