@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define KE_ABI_VERSION 1
+#define KE_ABI_VERSION 2
 
 typedef enum ke_status {
     KE_OK = 0,
@@ -38,17 +38,34 @@ typedef struct ke_ctx ke_ctx;
 int ke_abi_version(void);
 const char* ke_last_error(void);
 
-/* One context per (process, device).  Calls on one context must be serialised by the caller
- * (the reference drives this path from a single Qt worker thread: src/ui/dup_tab.py:118). */
+/* A context drives the devices it was created over (`ke_ctx_create(const int* devices, int n, ...)`).
+ * The reference runs this whole path from ONE Qt worker thread of ONE process (src/ui/dup_tab.py:118,
+ * src/core/jobs.py:299), so using several GPUs behind its seams means the library fans the work out itself:
+ *   - `d_` entry points act on the context they are handed: the first device of a multi-device context, or the
+ *     per-device child returned by ke_ctx_child(ctx, k);
+ *   - `_host` entry points split their units (images, triangle tiles, pairs) over ALL devices of the context with
+ *     one host thread per device; there is no device-to-device traffic on this path, hence no collective.
+ * Calls on one context must be serialised by the caller.  ke_ctx_create(device, ..) == ke_ctx_create_multi(&device, 1, ..). */
 int ke_ctx_create(int device, ke_ctx** out);
+int ke_ctx_create_multi(const int* devices, int n, ke_ctx** out);
 void ke_ctx_destroy(ke_ctx* ctx);
 int ke_ctx_device(const ke_ctx* ctx);
-/* Tuning / test knobs.  KE_OPT_PHASH_GENERIC=1 routes every image geometry through K1's generic
- * kernel (the one used for unaligned or very wide rows) instead of the fast one. */
+int ke_ctx_device_count(const ke_ctx* ctx);
+ke_ctx* ke_ctx_child(ke_ctx* ctx, int k); /* k in [0, device_count): child 0 is ctx itself; owned by ctx */
+/* Test knobs (the parity tests compare the kernel variants with each other through these).
+ * KE_OPT_PHASH_GENERIC=1 routes every image geometry through K1's generic kernel (the one that takes strided /
+ * unaligned / very wide rows) instead of the streaming tensor-pipe kernel. */
 #define KE_OPT_PHASH_GENERIC 1
 /* KE_OPT_JOIN_MODE: 0 auto (hybrid for large tables with threshold <= 15), 1 POPC kernel only,
- * 2 hybrid (POPC kernel + bit-sliced LOP3 kernel running concurrently), 3 bit-sliced kernel only. */
+ * 2 hybrid (POPC role + bit-sliced LOP3 role in one kernel), 3 bit-sliced kernel only. */
 #define KE_OPT_JOIN_MODE 2
+/* KE_OPT_PHASH_LADDER: K1 picks the fastest kernel that takes the geometry; 1 / 2 start that choice one / two steps
+ * lower (the parity tests run every kernel on every geometry it takes). */
+#define KE_OPT_PHASH_LADDER 5
+/* KE_OPT_SSIM_V1=1: K3 on the one-column-per-thread kernel (the one that takes unaligned banks). */
+#define KE_OPT_SSIM_V1 3
+/* KE_OPT_RESIZE_GENERIC=1: N1 gray resize on the generic two-pass kernels instead of the streaming one. */
+#define KE_OPT_RESIZE_GENERIC 4
 int ke_ctx_set_option(ke_ctx* ctx, int option, int value);
 int ke_ctx_sm_count(const ke_ctx* ctx);
 
@@ -77,9 +94,11 @@ int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int w, i
                    int64_t row_stride, uint64_t* d_phash, uint64_t* d_dhash, float* d_min_margin,
                    uint8_t* d_plane32, uint8_t* d_plane9x8, void* stream);
 
-/* Same, host buffers in and out (densely packed n*h*w*c): chunked H2D through pinned staging
- * overlapped with the kernel, results copied back.  This is the call behind the drop-in
- * core.fastsig.compute_signatures_mp (src/core/fastsig.py:65-99). */
+/* Same, host buffers in and out (densely packed n*h*w*c).  Images are split into contiguous ranges over the context's
+ * devices; per device, chunks of <= 256 MB go host -> device on two alternating streams with each chunk's kernel behind
+ * its copy.  Page-locked sources (cudaHostAlloc / cudaHostRegister, torch pinned tensors) are DMA'd in place; pageable
+ * ones pass through the context's pinned staging buffers (2 x 32 MB, filled by KE_STAGE_THREADS=4 host threads).
+ * This is the call behind the drop-in core.fastsig.compute_signatures_mp (src/core/fastsig.py:65-99). */
 int ke_phash_batch_host(ke_ctx* ctx, const uint8_t* h_img, int64_t n, int h, int w, int c, uint64_t* h_phash,
                         uint64_t* h_dhash, float* h_min_margin);
 
@@ -102,7 +121,9 @@ int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n, int thresh
                     void* stream);
 
 /* Host buffers in and out.  Returns KE_E_CAPACITY (and the required count in *out_count) when
- * more than `capacity` pairs qualify: nothing is silently truncated. */
+ * more than `capacity` pairs qualify: nothing is silently truncated.  On a multi-device context the caller's share of
+ * the tiles is dealt on over the devices (device k: t % (part_count * n_dev) == part_index + part_count * k; the table
+ * is uploaded to each, the lists are concatenated on the host), one more device per ~5e9 pairs. */
 int ke_hamming_join_host(ke_ctx* ctx, const uint64_t* h_hashes, int64_t n, int threshold, uint32_t flags,
                          int band_bits, int band_count, const uint64_t* h_band_allow, int part_index, int part_count,
                          uint32_t* h_out_i, uint32_t* h_out_j, uint8_t* h_out_dist, int64_t capacity,
@@ -118,15 +139,24 @@ int64_t ke_hamming_join_pairs(int64_t n, int part_index, int part_count);
  * integers, the per-pixel formula FP32, the mean FP64 (|delta| vs the reference's float32 path
  * < 1e-5).  Pair p compares images ia[p] and ib[p] of a bank of h x w x c uint8 images
  * (c = 1: 'L' planes as _compute_ssim prepares them; c = 3/4: RGB(A), converted with Pillow's
- * fixed-point luma on the fly).  h, w >= 7 or KE_E_UNSUPPORTED (the reference raises). */
+ * fixed-point luma on the fly).  h, w >= 7 or KE_E_UNSUPPORTED (the reference raises).
+ *
+ * gaussian = 0 is the reference's path.  gaussian = 1 is skimage's `gaussian_weights=True` variant (sigma 1.5, 11 taps,
+ * crop 5, cov_norm 121/120; h, w >= 11), which is how BASELINE.json words kernel 3 in its north_star; it mirrors
+ * scipy.ndimage.gaussian_filter on float32 images (FP64 accumulation per 1-D pass, float32 in between). */
 int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride, int64_t row_stride,
-                  const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs, double* d_ssim, void* stream);
+                  const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs, int gaussian, double* d_ssim, void* stream);
 
 /* Host buffers: pair p compares h_a + p*h*w*c with h_b + p*h*w*c (c = 1: 'L' planes), copied in
- * chunks overlapped with the kernel.  Behind the drop-in dup.refine._compute_ssim /
- * refine_pairs_batch. */
+ * chunks overlapped with the kernel (staged like ke_phash_batch_host), pairs split over the context's devices.
+ * Behind the drop-in dup.refine._compute_ssim / refine_pairs_batch. */
 int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w, int c,
-                       double* h_ssim);
+                       int gaussian, double* h_ssim);
+
+/* convert("L") (Pillow rgb2l) of the bank images d_idx[0..n) into packed h*w planes: what a multi-process scan ships
+ * between ranks for its cross-shard SSIM pairs instead of the RGB images (src/dup/refine.py:48-49). */
+int ke_luma_planes(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride, int64_t row_stride,
+                   const int64_t* d_idx, int64_t n, uint8_t* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * N1 — the refinement the shipped UI runs after a scan (SURVEY §8f "next" row): tile aHash and
@@ -160,13 +190,44 @@ int ke_plane_sad_pairs(ke_ctx* ctx, const uint8_t* d_planes, int64_t plane_bytes
  * Ids are arbitrary int64 values (file ids or table indices). */
 int ke_cluster_pairs_host(const int64_t* h_a, const int64_t* h_b, int64_t n_pairs, int64_t* h_nodes,
                           int64_t* h_node_rep, int64_t* n_nodes);
+/* The same on the device for pairs of table indices < n_nodes (lock-free union-find, larger root hooked under the
+ * smaller): d_label[v] = smallest index of v's component for every v that occurs in a pair, 0xFFFFFFFF otherwise. */
+int ke_cluster_pairs(ke_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int64_t n_pairs, int64_t n_nodes,
+                     uint32_t* d_label, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * N3 — table-level duplicate scan: DuplicateScanner.build_clusters (src/dup/scanner.py:211-356) on the
+ * COLUMNS of `iter_files_for_dup` (src/db/repository.py:416-455) instead of one DuplicateFile object per row:
+ * h_phash = the signed 64-bit `signatures.phash_u64` column (src/db/schema.py:65-72; same bits as the unsigned hash),
+ * h_file_id (nullable: rows are then distinct files), h_size (nullable: no size gate).  Steps, all on the device(s):
+ * band-bucket statistics and the KE_DUP_BUCKET_PAIR_CAP mask (:227-253; pair_cap <= 0: off), the all-pairs join with
+ * the band predicate over every device of the context (:262-290), the same-id and size-ratio gates (:271-279,
+ * :358-370; size_ratio <= 0: off), union-find + best_hamming (:304-318).
+ * Out: the members (rows with at least one edge) grouped by component — h_member_index (table row), h_member_label
+ * (= smallest row of the component), h_member_best (min edge distance), components by ascending label, rows ascending
+ * inside; and (edge_capacity > 0) the surviving edges sorted by (i, j).  KE_E_CAPACITY when a buffer is too small
+ * (stats->members / stats->edges then hold the required sizes).
+ * Requires distinct file ids (the reference de-duplicates edges by id pair, which only matters when they repeat);
+ * the cosine gate (:372-400) needs embeddings and stays with the caller. */
+typedef struct ke_scan_stats {
+    int64_t n_buckets, buckets_ge2, max_bucket; /* what the reference logs at :240-247 */
+    int64_t candidates;                          /* pairs within the threshold that share an allowed band */
+    int64_t after_same_id, edges;                /* after the same-id gate, after the size gate */
+    int64_t members, clusters;
+} ke_scan_stats;
+int ke_scan_table_host(ke_ctx* ctx, const int64_t* h_phash, const int64_t* h_file_id, const int64_t* h_size, int64_t n,
+                       int threshold, int band_bits, int band_count, double size_ratio, int64_t pair_cap,
+                       int64_t* h_member_index, int64_t* h_member_label, int32_t* h_member_best, int64_t member_capacity,
+                       uint32_t* h_edge_i, uint32_t* h_edge_j, uint8_t* h_edge_dist, int64_t edge_capacity,
+                       ke_scan_stats* stats);
 
 /* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py / tests only). */
 
-/* Synthetic image generator, the CUDA twin of kobato_b200.synth.synth_image (identical bytes). */
-int ke_synth_images(ke_ctx* ctx, uint8_t* d_out, int64_t start, int64_t count, int h, int w, int c, int64_t n_set,
-                    uint64_t seed, int planted_permille, void* stream);
+/* Synthetic image generator, the CUDA twin of kobato_b200.synth.synth_image (identical bytes): images
+ * start, start + item_stride, ... of a set of n_set. */
+int ke_synth_images(ke_ctx* ctx, uint8_t* d_out, int64_t start, int64_t item_stride, int64_t count, int h, int w, int c,
+                    int64_t n_set, uint64_t seed, int planted_permille, void* stream);
 
 /* POPC issue-rate microbenchmark: the integer roofline denominator of K2.
  * Returns POPC thread-instructions per SM clock per SM, and the SM clock it derived. */

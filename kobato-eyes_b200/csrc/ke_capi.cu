@@ -19,8 +19,11 @@ void ke_set_error(const char* fmt, ...) {
 extern "C" int ke_abi_version(void) { return KE_ABI_VERSION; }
 extern "C" const char* ke_last_error(void) { return g_err; }
 
-extern "C" int ke_ctx_create(int device, ke_ctx** out) {
-    KE_REQUIRE(out != nullptr, "ke_ctx_create: out is NULL");
+const char* ke_last_error_cstr() { return g_err; }
+
+namespace {
+
+int ctx_create_one(int device, ke_ctx** out) {
     *out = nullptr;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -41,16 +44,17 @@ extern "C" int ke_ctx_create(int device, ke_ctx** out) {
     ke_ctx* ctx = new (std::nothrow) ke_ctx();
     if (!ctx) return KE_E_NOMEM;
     ctx->device = device;
+    ctx->dev_ctx[0] = ctx;
     ctx->sm_count = prop.multiProcessorCount;
     for (auto& s : ctx->copy_stream) KE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     KE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) KE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : ctx->stage_ev) KE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     *out = ctx;
     return KE_OK;
 }
 
-extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
-    if (!ctx) return;
+void ctx_destroy_one(ke_ctx* ctx) {
     KeDeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     ke_tables_free(ctx->tables);
@@ -63,25 +67,79 @@ extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     for (auto ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->stage_ev)
+        if (ev) cudaEventDestroy(ev);
     delete ctx;
+}
+
+}  // namespace
+
+extern "C" int ke_ctx_create_multi(const int* devices, int n, ke_ctx** out) {
+    KE_REQUIRE(out != nullptr, "ke_ctx_create_multi: out is NULL");
+    *out = nullptr;
+    KE_REQUIRE(devices != nullptr && n >= 1 && n <= KE_MAX_DEVICES, "ke_ctx_create_multi: need 1..%d devices (got %d)",
+               KE_MAX_DEVICES, n);
+    for (int a = 0; a < n; ++a)
+        for (int b = a + 1; b < n; ++b) KE_REQUIRE(devices[a] != devices[b], "ke_ctx_create_multi: device %d listed twice", devices[a]);
+    ke_ctx* root = nullptr;
+    int rc = ctx_create_one(devices[0], &root);
+    if (rc) return rc;
+    for (int k = 1; k < n; ++k) {
+        ke_ctx* child = nullptr;
+        if ((rc = ctx_create_one(devices[k], &child))) {
+            for (int q = 1; q < k; ++q) ctx_destroy_one(root->dev_ctx[q]);
+            ctx_destroy_one(root);
+            return rc;
+        }
+        root->dev_ctx[k] = child;
+    }
+    root->n_dev = n;
+    *out = root;
+    return KE_OK;
+}
+
+extern "C" int ke_ctx_create(int device, ke_ctx** out) { return ke_ctx_create_multi(&device, 1, out); }
+
+extern "C" void ke_ctx_destroy(ke_ctx* ctx) {
+    if (!ctx) return;
+    for (int k = 1; k < ctx->n_dev; ++k)
+        if (ctx->dev_ctx[k]) ctx_destroy_one(ctx->dev_ctx[k]);
+    ctx_destroy_one(ctx);
 }
 
 extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
     KE_REQUIRE(ctx != nullptr, "ke_ctx_set_option: ctx is NULL");
     switch (option) {
-        case KE_OPT_PHASH_GENERIC: ctx->force_generic_phash = value ? 1 : 0; return KE_OK;
-        case KE_OPT_JOIN_MODE:
-            KE_REQUIRE(value >= 0 && value <= 3, "ke_ctx_set_option: join mode must be 0..3");
-            ctx->join_mode = value;
-            return KE_OK;
+        case KE_OPT_PHASH_GENERIC:
+        case KE_OPT_PHASH_LADDER:
+        case KE_OPT_SSIM_V1:
+        case KE_OPT_RESIZE_GENERIC: break;
+        case KE_OPT_JOIN_MODE: KE_REQUIRE(value >= 0 && value <= 3, "ke_ctx_set_option: join mode must be 0..3"); break;
+        default: ke_set_error("ke_ctx_set_option: unknown option %d", option); return KE_E_INVALID;
     }
-    ke_set_error("ke_ctx_set_option: unknown option %d", option);
-    return KE_E_INVALID;
+    for (int k = 0; k < ctx->n_dev; ++k) {
+        ke_ctx* c = ctx->dev_ctx[k];
+        switch (option) {
+            case KE_OPT_PHASH_GENERIC: c->force_generic_phash = value ? 1 : 0; break;
+            case KE_OPT_PHASH_LADDER: c->phash_ladder = value; break;
+            case KE_OPT_SSIM_V1: c->force_ssim_v1 = value ? 1 : 0; break;
+            case KE_OPT_RESIZE_GENERIC: c->force_generic_resize = value ? 1 : 0; break;
+            default: c->join_mode = value;
+        }
+    }
+    return KE_OK;
 }
 
 extern "C" int ke_ctx_device(const ke_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" int ke_ctx_device_count(const ke_ctx* ctx) { return ctx ? ctx->n_dev : -1; }
+extern "C" ke_ctx* ke_ctx_child(ke_ctx* ctx, int k) { return (ctx && k >= 0 && k < ctx->n_dev) ? ctx->dev_ctx[k] : nullptr; }
 extern "C" int ke_ctx_sm_count(const ke_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
-extern "C" int64_t ke_ctx_launch_count(const ke_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int64_t ke_ctx_launch_count(const ke_ctx* ctx) {
+    if (!ctx) return -1;
+    int64_t total = 0;
+    for (int k = 0; k < ctx->n_dev; ++k) total += ctx->dev_ctx[k]->launches;
+    return total;
+}
 
 int ke_ctx_scratch(ke_ctx* ctx, int slot, size_t bytes, void** out) {
     if (ctx->d_scratch_bytes[slot] < bytes) {

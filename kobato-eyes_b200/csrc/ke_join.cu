@@ -69,29 +69,37 @@ __device__ __forceinline__ bool band_match(uint64_t x, const JoinArgs& a, uint64
     return false;
 }
 
-__device__ __noinline__ void emit_hits(const JoinArgs& a, const uint64_t* rows, long long row0, const uint64_t* cols,
-                                       long long col0, int jbase, int rpt, uint32_t rowmask) {
-    // Re-evaluate the kColBatch pairs of every flagged row of this thread with every filter.
-    for (int k = 0; k < rpt; ++k) {
-        if (!((rowmask >> k) & 1u)) continue;
-        const long long i = row0 + threadIdx.x + (long long)k * kThreads;
-        if (i >= a.n) continue;
-        for (int jj = 0; jj < kColBatch; ++jj) {
-            const long long j = col0 + jbase + jj;
-            if (j >= a.n || j <= i) continue;
-            const uint64_t x = rows[k] ^ cols[jbase + jj];
-            const int d = __popcll(x);
-            if (d > a.threshold) continue;
-            if (a.flags & KE_JOIN_REQUIRE_BAND) {
-                const uint64_t allow = a.band_allow ? (a.band_allow[i] & a.band_allow[j]) : ~0ull;
-                if (!band_match(x, a, allow)) continue;
-            }
-            const unsigned long long slot = atomicAdd(a.count, 1ull);
-            if ((long long)slot < a.capacity) {
-                a.out_i[slot] = (uint32_t)i;
-                a.out_j[slot] = (uint32_t)j;
-                a.out_d[slot] = (uint8_t)d;
-            }
+// Slow path of the POPC role, run by the WHOLE warp.  `flagged` = lanes whose 4-column batch holds a pair within the
+// threshold in one of their rows (`rowmask`).  For every flagged lane the warp re-evaluates that lane's RPT x 4 pairs in
+// one step — lane L takes (row L / 4, column L % 4) — with every filter (bounds, i < j, exact distance, band predicate,
+// allow mask) and appends (i, j, d) through one global atomic per hit.  A flagged lane used to walk its own pairs
+// serially while the other 31 waited; on tables of real pHashes (about one near pair per thousand, most of them
+// rejected by the band predicate) that serial walk was a third of the kernel's time.
+template <int RPT>
+__device__ __noinline__ void emit_hits_warp(const JoinArgs& a, long long row0, const uint64_t* cols, long long col0,
+                                            int jbase, uint32_t rowmask, uint32_t flagged) {
+    const int lane = threadIdx.x & 31;
+    const int k = lane >> 2, jj = lane & 3;
+    const uint64_t colv = cols[jbase + jj];
+    const long long j = col0 + jbase + jj;
+    for (uint32_t f = flagged; f; f &= f - 1u) {
+        const int src = __ffs(f) - 1;
+        const uint32_t rm = __shfl_sync(0xffffffffu, rowmask, src);
+        if (k >= RPT || !((rm >> k) & 1u)) continue;
+        const long long i = row0 + (threadIdx.x & ~31) + src + (long long)k * kThreads;
+        if (i >= a.n || j >= a.n || j <= i) continue;
+        const uint64_t x = __ldg(a.hashes + i) ^ colv;
+        const int d = __popcll(x);
+        if (d > a.threshold) continue;
+        if (a.flags & KE_JOIN_REQUIRE_BAND) {
+            const uint64_t allow = a.band_allow ? (a.band_allow[i] & a.band_allow[j]) : ~0ull;
+            if (!band_match(x, a, allow)) continue;
+        }
+        const unsigned long long slot = atomicAdd(a.count, 1ull);
+        if ((long long)slot < a.capacity) {
+            a.out_i[slot] = (uint32_t)i;
+            a.out_j[slot] = (uint32_t)j;
+            a.out_d[slot] = (uint8_t)d;
         }
     }
 }
@@ -128,13 +136,12 @@ __device__ __forceinline__ void popc_role(const JoinArgs& a, uint64_t* cols, lon
             cols[threadIdx.x + k * kThreads] = j < a.n ? __ldg(a.hashes + j) : ~0ull;  // pad: distance 64 from row pad 0
         }
         uint32_t al[RPT], ah[RPT];
-        uint64_t rows[RPT];
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const long long i = row0 + threadIdx.x + (long long)k * kThreads;
-            rows[k] = i < a.n ? __ldg(a.hashes + i) : 0ull;
-            al[k] = (uint32_t)rows[k];
-            ah[k] = (uint32_t)(rows[k] >> 32);
+            const uint64_t row = i < a.n ? __ldg(a.hashes + i) : 0ull;
+            al[k] = (uint32_t)row;
+            ah[k] = (uint32_t)(row >> 32);
         }
         role_sync<BAR, kThreads>();
 
@@ -160,11 +167,12 @@ __device__ __forceinline__ void popc_role(const JoinArgs& a, uint64_t* cols, lon
             int any = 0;
 #pragma unroll
             for (int k = 0; k < RPT; ++k) any |= acc[k];
-            if (any < 0) {
+            const uint32_t flagged = __ballot_sync(0xffffffffu, any < 0);  // the j loop is warp-uniform: all lanes are here
+            if (flagged) {
                 uint32_t rowmask = 0u;
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) rowmask |= ((uint32_t)acc[k] >> 31) << k;
-                emit_hits(a, rows, row0, cols, col0, j, RPT, rowmask);
+                emit_hits_warp<RPT>(a, row0, cols, col0, j, rowmask, flagged);
             }
         }
     }
@@ -372,10 +380,15 @@ int launch_hybrid(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream, int mode) {
     a.tiles_per_dim = (a.n + TILE - 1) / TILE;
     a.tile_total = a.tiles_per_dim * (a.tiles_per_dim + 1) / 2;
     const long long nblk = (a.n + 31) / 32;
+    // The bit-sliced table and the tile queue belong to THIS call: stream-ordered allocations, so that two joins in
+    // flight on one context (different streams / threads) never share them.
     void *d_sliced = nullptr, *d_queue = nullptr;
-    int rc;
-    if ((rc = ke_ctx_scratch(ctx, 8, (size_t)nblk * 256 + 256, &d_sliced))) return rc;
-    if ((rc = ke_ctx_scratch(ctx, 9, 64, &d_queue))) return rc;
+    KE_CUDA(cudaMallocAsync(&d_sliced, (size_t)nblk * 256 + 256, stream));
+    if (cudaMallocAsync(&d_queue, 64, stream) != cudaSuccess) {
+        cudaFreeAsync(d_sliced, stream);
+        ke_set_error("ke_hamming_join: cudaMallocAsync failed");
+        return KE_E_NOMEM;
+    }
     a.sliced = (const uint32_t*)d_sliced;
     a.queue = (unsigned long long*)d_queue;
     KE_CUDA(cudaMemsetAsync(d_queue, 0, 32, stream));
@@ -392,12 +405,16 @@ int launch_hybrid(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream, int mode) {
     }
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
-    if (getenv("KE_JOIN_DEBUG")) {  // tuning probe: how many tiles each kernel took
+#ifdef KE_TUNING_PROBES
+    if (getenv("KE_JOIN_DEBUG")) {  // tuning probe: how many tiles each role took
         unsigned long long q[4] = {0, 0, 0, 0};
         KE_CUDA(cudaStreamSynchronize(stream));
         KE_CUDA(cudaMemcpy(q, d_queue, 32, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[ke_join] tiles=%lld popc=%llu sliced=%llu\n", a.tile_total, q[1], q[2]);
     }
+#endif
+    KE_CUDA(cudaFreeAsync(d_sliced, stream));
+    KE_CUDA(cudaFreeAsync(d_queue, stream));
     return KE_OK;
 }
 
@@ -476,13 +493,12 @@ extern "C" int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n,
     }
 }
 
-extern "C" int ke_hamming_join_host(ke_ctx* ctx, const uint64_t* h_hashes, int64_t n, int threshold, uint32_t flags,
-                                    int band_bits, int band_count, const uint64_t* h_band_allow, int part_index,
-                                    int part_count, uint32_t* h_out_i, uint32_t* h_out_j, uint8_t* h_out_dist,
-                                    int64_t capacity, int64_t* out_count) {
-    KE_REQUIRE(ctx != nullptr && out_count != nullptr, "ke_hamming_join_host: NULL argument");
-    KE_REQUIRE(n >= 0 && capacity >= 0, "ke_hamming_join_host: negative size");
-    KE_REQUIRE(n == 0 || h_hashes != nullptr, "ke_hamming_join_host: h_hashes is NULL");
+// Single-device body of ke_hamming_join_host (ke_multi.cu fans it over the devices of a context): table up, join,
+// count back; the candidate lists stay in the context's scratch (*d_i, *d_j, *d_d) for the caller to copy out.
+int ke_hamming_join_host_one(ke_ctx* ctx, const uint64_t* h_hashes, int64_t n, int threshold, uint32_t flags, int band_bits,
+                             int band_count, const uint64_t* h_band_allow, int part_index, int part_count,
+                             uint32_t** d_i_out, uint32_t** d_j_out, uint8_t** d_d_out, int64_t capacity,
+                             int64_t* out_count) {
     *out_count = 0;
     KeDeviceGuard guard(ctx->device);
     cudaStream_t s = ctx->copy_stream[0];
@@ -493,10 +509,10 @@ extern "C" int ke_hamming_join_host(ke_ctx* ctx, const uint64_t* h_hashes, int64
     if ((rc = ke_ctx_scratch(ctx, 2, (size_t)capacity * 4 + 8, &d_j))) return rc;
     if ((rc = ke_ctx_scratch(ctx, 3, (size_t)capacity + 8, &d_d))) return rc;
     if ((rc = ke_ctx_scratch(ctx, 4, 64, &d_cnt))) return rc;
-    if (n) KE_CUDA(cudaMemcpyAsync(d_h, h_hashes, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (n && (rc = ke_h2d_staged(ctx, d_h, h_hashes, (size_t)n * 8, s))) return rc;
     if (h_band_allow && (flags & KE_JOIN_REQUIRE_BAND) && n) {
         if ((rc = ke_ctx_scratch(ctx, 5, (size_t)n * 8 + 8, &d_allow))) return rc;
-        KE_CUDA(cudaMemcpyAsync(d_allow, h_band_allow, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        if ((rc = ke_h2d_staged(ctx, d_allow, h_band_allow, (size_t)n * 8, s))) return rc;
     }
     rc = ke_hamming_join(ctx, (const uint64_t*)d_h, n, threshold, flags, band_bits, band_count,
                          (const uint64_t*)d_allow, part_index, part_count, (uint32_t*)d_i, (uint32_t*)d_j,
@@ -506,17 +522,9 @@ extern "C" int ke_hamming_join_host(ke_ctx* ctx, const uint64_t* h_hashes, int64
     KE_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
     KE_CUDA(cudaStreamSynchronize(s));
     *out_count = (int64_t)cnt;
-    const size_t take = (size_t)((int64_t)cnt < capacity ? (int64_t)cnt : capacity);
-    if (take) {
-        KE_CUDA(cudaMemcpyAsync(h_out_i, d_i, take * 4, cudaMemcpyDeviceToHost, s));
-        KE_CUDA(cudaMemcpyAsync(h_out_j, d_j, take * 4, cudaMemcpyDeviceToHost, s));
-        KE_CUDA(cudaMemcpyAsync(h_out_dist, d_d, take, cudaMemcpyDeviceToHost, s));
-        KE_CUDA(cudaStreamSynchronize(s));
-    }
-    if ((int64_t)cnt > capacity) {
-        ke_set_error("ke_hamming_join_host: %llu pairs qualify but capacity is %lld", cnt, (long long)capacity);
-        return KE_E_CAPACITY;
-    }
+    *d_i_out = (uint32_t*)d_i;
+    *d_j_out = (uint32_t*)d_j;
+    *d_d_out = (uint8_t*)d_d;
     return KE_OK;
 }
 

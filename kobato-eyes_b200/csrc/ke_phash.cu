@@ -1257,6 +1257,7 @@ bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, int& slot_shift, F
     if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || a.n_bal > kMaxItems) return false;
     struct Cand { int rpl, sub, shift; };
     const Cand cands[] = {{1, 8, 1}, {2, 8, 1}, {1, 4, 1}, {1, 2, 1}, {1, 1, 1}};
+#ifdef KE_TUNING_PROBES
     if (const char* env = getenv("KE_PHASH_CFG")) {  // tuning override: "rpl,sub_rows,slot_shift"
         Cand cd{0, 0, 0};
         if (sscanf(env, "%d,%d,%d", &cd.rpl, &cd.sub, &cd.shift) == 3 && (cd.rpl == 1 || cd.rpl == 2) && cd.sub >= 1 &&
@@ -1268,6 +1269,7 @@ bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, int& slot_shift, F
             }
         }
     }
+#endif
     for (int budget : {113 * 1024, 227 * 1024}) {
         for (const Cand& cd : cands) {
             const long long sub_bytes = cd.sub * row_bytes;
@@ -1292,9 +1294,7 @@ int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, c
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > a.n) grid = a.n;
-    const char* dbg_env = getenv("KE_PHASH_DBG");
-    ke_phash_fast_kernel<C, RPL><<<(unsigned)grid, kFastThreads, L.total, s>>>(a, sub_rows, slot_shift,
-                                                                                dbg_env ? atoi(dbg_env) : 0);
+    ke_phash_fast_kernel<C, RPL><<<(unsigned)grid, kFastThreads, L.total, s>>>(a, sub_rows, slot_shift, 0);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;
@@ -1986,7 +1986,9 @@ bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_by
         if (a.mma_nk[q] > kNKP) return false;  // wide-target B fragments must fit the register file
     pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
     int want_sub = 16, want_shift = 1, want_nlb = 2;
+#ifdef KE_TUNING_PROBES
     if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d,%d", &want_sub, &want_shift, &want_nlb);  // tuning override
+#endif
     if (want_nlb < 2 || want_nlb > kMaxLumaBufs) want_nlb = 2;
     for (int sub : {want_sub, 8, 4, 2, 1}) {
         if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
@@ -2015,11 +2017,12 @@ int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > a.n) grid = a.n;
-    const char* dbg_env = getenv("KE_PHASH_DBG");
-    const char* ns_env = getenv("KE_PHASH_SLEEP");  // tuning override: consumer poll interval in ns
-    const int ns = ns_env ? atoi(ns_env) : 200;
-    ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes, nlb,
-                                                                      ((dbg_env ? atoi(dbg_env) : 0) & 0xFF) | (ns << 8));
+    int dbg = 0, ns = 200;  // consumer poll interval in ns
+#ifdef KE_TUNING_PROBES
+    if (const char* dbg_env = getenv("KE_PHASH_DBG")) dbg = atoi(dbg_env) & 0xFF;  // bit 2: no horizontal MMA, 4: no vertical pass, ...
+    if (const char* ns_env = getenv("KE_PHASH_SLEEP")) ns = atoi(ns_env);
+#endif
+    ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes, nlb, dbg | (ns << 8));
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;
@@ -2047,15 +2050,14 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // Kernel ladder, fastest first; each config function says whether its kernel takes the shape:
     //   v5 (tensor-pipe resamples, 7.5 M img/s at 512x512x3) -> v4 (same rings, dp4a taps: 2.2 M) -> fast (lanes = rows,
     //   widths that are not a multiple of 16: 2.0 M) -> generic (strided / unaligned / very wide rows).
-    // KE_PHASH_KERNEL=v4|fast starts the ladder lower (tests, comparisons).
-    const char* which = getenv("KE_PHASH_KERNEL");
-    if (!ctx->force_generic_phash && (!which || !strcmp(which, "v5"))) {
+    const int ladder = ctx->phash_ladder;  // KE_OPT_PHASH_LADDER (tests): 0 = from the top, 1 = skip v5, 2 = skip v5 and v4
+    if (!ctx->force_generic_phash && ladder == 0) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0, nlb = 2;
         V5Layout VL;
         if (v5_config<C>(a, sub_rows, slot_shift, pitch_bytes, nlb, VL))
             return launch_v5<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, nlb, VL, s);
     }
-    if (!ctx->force_generic_phash && !(which && !strcmp(which, "fast"))) {
+    if (!ctx->force_generic_phash && ladder <= 1) {
         int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
         V4Layout VL;
         if (v4_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
@@ -2160,13 +2162,12 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     }
 }
 
-extern "C" int ke_phash_batch_host(ke_ctx* ctx, const uint8_t* h_img, int64_t n, int h, int w, int c,
-                                   uint64_t* h_phash, uint64_t* h_dhash, float* h_min_margin) {
-    KE_REQUIRE(ctx != nullptr, "ke_phash_batch_host: ctx is NULL");
-    KE_REQUIRE(n >= 0, "ke_phash_batch_host: n < 0");
+// Single-device body of ke_phash_batch_host (ke_multi.cu fans it over the devices of a context): chunks of <= 256 MB go
+// host -> device on two alternating streams (pinned sources by DMA in place, pageable ones through the context's pinned
+// staging buffers), each chunk's kernel follows its copy on the same stream, so copy k+1 overlaps kernel k.
+int ke_phash_batch_host_one(ke_ctx* ctx, const uint8_t* h_img, int64_t n, int h, int w, int c, uint64_t* h_phash,
+                            uint64_t* h_dhash, float* h_min_margin) {
     if (n == 0) return KE_OK;
-    KE_REQUIRE(h_img && h_phash && h_dhash, "ke_phash_batch_host: NULL buffer");
-    KE_REQUIRE(h > 0 && w > 0 && (c == 1 || c == 3 || c == 4), "ke_phash_batch_host: bad geometry %dx%dx%d", w, h, c);
     KeDeviceGuard guard(ctx->device);
     const int64_t img_bytes = (int64_t)h * w * c;
     const int64_t img_stride = (img_bytes + 15) / 16 * 16;  // keep every image 16-byte aligned on the device
@@ -2185,12 +2186,8 @@ extern "C" int ke_phash_batch_host(ke_ctx* ctx, const uint8_t* h_img, int64_t n,
         const int b = k & 1;
         const int64_t cnt = std::min<int64_t>(per_chunk, n - i0);
         cudaStream_t s = ctx->copy_stream[b];
-        if (img_stride == img_bytes) {
-            KE_CUDA(cudaMemcpyAsync(d_buf[b], h_img + i0 * img_bytes, (size_t)(cnt * img_bytes), cudaMemcpyHostToDevice, s));
-        } else {
-            KE_CUDA(cudaMemcpy2DAsync(d_buf[b], (size_t)img_stride, h_img + i0 * img_bytes, (size_t)img_bytes,
-                                      (size_t)img_bytes, (size_t)cnt, cudaMemcpyHostToDevice, s));
-        }
+        if ((rc = ke_h2d_staged_2d(ctx, d_buf[b], (size_t)img_stride, h_img + i0 * img_bytes, (size_t)img_bytes, (size_t)cnt, s)))
+            return rc;
         rc = ke_phash_batch(ctx, (const uint8_t*)d_buf[b], cnt, h, w, c, img_stride, (int64_t)w * c,
                             (uint64_t*)d_ph + i0, (uint64_t*)d_dh + i0, (float*)d_mm + i0, nullptr, nullptr, s);
         if (rc) return rc;

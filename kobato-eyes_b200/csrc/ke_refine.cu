@@ -291,7 +291,7 @@ extern "C" int ke_gray_resize_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n
     KeDeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (!getenv("KE_RESIZE_GENERIC")) {  // streaming tensor-pipe kernel for the shapes it takes (ke_resize_mma.cu)
+    if (!ctx->force_generic_resize) {  // streaming tensor-pipe kernel for the shapes it takes (ke_resize_mma.cu)
         int taken = 0;
         if ((rc = ke_gray_resize_mma(ctx, d_img, n, h, w, c, img_stride, row_stride, out_w, out_h, filter, d_out, s, &taken)))
             return rc;
@@ -358,6 +358,72 @@ extern "C" int ke_plane_sad_pairs(ke_ctx* ctx, const uint8_t* d_planes, int64_t 
     KeDeviceGuard guard(ctx->device);
     ke_plane_sad_kernel<<<grid_for(n_pairs * 32, 256, ctx), 256, 0, (cudaStream_t)stream>>>(
         d_planes, plane_bytes, (const long long*)d_ia, (const long long*)d_ib, n_pairs, (unsigned long long*)d_out);
+    KE_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return KE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// convert("L") of selected bank images into packed planes (Pillow rgb2l, src/dup/refine.py:48-49): what the
+// multi-GPU scan ships between ranks for its cross-shard SSIM pairs (a third of the RGB bytes).
+
+namespace {
+template <int C>
+__global__ void __launch_bounds__(256) ke_luma_planes_kernel(const uint8_t* __restrict__ bank, int h, int w, long long img_stride,
+                                                             long long row_stride, const long long* __restrict__ idx,
+                                                             long long n, uint8_t* __restrict__ out) {
+    const long long per = (long long)h * w, total = n * per;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long k = e / per, r = e - k * per;
+        const int y = (int)(r / w), x = (int)(r - (long long)y * w);
+        out[e] = (uint8_t)luma_at<C>(bank + idx[k] * img_stride + (long long)y * row_stride + (long long)x * C);
+    }
+}
+
+// RGB rows on 4-byte boundaries, w % 4 == 0: a thread turns 12 bytes (3 coalesced words) into one word of 4 luma bytes
+__global__ void __launch_bounds__(256) ke_luma_planes_rgb4_kernel(const uint8_t* __restrict__ bank, int h, int w,
+                                                                  long long img_stride, long long row_stride,
+                                                                  const long long* __restrict__ idx, long long n,
+                                                                  uint32_t* __restrict__ out) {
+    const int wq = w >> 2;
+    const long long per = (long long)h * wq, total = n * per;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long k = e / per, r = e - k * per;
+        const int y = (int)(r / wq), q = (int)(r - (long long)y * wq);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(bank + idx[k] * img_stride + (long long)y * row_stride) + 3 * q;
+        const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        auto lum = [](uint32_t r_, uint32_t g_, uint32_t b_) { return (r_ * 19595u + g_ * 38470u + b_ * 7471u + 0x8000u) >> 16; };
+        const uint32_t l0 = lum(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const uint32_t l1 = lum(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const uint32_t l2 = lum((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const uint32_t l3 = lum((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        out[e] = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+    }
+}
+}  // namespace
+
+extern "C" int ke_luma_planes(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride, int64_t row_stride,
+                              const int64_t* d_idx, int64_t n, uint8_t* d_out, void* stream) {
+    KE_REQUIRE(ctx && n >= 0 && h > 0 && w > 0, "ke_luma_planes: bad arguments");
+    KE_REQUIRE(c == 1 || c == 3 || c == 4, "ke_luma_planes: channels must be 1, 3 or 4 (got %d)", c);
+    if (n == 0) return KE_OK;
+    KE_REQUIRE(d_bank && d_idx && d_out, "ke_luma_planes: NULL buffer");
+    KeDeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c == 3 && (w & 3) == 0 && (row_stride & 3) == 0 && (img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(d_bank) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(d_out) & 3) == 0) {
+        ke_luma_planes_rgb4_kernel<<<grid_for(n * h * (w >> 2), 256, ctx), 256, 0, s>>>(d_bank, h, w, img_stride, row_stride,
+                                                                                    (const long long*)d_idx, n, (uint32_t*)d_out);
+        KE_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return KE_OK;
+    }
+    const unsigned grid = grid_for(n * h * w, 256, ctx);
+    switch (c) {
+        case 1: ke_luma_planes_kernel<1><<<grid, 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, (const long long*)d_idx, n, d_out); break;
+        case 3: ke_luma_planes_kernel<3><<<grid, 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, (const long long*)d_idx, n, d_out); break;
+        default: ke_luma_planes_kernel<4><<<grid, 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, (const long long*)d_idx, n, d_out);
+    }
     KE_CUDA(cudaGetLastError());
     ctx->launches++;
     return KE_OK;

@@ -20,9 +20,12 @@
 // exchange at all.
 //
 // Algorithmic HBM bytes per pair: 2*h*w*c read + 8 written.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <vector>
 
 #include "ke_common.cuh"
 
@@ -46,6 +49,7 @@ struct SsimArgs {
     int rgb_words; // RGB bank whose rows and images start on 4-byte boundaries: vectorised luma staging
     double inv_count;
     double* out;
+    double* partial;  // [n_pairs][n_cblocks] column-block sums when a plane spans several column blocks
 };
 
 __device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) ke_ssim_kernel(const SsimArgs a) {
 #pragma unroll
             for (int i = 0; i < kThreads / 32; ++i) t += s_red[i];
             if (a.n_cblocks == 1) a.out[pair] = t * a.inv_count;
-            else atomicAdd(&a.out[pair], t * a.inv_count);
+            else a.partial[unit] = t;  // summed in column-block order by ke_ssim_finish_kernel: bit-reproducible
         }
     }
 }
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(kT4, KE_SSIM4_CTAS) ke_ssim4_kernel(const Ssim
 #pragma unroll
             for (int i = 0; i < kT4 / 32; ++i) t += s_red[i];
             if (a.n_cblocks == 1) a.out[pair] = t * a.inv_count;
-            else atomicAdd(&a.out[pair], t * a.inv_count);
+            else a.partial[unit] = t;  // summed in column-block order by ke_ssim_finish_kernel: bit-reproducible
         }
     }
 }
@@ -706,7 +710,7 @@ __global__ void __launch_bounds__(kT4, KE_SSIM4S_CTAS) ke_ssim4s_kernel(const Ss
 #pragma unroll
             for (int i = 0; i < kT4 / 32; ++i) t += s_red[i];
             if (a.n_cblocks == 1) a.out[pair] = t * a.inv_count;
-            else atomicAdd(&a.out[pair], t * a.inv_count);
+            else a.partial[unit] = t;  // summed in column-block order by ke_ssim_finish_kernel: bit-reproducible
         }
     }
 }
@@ -748,24 +752,168 @@ int launch_ssim(ke_ctx* ctx, SsimArgs& a, cudaStream_t s) {
     return KE_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Gaussian-window variant (`gaussian != 0`): skimage's structural_similarity(..., gaussian_weights=True) — sigma 1.5,
+// truncate 3.5 -> 11 taps, win_size 11 (crop 5, cov_norm 121/120).  NOT the reference's path (src/dup/refine.py:52 uses
+// the uniform window); offered because BASELINE.json's north_star words kernel 3 as "a separable Gaussian window".
+// It mirrors scipy.ndimage.gaussian_filter on float32 images operation by operation: axis 0 then axis 1, every 1-D pass
+// accumulated in FP64 in NI_Correlate1D's symmetric order (centre tap, then (x[-j] + x[+j]) * w[j] from the outermost
+// pair inwards, no FMA contraction) and rounded to float32 in between; the point formula in float32, the mean in FP64.
+// So constant and identical images give exactly the values the float32 reference path gives.
+
+constexpr int kGaussWin = 11, kGaussR = 5;
+constexpr int kGTW = 32, kGTH = 16, kGThreads = 128;
+constexpr int kGIW = kGTW + 2 * kGaussR, kGIH = kGTH + 2 * kGaussR;  // 42 x 26 input pixels per tile
+
+__constant__ double c_gauss[kGaussR + 1];  // w[0] = outermost tap ... w[5] = centre
+
+struct GaussArgs {
+    const uint8_t* bank;
+    int h, w, c;
+    long long img_stride, row_stride;
+    const long long* ia;
+    const long long* ib;
+    long long n_pairs;
+    int tiles_x, tiles_y;
+    double* partial;  // [n_pairs][tiles_y * tiles_x]
+};
+
+__device__ __forceinline__ float gauss_line(const float* x, int stride) {  // 11 taps centred on x[0]
+    double t = __dmul_rn((double)x[0], c_gauss[kGaussR]);
+#pragma unroll
+    for (int j = kGaussR; j >= 1; --j)
+        t = __dadd_rn(t, __dmul_rn(__dadd_rn((double)x[-j * stride], (double)x[j * stride]), c_gauss[kGaussR - j]));
+    return (float)t;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kGThreads) ke_ssim_gauss_kernel(const GaussArgs a) {
+    __shared__ float s_in[2][kGIH][kGIW];        // u, v as float32 pixel / 255
+    __shared__ float s_mid[5][kGTH][kGIW + 1];   // axis-0 pass of u, v, uu, vv, uv (float32, like scipy's intermediate)
+    __shared__ double s_red[kGThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles = a.tiles_x * a.tiles_y;
+    const long long n_units = a.n_pairs * tiles;
+    const float cov_norm = (float)(121.0 / 120.0), C1 = (float)(0.01 * 0.01), C2 = (float)(0.03 * 0.03);
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long pair = unit / tiles;
+        const int tl = (int)(unit - pair * tiles), ty = tl / a.tiles_x, tx = tl - ty * a.tiles_x;
+        const int oy0 = kGaussR + ty * kGTH, ox0 = kGaussR + tx * kGTW;  // first output pixel of the tile (cropped map)
+        const int out_rows = min(kGTH, (a.h - kGaussR) - oy0), out_cols = min(kGTW, (a.w - kGaussR) - ox0);
+        const uint8_t* img[2] = {a.bank + a.ia[pair] * a.img_stride, a.bank + a.ib[pair] * a.img_stride};
+        __syncthreads();  // previous unit's readers are done
+        for (int idx = tid; idx < 2 * kGIH * kGIW; idx += kGThreads) {
+            const int im = idx / (kGIH * kGIW), rem = idx - im * (kGIH * kGIW), r = rem / kGIW, x = rem - r * kGIW;
+            const int gy = oy0 - kGaussR + r, gx = ox0 - kGaussR + x;
+            float v = 0.f;
+            if (gy < a.h && gx < a.w) v = __fdiv_rn((float)luma_of<C>(img[im] + (long long)gy * a.row_stride + (long long)gx * C), 255.0f);
+            s_in[im][r][x] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < kGTH * kGIW; idx += kGThreads) {  // axis 0 (rows) first, as scipy does
+            const int r = idx / kGIW, x = idx - r * kGIW;
+            float col[5][kGaussWin];
+#pragma unroll
+            for (int j = 0; j < kGaussWin; ++j) {
+                const float u = s_in[0][r + j][x], v = s_in[1][r + j][x];
+                col[0][j] = u, col[1][j] = v, col[2][j] = __fmul_rn(u, u), col[3][j] = __fmul_rn(v, v), col[4][j] = __fmul_rn(u, v);
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) s_mid[q][r][x] = gauss_line(&col[q][kGaussR], 1);
+        }
+        __syncthreads();
+        double total = 0.0;
+        for (int idx = tid; idx < kGTH * kGTW; idx += kGThreads) {
+            const int r = idx / kGTW, x = idx - r * kGTW;
+            if (r >= out_rows || x >= out_cols) continue;
+            const float ux = gauss_line(&s_mid[0][r][x + kGaussR], 1), uy = gauss_line(&s_mid[1][r][x + kGaussR], 1);
+            const float uxx = gauss_line(&s_mid[2][r][x + kGaussR], 1), uyy = gauss_line(&s_mid[3][r][x + kGaussR], 1);
+            const float uxy = gauss_line(&s_mid[4][r][x + kGaussR], 1);
+            const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
+            const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
+            const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
+            const float A1 = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, ux), uy), C1), A2 = __fadd_rn(__fmul_rn(2.0f, vxy), C2);
+            const float B1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), C1), B2 = __fadd_rn(__fadd_rn(vx, vy), C2);
+            total += (double)__fdiv_rn(__fmul_rn(A1, A2), __fmul_rn(B1, B2));
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+        if (lane == 0) s_red[warp] = total;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kGThreads / 32; ++i) t += s_red[i];
+            a.partial[unit] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ke_ssim_finish_kernel(const double* __restrict__ partial, long long n_pairs, int n_cblocks,
+                                                             double inv_count, double* __restrict__ out) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    double t = 0.0;
+    for (int cb = 0; cb < n_cblocks; ++cb) t += partial[p * n_cblocks + cb];
+    out[p] = t * inv_count;
+}
+
+int g_gauss_uploaded_device = -1;
+
+int launch_ssim_gauss(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride, int64_t row_stride,
+                      const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs, double* d_ssim, cudaStream_t s) {
+    if (g_gauss_uploaded_device != ctx->device) {
+        // scipy.ndimage._filters._gaussian_kernel1d(sigma=1.5, order=0, radius=5): exp(-0.5 / sigma^2 * x^2) / sum, in double
+        double phi[kGaussWin], sum = 0.0;
+        for (int x = -kGaussR; x <= kGaussR; ++x) sum += (phi[x + kGaussR] = std::exp(-0.5 / (1.5 * 1.5) * (double)(x * x)));
+        double wts[kGaussR + 1];
+        for (int j = 0; j <= kGaussR; ++j) wts[j] = phi[j] / sum;
+        KE_CUDA(cudaMemcpyToSymbol(c_gauss, wts, sizeof(wts)));
+        g_gauss_uploaded_device = ctx->device;
+    }
+    GaussArgs a;
+    a.bank = d_bank, a.h = h, a.w = w, a.c = c, a.img_stride = img_stride, a.row_stride = row_stride;
+    a.ia = (const long long*)d_ia, a.ib = (const long long*)d_ib, a.n_pairs = n_pairs;
+    a.tiles_x = (w - 2 * kGaussR + kGTW - 1) / kGTW, a.tiles_y = (h - 2 * kGaussR + kGTH - 1) / kGTH;
+    const int tiles = a.tiles_x * a.tiles_y;
+    KE_CUDA(cudaMallocAsync((void**)&a.partial, (size_t)n_pairs * tiles * sizeof(double), s));
+    const long long units = n_pairs * tiles;
+    const unsigned grid = (unsigned)std::min<long long>(units, (long long)ctx->sm_count * 8);
+    switch (c) {
+        case 1: ke_ssim_gauss_kernel<1><<<grid, kGThreads, 0, s>>>(a); break;
+        case 3: ke_ssim_gauss_kernel<3><<<grid, kGThreads, 0, s>>>(a); break;
+        default: ke_ssim_gauss_kernel<4><<<grid, kGThreads, 0, s>>>(a); break;
+    }
+    ke_ssim_finish_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(
+        a.partial, n_pairs, tiles, 1.0 / ((double)(h - 2 * kGaussR) * (double)(w - 2 * kGaussR)), d_ssim);
+    ctx->launches += 2;
+    cudaFreeAsync(a.partial, s);
+    KE_CUDA(cudaGetLastError());
+    return KE_OK;
+}
+
 }  // namespace
 
 extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int64_t img_stride,
-                             int64_t row_stride, const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs,
+                             int64_t row_stride, const int64_t* d_ia, const int64_t* d_ib, int64_t n_pairs, int gaussian,
                              double* d_ssim, void* stream) {
     KE_REQUIRE(ctx != nullptr, "ke_ssim_batch: ctx is NULL");
     KE_REQUIRE(n_pairs >= 0, "ke_ssim_batch: n_pairs < 0");
     if (n_pairs == 0) return KE_OK;
     KE_REQUIRE(d_bank && d_ia && d_ib && d_ssim, "ke_ssim_batch: NULL buffer");
     KE_REQUIRE(c == 1 || c == 3 || c == 4, "ke_ssim_batch: channels must be 1, 3 or 4 (got %d)", c);
-    if (h < kWin || w < kWin) {
-        ke_set_error("win_size exceeds image extent (%dx%d < 7)", w, h);
-        return KE_E_UNSUPPORTED;
+    {
+        const int win = gaussian ? kGaussWin : kWin;
+        if (h < win || w < win) {
+            ke_set_error("win_size exceeds image extent (%dx%d < %d)", w, h, win);
+            return KE_E_UNSUPPORTED;
+        }
     }
     KE_REQUIRE(row_stride >= (int64_t)w * c && img_stride >= (int64_t)(h - 1) * row_stride + (int64_t)w * c,
                "ke_ssim_batch: strides smaller than the image");
     KeDeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
+    if (gaussian) return launch_ssim_gauss(ctx, d_bank, h, w, c, img_stride, row_stride, d_ia, d_ib, n_pairs, d_ssim, s);
     SsimArgs a;
     a.bank = d_bank;
     a.h = h;
@@ -783,39 +931,48 @@ extern "C" int ke_ssim_batch(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, i
     a.pitch = a.use_bulk ? w : ((std::min(w, kBlockCols + 6) + 3) / 4 * 4 + 4);
     a.inv_count = 1.0 / ((double)(h - 6) * (double)(w - 6));
     a.out = d_ssim;
-    if (a.n_cblocks > 1) KE_CUDA(cudaMemsetAsync(d_ssim, 0, (size_t)n_pairs * sizeof(double), s));
+    a.partial = nullptr;
+    if (a.n_cblocks > 1)  // stream-ordered: belongs to this call, freed after the finish kernel
+        KE_CUDA(cudaMallocAsync((void**)&a.partial, (size_t)n_pairs * a.n_cblocks * sizeof(double), s));
     // v2 (four output columns per thread): strips by one bulk copy per image when the plane is a contiguous 'L' block,
     // else by cp.async pieces (needs 16-byte aligned rows); v1 (one column per thread, plain loads) takes the rest.
-    const char* which = getenv("KE_SSIM_KERNEL");  // tuning override: "v1" | "v2"
     const bool can_stage = (row_stride % 16) == 0 && (img_stride % 16) == 0 && ((int64_t)w * c) % 16 == 0 &&
                            (reinterpret_cast<uintptr_t>(d_bank) & 15) == 0;
-    const bool use_v1 = which ? !strcmp(which, "v1") : !(a.use_bulk || can_stage);
-    if (use_v1 || !(a.use_bulk || can_stage)) {
-        switch (c) {
-            case 1: return launch_ssim<1>(ctx, a, s);
-            case 3: return launch_ssim<3>(ctx, a, s);
-            default: return launch_ssim<4>(ctx, a, s);
+    bool use_v1 = !(a.use_bulk || can_stage);
+#ifdef KE_TUNING_PROBES
+    if (const char* which = getenv("KE_SSIM_KERNEL")) use_v1 = use_v1 || !strcmp(which, "v1");  // "v1" | "v2"
+#endif
+    if (ctx->force_ssim_v1) use_v1 = true;
+    int rc;
+    if (use_v1) {
+        rc = c == 1 ? launch_ssim<1>(ctx, a, s) : c == 3 ? launch_ssim<3>(ctx, a, s) : launch_ssim<4>(ctx, a, s);
+    } else if (a.use_bulk) {
+        rc = launch_ssim4<1>(ctx, a, s);
+    } else {
+        // staged v2 reads up to 11 bytes past a thread's first column and converts 16 pixels per step
+        a.pitch = (std::min(w, kBlockCols + 6) + 15) / 16 * 16 + 16;
+        rc = c == 1 ? launch_ssim4s<1>(ctx, a, s) : c == 3 ? launch_ssim4s<3>(ctx, a, s) : launch_ssim4s<4>(ctx, a, s);
+    }
+    if (a.partial) {
+        if (rc == KE_OK) {
+            ke_ssim_finish_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(a.partial, n_pairs, a.n_cblocks, a.inv_count,
+                                                                                   d_ssim);
+            ctx->launches++;
         }
+        cudaFreeAsync(a.partial, s);
+        if (rc == KE_OK) KE_CUDA(cudaGetLastError());
     }
-    if (a.use_bulk) return launch_ssim4<1>(ctx, a, s);
-    // staged v2 reads up to 11 bytes past a thread's first column and converts 16 pixels per step
-    a.pitch = (std::min(w, kBlockCols + 6) + 15) / 16 * 16 + 16;
-    switch (c) {
-        case 1: return launch_ssim4s<1>(ctx, a, s);
-        case 3: return launch_ssim4s<3>(ctx, a, s);
-        default: return launch_ssim4s<4>(ctx, a, s);
-    }
+    return rc;
 }
 
-extern "C" int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w,
-                                  int c, double* h_ssim) {
-    KE_REQUIRE(ctx != nullptr, "ke_ssim_pairs_host: ctx is NULL");
-    KE_REQUIRE(n_pairs >= 0, "ke_ssim_pairs_host: n_pairs < 0");
+// Single-device body of ke_ssim_pairs_host (ke_multi.cu fans it over the devices of a context).
+int ke_ssim_pairs_host_one(ke_ctx* ctx, const uint8_t* h_a, const uint8_t* h_b, int64_t n_pairs, int h, int w, int c,
+                           int gaussian, double* h_ssim) {
     if (n_pairs == 0) return KE_OK;
-    KE_REQUIRE(h_a && h_b && h_ssim, "ke_ssim_pairs_host: NULL buffer");
     KE_REQUIRE(c == 1 || c == 3 || c == 4, "ke_ssim_pairs_host: channels must be 1, 3 or 4 (got %d)", c);
-    if (h < kWin || w < kWin) {
-        ke_set_error("win_size exceeds image extent (%dx%d < 7)", w, h);
+    const int win = gaussian ? kGaussWin : kWin;
+    if (h < win || w < win) {
+        ke_set_error("win_size exceeds image extent (%dx%d < %d)", w, h, win);
         return KE_E_UNSUPPORTED;
     }
     KeDeviceGuard guard(ctx->device);
@@ -844,12 +1001,10 @@ extern "C" int ke_ssim_pairs_host(ke_ctx* ctx, const uint8_t* h_a, const uint8_t
         cudaStream_t s = ctx->copy_stream[b];
         uint8_t* da = (uint8_t*)d_bank[b];
         uint8_t* db = da + per_chunk * stride;
-        KE_CUDA(cudaMemcpy2DAsync(da, (size_t)stride, h_a + p0 * plane, (size_t)plane, (size_t)plane, (size_t)cnt,
-                                  cudaMemcpyHostToDevice, s));
-        KE_CUDA(cudaMemcpy2DAsync(db, (size_t)stride, h_b + p0 * plane, (size_t)plane, (size_t)plane, (size_t)cnt,
-                                  cudaMemcpyHostToDevice, s));
+        if ((rc = ke_h2d_staged_2d(ctx, da, (size_t)stride, h_a + p0 * plane, (size_t)plane, (size_t)cnt, s))) return rc;
+        if ((rc = ke_h2d_staged_2d(ctx, db, (size_t)stride, h_b + p0 * plane, (size_t)plane, (size_t)cnt, s))) return rc;
         rc = ke_ssim_batch(ctx, da, h, w, c, stride, (int64_t)w * c, (const int64_t*)d_idx, (const int64_t*)d_idx + per_chunk, cnt,
-                           (double*)d_out + p0, s);
+                           gaussian, (double*)d_out + p0, s);
         if (rc) return rc;
     }
     for (auto s : ctx->copy_stream) KE_CUDA(cudaStreamSynchronize(s));

@@ -30,13 +30,13 @@ __device__ __forceinline__ int lerp_at(const unsigned char* grid, int g, int y, 
     return (top * (256 - ty) + bot * ty) >> 16;
 }
 
-__global__ void __launch_bounds__(kThreads) ke_synth_kernel(unsigned char* out, long long start, int h, int w, int c,
-                                                            long long n_set, unsigned long long seed,
+__global__ void __launch_bounds__(kThreads) ke_synth_kernel(unsigned char* out, long long start, long long item_stride, int h,
+                                                            int w, int c, long long n_set, unsigned long long seed,
                                                             int planted_permille, int slabs) {
     __shared__ unsigned char g1[4][G1 * G1], g2[4][G2 * G2];
     const long long k = blockIdx.x / slabs;
     const int slab = blockIdx.x % slabs;
-    const long long i = start + k;
+    const long long i = start + k * item_stride;
     const long long n_base = n_set - (n_set * planted_permille) / 1000;
     long long src = i;
     int variant = 0;
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kThreads) ke_synth_kernel(unsigned char* out, 
 
 }  // namespace
 
-extern "C" int ke_synth_images(ke_ctx* ctx, uint8_t* d_out, int64_t start, int64_t count, int h, int w, int c,
-                               int64_t n_set, uint64_t seed, int planted_permille, void* stream) {
+extern "C" int ke_synth_images(ke_ctx* ctx, uint8_t* d_out, int64_t start, int64_t item_stride, int64_t count, int h, int w,
+                               int c, int64_t n_set, uint64_t seed, int planted_permille, void* stream) {
     KE_REQUIRE(ctx && d_out, "ke_synth_images: NULL argument");
     KE_REQUIRE(count >= 0 && h > 0 && w > 0 && c >= 1 && c <= 4, "ke_synth_images: bad geometry");
     if (count == 0) return KE_OK;
@@ -84,7 +84,7 @@ extern "C" int ke_synth_images(ke_ctx* ctx, uint8_t* d_out, int64_t start, int64
     const int slabs = (h + kSlabRows - 1) / kSlabRows;
     KE_REQUIRE(count * slabs < (1ll << 31), "ke_synth_images: too many images in one call");
     ke_synth_kernel<<<(unsigned)(count * slabs), kThreads, 0, (cudaStream_t)stream>>>(
-        d_out, start, h, w, c, n_set, seed, planted_permille, slabs);
+        d_out, start, item_stride, h, w, c, n_set, seed, planted_permille, slabs);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;

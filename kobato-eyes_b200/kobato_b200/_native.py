@@ -14,6 +14,10 @@ KE_OK, KE_E_INVALID, KE_E_CUDA, KE_E_CAPACITY, KE_E_NOMEM, KE_E_UNSUPPORTED = 0,
 KE_JOIN_REQUIRE_BAND = 1
 KE_OPT_PHASH_GENERIC = 1
 KE_OPT_JOIN_MODE = 2
+KE_OPT_SSIM_V1 = 3
+KE_OPT_RESIZE_GENERIC = 4
+KE_OPT_PHASH_LADDER = 5
+KE_ABI_VERSION = 2
 
 _LIB_PATH = Path(__file__).resolve().parent / "libkobato_b200.so"
 _lib = None
@@ -40,6 +44,9 @@ _SIGNATURES = {
     "ke_abi_version": (C.c_int, []),
     "ke_last_error": (C.c_char_p, []),
     "ke_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ke_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "ke_ctx_device_count": (C.c_int, [C.c_void_p]),
+    "ke_ctx_child": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ke_ctx_destroy": (None, [C.c_void_p]),
     "ke_ctx_device": (C.c_int, [C.c_void_p]),
     "ke_ctx_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -59,9 +66,15 @@ _SIGNATURES = {
                                        C.POINTER(C.c_int64)]),
     "ke_hamming_join_pairs": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "ke_ssim_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
-                                C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "ke_ssim_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "ke_ssim_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "ke_luma_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                 C.c_int64, C.c_void_p, C.c_void_p]),
+    "ke_cluster_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ke_scan_table_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                     C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ke_gray_resize_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                        C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ke_tile_ahash_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -70,8 +83,8 @@ _SIGNATURES = {
     "ke_plane_sad_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p]),
     "ke_cluster_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
-    "ke_synth_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
-                                  C.c_uint64, C.c_int, C.c_void_p]),
+    "ke_synth_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                  C.c_int64, C.c_uint64, C.c_int, C.c_void_p]),
     "ke_microbench_popc": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -99,7 +112,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.ke_abi_version() != 1:
+            if lib.ke_abi_version() != KE_ABI_VERSION:
                 raise KobatoNativeError("libkobato_b200.so ABI version mismatch")
             _lib = lib
     return _lib
@@ -119,16 +132,33 @@ def check(status: int, what: str = "") -> None:
     raise KobatoNativeError(f"{what}: {msg} (status {status})", status)
 
 
-class Context:
-    """Owns one ``ke_ctx`` (one per process and device)."""
+class ScanStats(C.Structure):
+    """``ke_scan_stats`` of include/kobato_b200.h."""
 
-    def __init__(self, device: int = 0):
+    _fields_ = [(name, C.c_int64) for name in ("n_buckets", "buckets_ge2", "max_bucket", "candidates", "after_same_id",
+                                               "edges", "members", "clusters")]
+
+    def as_dict(self) -> dict:
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+class Context:
+    """Owns one ``ke_ctx``: one device, or several (``ke_ctx_create_multi``: the ``_host`` entry points then fan their
+    units over all of them, ``child(k)`` drives device k with ``d_`` pointers)."""
+
+    def __init__(self, device=0, *, _borrowed=None):
         lib = load()
-        handle = C.c_void_p()
-        check(lib.ke_ctx_create(int(device), C.byref(handle)), "ke_ctx_create")
-        self._h = handle
-        self.device = int(device)
-        self.sm_count = lib.ke_ctx_sm_count(handle)
+        if _borrowed is not None:  # a child of a multi-device context: not ours to destroy
+            self._h, self._owned = C.c_void_p(_borrowed), False
+        else:
+            devices = [int(device)] if isinstance(device, int) else [int(d) for d in device]
+            arr = (C.c_int * len(devices))(*devices)
+            handle = C.c_void_p()
+            check(lib.ke_ctx_create_multi(arr, len(devices), C.byref(handle)), "ke_ctx_create_multi")
+            self._h, self._owned = handle, True
+        self.device = int(lib.ke_ctx_device(self._h))
+        self.n_devices = int(lib.ke_ctx_device_count(self._h))
+        self.sm_count = lib.ke_ctx_sm_count(self._h)
         self.lock = threading.Lock()
 
     @property
@@ -136,6 +166,17 @@ class Context:
         if self._h is None:
             raise KobatoNativeError("context already destroyed")
         return self._h
+
+    @property
+    def devices(self) -> list[int]:
+        lib = load()
+        return [int(lib.ke_ctx_device(C.c_void_p(lib.ke_ctx_child(self.handle, k)))) for k in range(self.n_devices)]
+
+    def child(self, k: int) -> "Context":
+        h = load().ke_ctx_child(self.handle, int(k))
+        if not h:
+            raise IndexError(k)
+        return self if k == 0 else Context(_borrowed=h)
 
     @property
     def launches(self) -> int:
@@ -146,7 +187,8 @@ class Context:
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
-            load().ke_ctx_destroy(self._h)
+            if self._owned:
+                load().ke_ctx_destroy(self._h)
             self._h = None
 
     def __del__(self):  # pragma: no cover
@@ -157,10 +199,71 @@ class Context:
 
 
 _contexts: dict[int, Context] = {}
+_group: Context | None = None
+
+
+def _default_devices() -> list[int]:
+    """Devices of the process-wide multi-device context: ``KE_DEVICES=0,2,3`` if set; under a one-process-per-GPU
+    launcher (``WORLD_SIZE`` > 1: bench.py, pipeline.scan) this rank's device only; otherwise every visible device —
+    the reference calls this path from one worker thread of one process (src/ui/dup_tab.py:118)."""
+    import os
+    import sys
+
+    env = os.environ.get("KE_DEVICES", "").strip()
+    if env and env != "all":
+        return [int(x) for x in env.split(",") if x.strip()]
+    torch = sys.modules.get("torch")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not env:
+        if torch is not None and torch.cuda.is_available():
+            return [torch.cuda.current_device()]
+        return [int(os.environ.get("LOCAL_RANK", "0"))]
+    if torch is not None and torch.cuda.is_available():
+        return list(range(torch.cuda.device_count()))
+    try:
+        import ctypes.util
+
+        rt = C.CDLL(ctypes.util.find_library("cudart") or "libcudart.so")
+        n = C.c_int(0)
+        if rt.cudaGetDeviceCount(C.byref(n)) == 0 and n.value > 0:
+            return list(range(n.value))
+    except OSError:
+        pass
+    return [0]
+
+
+def group(devices=None) -> Context:
+    """The process-wide multi-device context behind the host-array entry points (``ops.*`` on numpy inputs and the
+    drop-in modules on top of them).  ``devices`` (first call only) overrides ``KE_DEVICES`` / the default."""
+    global _group
+    with _lock:
+        g = _group
+    if g is None:
+        g = Context(list(devices) if devices is not None else _default_devices())
+        with _lock:
+            if _group is None:
+                _group = g
+                for k, dev in enumerate(g.devices):  # device tensors on these GPUs share the children
+                    _contexts.setdefault(dev, g.child(k))
+            g = _group
+    return g
+
+
+def reset_group(devices=None) -> Context:
+    """Drop the process-wide context (tests) and build a new one over ``devices``."""
+    global _group
+    with _lock:
+        old, _group = _group, None
+        if old is not None:
+            for dev in list(_contexts):
+                if _contexts[dev] is old or not _contexts[dev]._owned:
+                    del _contexts[dev]
+    if old is not None:
+        old.close()
+    return group(devices)
 
 
 def context(device: int | None = None) -> Context:
-    """Process-wide context for ``device`` (default: torch's current device if torch is loaded, else 0)."""
+    """Process-wide single-device context for ``device`` (default: torch's current device if torch is loaded, else 0)."""
     if device is None:
         device = 0
         import sys

@@ -92,13 +92,15 @@ def hash_decoded(decoded: list) -> list[Tuple[int, int, int] | None]:
         return out
     try:
         sigs = phash_dhash_many([decoded[k][1] for k in live])
-    except ValueError:
-        # one undecodable geometry must not sink the window: retry one by one, dropping failures
+    except Exception:
+        # one failing geometry (bad shape, rows that do not fit shared memory, a CUDA error status ...) must not sink
+        # the window: the reference's worker swallows ANY exception of a file and returns None (:36-37), so retry one by
+        # one and drop only the failures
         sigs = []
         for k in live:
             try:
                 sigs.append(phash_dhash_many([decoded[k][1]])[0])
-            except ValueError:
+            except Exception:
                 sigs.append(None)
     for k, s in zip(live, sigs):
         if s is not None:
@@ -121,13 +123,25 @@ def compute_signatures_mp(
     done = 0
     results: List[Tuple[int, int, int]] = []
     workers = max_workers or max(1, (os.cpu_count() or 4) - 1)
-    window = max(1, int(chunksize)) * workers  # decoded images in flight between GPU launches
+    # Decoded images in flight between GPU launches: at most chunksize x workers files AND at most KE_SIG_WINDOW_MB of
+    # pixels (default 512 MB) — the reference holds one image per worker, and multi-megapixel photographs are ~50 MB
+    # each once decoded, so the window is bounded by bytes, not only by count.
+    window = max(1, int(chunksize)) * workers
+    window_bytes = int(os.environ.get("KE_SIG_WINDOW_MB", "512")) << 20
+    step = max(1, workers) * 2
     with ThreadPoolExecutor(max_workers=workers) as pool:
-        for start in range(0, total, window):
+        start = 0
+        while start < total:
             if cancel_fn and cancel_fn():
                 pool.shutdown(wait=False, cancel_futures=True)
                 return results
-            decoded = list(pool.map(_decode_worker, tasks[start:start + window]))
+            decoded: list = []
+            held = 0
+            while start < total and len(decoded) < window and held < window_bytes:
+                part = list(pool.map(_decode_worker, tasks[start:start + min(step, window - len(decoded))]))
+                held += sum(d[1].nbytes for d in part if d is not None)
+                decoded += part
+                start += len(part)
             for out in hash_decoded(decoded):
                 if cancel_fn and cancel_fn():
                     pool.shutdown(wait=False, cancel_futures=True)

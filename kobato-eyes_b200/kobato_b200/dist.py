@@ -79,14 +79,15 @@ def _gather_padded(padded):
     return out
 
 
-def all_gather_hashes(local):
+def all_gather_hashes(local, return_counts: bool = False):
     """Concatenate per-rank int64 hash shards (possibly of different lengths) on every rank: the counts, then ONE
-    all_gather of the (padded) shards; equal shards (the weak-scaling case) need no padding and no re-packing."""
+    all_gather of the (padded) shards; equal shards (the weak-scaling case) need no padding and no re-packing.
+    With ``return_counts`` also the per-rank shard lengths (rank r owns rows ``sum(counts[:r]) ...`` of the table)."""
     import torch
 
     rank, size = world()
     if size == 1:
-        return local
+        return (local, [int(local.numel())]) if return_counts else local
     local = local.contiguous().view(-1)
     counts = _gather_counts(local.numel(), local.device)
     cap = max(max(counts), 1)
@@ -97,8 +98,56 @@ def all_gather_hashes(local):
         padded[: local.numel()] = local
     out = _gather_padded(padded)
     if all(c == cap for c in counts):
-        return out.view(-1)
-    return torch.cat([out[r, :c] for r, c in enumerate(counts)])
+        table = out.view(-1)
+    else:
+        table = torch.cat([out[r, :c] for r, c in enumerate(counts)])
+    return (table, counts) if return_counts else table
+
+
+def plan_cross_pairs(ci: np.ndarray, cj: np.ndarray, offsets: np.ndarray, rank: int, size: int) -> dict:
+    """Who verifies which candidate pair, and which images travel for it.  Pure arithmetic on the (global) candidate
+    list every rank holds, so all ranks derive the same plan without exchanging anything.
+
+    ``offsets[r]`` = first table row of rank r (``offsets[size]`` = table length; shards may be unequal).  A pair whose
+    images live on one rank is scored there; a cross-shard pair (i on rank a, j on rank b) is scored by a when i + j is
+    even and by b otherwise, so neither end of the table collects all of them.  The other image comes over as a luma plane.
+
+    Returns: ``local`` (positions of the pairs this rank scores from its own bank), ``cross`` (positions it scores with
+    one received image), ``send[s]`` (sorted distinct global rows of MINE that rank s needs), ``recv[r]`` (sorted distinct
+    global rows of rank r that I need): ``send`` of r towards s equals ``recv`` of s from r by construction."""
+    ci = np.asarray(ci, np.int64)
+    cj = np.asarray(cj, np.int64)
+    offsets = np.asarray(offsets, np.int64)
+    own_i = np.searchsorted(offsets, ci, side="right") - 1
+    own_j = np.searchsorted(offsets, cj, side="right") - 1
+    scorer = np.where(own_i == own_j, own_i, np.where(((ci + cj) & 1) == 0, own_i, own_j))
+    is_cross = own_i != own_j
+    # the image that has to travel: the one NOT owned by the scorer
+    trav = np.where(scorer == own_i, cj, ci)
+    trav_owner = np.where(scorer == own_i, own_j, own_i)
+    send, recv = [], []
+    for peer in range(size):
+        out_sel = is_cross & (trav_owner == rank) & (scorer == peer)
+        in_sel = is_cross & (trav_owner == peer) & (scorer == rank)
+        send.append(np.unique(trav[out_sel]) if peer != rank else np.zeros(0, np.int64))
+        recv.append(np.unique(trav[in_sel]) if peer != rank else np.zeros(0, np.int64))
+    return {"local": np.flatnonzero(~is_cross & (scorer == rank)), "cross": np.flatnonzero(is_cross & (scorer == rank)),
+            "send": send, "recv": recv, "own_i": own_i, "own_j": own_j, "scorer": scorer}
+
+
+def exchange_rows(rows, send_counts, recv_counts):
+    """ONE ``all_to_all_single``: ``rows`` = [sum(send_counts), k] with the rows for rank 0 first, then rank 1, ...;
+    returns [sum(recv_counts), k] ordered by source rank."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    out = torch.empty((int(sum(recv_counts)),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    if size == 1:
+        return out
+    dist.all_to_all_single(out, rows.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
+                           input_split_sizes=[int(c) for c in send_counts])
+    return out
 
 
 def all_gather_varlen(local):

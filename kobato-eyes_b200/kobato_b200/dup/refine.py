@@ -133,9 +133,19 @@ def refine_pairs_batch(pairs: Sequence[tuple[int, int, str | Path, str | Path]],
                        use_orb: bool = True) -> list[RefinedMatch | None]:
     """[(file_id_a, file_id_b, path_a, path_b)] -> [RefinedMatch | None], same per-pair semantics
     as ``refine_pair`` with every SSIM of one geometry in a single GPU launch."""
+    cfg = thresholds or RefinementThresholds()
+    # bounded rounds: the planes of at most KE_REFINE_CHUNK pairs (default 256) are resident between SSIM launches
+    # (the reference holds one pair at a time; multi-megapixel planes of ALL pairs would not fit host memory)
+    chunk = max(1, int(os.environ.get("KE_REFINE_CHUNK", "256")))
+    out: list[RefinedMatch | None] = []
+    for lo in range(0, len(pairs), chunk):
+        out += _refine_chunk(pairs[lo:lo + chunk], cfg, max_workers, use_orb)
+    return out
+
+
+def _refine_chunk(pairs, cfg: RefinementThresholds, max_workers, use_orb) -> list[RefinedMatch | None]:
     from .. import ops
 
-    cfg = thresholds or RefinementThresholds()
     workers = max_workers or max(1, (os.cpu_count() or 4) - 1)
 
     def prepare(pair):
@@ -168,7 +178,7 @@ def refine_pairs_batch(pairs: Sequence[tuple[int, int, str | Path, str | Path]],
         try:
             vals = ops.ssim_pairs(np.stack([prepared[k]["planes"][0] for k in members]),
                                   np.stack([prepared[k]["planes"][1] for k in members]))
-        except ValueError as exc:  # e.g. a side < 7: skimage raises, the reference records "ssim unavailable"
+        except Exception as exc:  # e.g. a side < 7: skimage raises, the reference records "ssim unavailable" (:91-94)
             logger.warning("SSIM refinement failed for %d pair(s) of shape %s: %s", len(members), shape, exc)
             continue
         for k, v in zip(members, vals.tolist()):

@@ -11,11 +11,15 @@ returns them inside the cluster entries.
 
 How the work is split:
   * the reference's per-bucket double loop (:262-290) is replaced by ONE all-pairs Hamming join
-    on the GPU (``ke_hamming_join`` with the band-equality predicate, which makes the candidate
+    on the GPU(s) (``ke_hamming_join`` with the band-equality predicate, which makes the candidate
     set identical to the LSH buckets' — see tests/test_oracle_pinned.py);
-  * ``KE_DUP_BUCKET_PAIR_CAP`` (:239-266) becomes a per-hash band mask computed with NumPy;
-  * the cheap per-candidate filters (same id, size ratio, cosine), edge de-duplication, DSU,
-    keeper choice and the sorts run on the host over the (few) surviving pairs.
+  * the table path (default; ``ke_scan_table_host``): bucket statistics, the
+    ``KE_DUP_BUCKET_PAIR_CAP`` mask (:239-266), the same-id / size-ratio gates (:271-279) and the DSU +
+    ``best_hamming`` (:304-318) all run on the device over COLUMN ARRAYS; Python only builds the
+    ``DuplicateCluster`` objects of the members (keeper choice and the sorts, :320-356).
+    ``build_clusters_from_columns`` takes the SQLite columns directly (no per-row objects at all);
+  * the legacy path (cosine gate in use, repeated file ids, or an injected ``join``): per-candidate
+    filters, edge de-duplication, DSU on the host over the (few) surviving pairs.
 """
 from __future__ import annotations
 
@@ -207,11 +211,12 @@ class _Bands:
 class DuplicateScanner:
     """Duplicate clusters from a GPU all-pairs Hamming join + host DSU (reference :203-415)."""
 
-    def __init__(self, config: DuplicateScanConfig, *, join=None) -> None:
+    def __init__(self, config: DuplicateScanConfig, *, join=None, scan_table=None) -> None:
         self._config = config
         assert config.band_bits * config.band_count <= 64, "band config too large"
         self._band_mask = (1 << config.band_bits) - 1
-        self._join = join  # injectable for tests / multi-GPU (see kobato_b200.dist)
+        self._join = join  # injectable for tests / multi-process joins (see kobato_b200.dist): selects the legacy path
+        self._scan_table = scan_table  # injectable stand-in for ops.scan_table (tests)
 
     # -- candidate search ---------------------------------------------------------------
 
@@ -289,10 +294,78 @@ class DuplicateScanner:
                     cfg.cosine_threshold)
         if not candidates:
             return []
+        if self._join is None and not self._cosine_in_use(candidates):
+            n = len(candidates)
+            ids = np.fromiter((int(f.file_id) for f in candidates), dtype=np.int64, count=n)
+            if _all_distinct(ids):
+                hashes = np.fromiter((int(f.phash) & U64 for f in candidates), dtype=np.uint64, count=n)
+                sizes = np.fromiter((int(f.size or 0) for f in candidates), dtype=np.int64, count=n)
+                scan = self._scan_columns(hashes, ids, sizes)
+                return self._clusters_of(scan, candidates.__getitem__)
         edges = self.find_edges(candidates)
         if not edges:
             return []
         return assemble_clusters(candidates, edges)
+
+    def build_clusters_from_columns(self, file_id, phash, size=None, *, make_file) -> list[DuplicateCluster]:
+        """``build_clusters`` for callers that hold the rows of ``iter_files_for_dup`` (reference
+        src/db/repository.py:416-455) as column arrays: ``file_id`` int64 (distinct), ``phash`` int64 — SQLite's signed
+        ``phash_u64`` (src/db/schema.py:65-72) — or uint64, ``size`` int64 or None.  ``make_file(row_index)`` must
+        return the ``DuplicateFile`` of a table row; it is called for the members of clusters only."""
+        cfg = self._config
+        if cfg.cosine_threshold is not None:
+            raise ValueError("the cosine gate needs embeddings: use build_clusters(files)")
+        ids = np.ascontiguousarray(file_id, np.int64).reshape(-1)
+        if not _all_distinct(ids):
+            raise ValueError("build_clusters_from_columns needs distinct file ids")
+        logger.info("dup: candidates=%d band_bits=%d band_count=%d ham_th=%d size_ratio=%s cosine_th=%s", len(ids),
+                    cfg.band_bits, cfg.band_count, cfg.hamming_threshold, cfg.size_ratio, cfg.cosine_threshold)
+        if len(ids) == 0:
+            return []
+        return self._clusters_of(self._scan_columns(phash, ids, size), make_file)
+
+    def _cosine_in_use(self, candidates: Sequence) -> bool:
+        """The cosine gate (:372-400) can only drop a pair when a threshold is set AND embeddings exist."""
+        if self._config.cosine_threshold is None:
+            return False
+        return any(getattr(f, "embedding", None) for f in candidates)
+
+    def _scan_columns(self, hashes, ids, sizes) -> dict:
+        scan_table = self._scan_table
+        if scan_table is None:
+            from .. import ops
+
+            scan_table = ops.scan_table
+        cfg = self._config
+        pair_cap = _safe_positive_int(os.environ.get("KE_DUP_BUCKET_PAIR_CAP"))
+        scan = scan_table(hashes, ids, sizes, threshold=cfg.hamming_threshold, band_bits=cfg.band_bits,
+                              band_count=cfg.band_count, size_ratio=cfg.size_ratio, pair_cap=pair_cap)
+        st = {"n_buckets": 0, "buckets_ge2": 1, "max_bucket": 0, "candidates": 0, "after_same_id": 0, "edges": 0,
+              "members": 0, "clusters": 0, **scan["stats"]}
+        max_pairs = (st["max_bucket"] * (st["max_bucket"] - 1)) // 2
+        logger.info("dup: buckets=%d (>=2:%d) max_bucket=%d max_bucket_pairs=%d pair_cap=%s", st["n_buckets"],
+                    st["buckets_ge2"], st["max_bucket"], max_pairs, pair_cap)
+        if pair_cap is not None and max_pairs > pair_cap:
+            logger.warning("dup: largest bucket has %d pair(s), above KE_DUP_BUCKET_PAIR_CAP=%d; large buckets "
+                           "will be skipped", max_pairs, pair_cap)
+        if st["buckets_ge2"] == 0:
+            logger.warning("dup: no bucket has 2+ items -> edges=0")
+        logger.info("dup: gpu candidates (band & ham)=%d -> distinct ids=%d -> size=%d edges -> members=%d clusters=%d",
+                    st["candidates"], st["after_same_id"], st["edges"], st["members"], st["clusters"])
+        return scan
+
+    @staticmethod
+    def _clusters_of(scan: dict, file_of) -> list[DuplicateCluster]:
+        """Members grouped by component -> ordered ``DuplicateCluster`` list (reference :320-356)."""
+        index, best, offsets = scan["index"].tolist(), scan["best"].tolist(), scan["offsets"].tolist()
+        clusters: list[DuplicateCluster] = []
+        for lo, hi in zip(offsets[:-1], offsets[1:]):
+            if hi - lo < 2:
+                continue
+            entries = [DuplicateClusterEntry(file=file_of(index[q]), best_hamming=best[q]) for q in range(lo, hi)]
+            clusters.append(_ordered_cluster(entries))
+        clusters.sort(key=_cluster_key)
+        return clusters
 
     # -- per-candidate gates (reference :358-400) ----------------------------------------
 
@@ -367,12 +440,30 @@ def assemble_clusters(candidates: Sequence, edges: Mapping[tuple[int, int], Dupl
         entries = [DuplicateClusterEntry(file=by_id[m], best_hamming=best.get(m)) for m in sorted(members) if m in by_id]
         if len(entries) < 2:
             continue
-        keeper_id = DuplicateScanner._choose_keeper(entries)
-        entries.sort(key=lambda e: (0 if e.file.file_id == keeper_id else 1, -(e.file.size or 0), -_resolution(e.file),
-                                    -_ext_priority(e.file), Path(e.file.path).name.lower(), e.file.file_id))
-        clusters.append(DuplicateCluster(files=entries, keeper_id=keeper_id))
-    clusters.sort(key=lambda c: (-(max(e.file.size or 0 for e in c.files)), Path(c.files[0].file.path).as_posix().lower()))
+        clusters.append(_ordered_cluster(entries))
+    clusters.sort(key=_cluster_key)
     return clusters
+
+
+def _ordered_cluster(entries: list) -> DuplicateCluster:
+    """Keeper choice and the keeper-first entry order of the reference (:336-352)."""
+    keeper_id = DuplicateScanner._choose_keeper(entries)
+    entries.sort(key=lambda e: (0 if e.file.file_id == keeper_id else 1, -(e.file.size or 0), -_resolution(e.file),
+                                -_ext_priority(e.file), Path(e.file.path).name.lower(), e.file.file_id))
+    return DuplicateCluster(files=entries, keeper_id=keeper_id)
+
+
+def _cluster_key(c: DuplicateCluster):
+    return (-(max(e.file.size or 0 for e in c.files)), Path(c.files[0].file.path).as_posix().lower())
+
+
+def _all_distinct(ids: np.ndarray) -> bool:
+    """SQLite's ``ORDER BY f.id`` hands the ids over ascending: one pass; anything else goes through a sort."""
+    if ids.size < 2:
+        return True
+    if bool(np.all(ids[1:] > ids[:-1])):
+        return True
+    return np.unique(ids).size == ids.size
 
 
 __all__ = ["DuplicateFile", "DuplicateCluster", "DuplicateClusterEntry", "DuplicateScanConfig", "DuplicateScanner"]

@@ -81,7 +81,7 @@ def phash_dhash_batch(images, *, want_margin: bool = False, want_planes: bool = 
         n, h, w, c = x.shape
         if want_planes:
             raise ValueError("planes are only returned for device tensors")
-        ctx = nat.context()
+        ctx = nat.group()  # every device of the process-wide context takes a contiguous range of the images
         ph = np.empty(n, np.int64)
         dh = np.empty(n, np.int64)
         mg = np.empty(n, np.float32) if want_margin else None
@@ -145,7 +145,7 @@ def hamming_join(hashes, threshold: int, *, require_band: bool = False, band_bit
         if h.dtype not in (np.int64, np.uint64):
             raise ValueError("hashes must be int64 or uint64")
         n = h.shape[0]
-        ctx = nat.context()
+        ctx = nat.group()  # the tiles of the triangle are dealt over every device of the process-wide context
         allow = np.ascontiguousarray(band_allow, np.uint64) if band_allow is not None else None
         cap = int(capacity) if capacity is not None else max(1 << 16, 4 * n)
         while True:
@@ -204,11 +204,12 @@ def hamming_join_device(hashes, threshold: int, *, require_band: bool = False, b
 # ----------------------------------------------------------------------------- K3
 
 
-def ssim_batch(bank, ia, ib):
+def ssim_batch(bank, ia, ib, *, gaussian: bool = False):
     """SSIM of pairs (bank[ia[p]], bank[ib[p]]) — reference src/dup/refine.py:52 semantics.
 
     bank: CUDA uint8 tensor ``[m,h,w]`` ('L' planes) or ``[m,h,w,c]`` (RGB/RGBA, Pillow luma applied
-    on the fly); ia/ib: index sequences.  Returns a float64 CUDA tensor ``[n_pairs]``."""
+    on the fly); ia/ib: index sequences.  Returns a float64 CUDA tensor ``[n_pairs]``.
+    ``gaussian=True`` is skimage's ``gaussian_weights=True`` window (not the reference's path)."""
     torch = _torch()
     lib = nat.load()
     if not (_is_tensor(bank) and bank.is_cuda and bank.dtype == torch.uint8):
@@ -230,14 +231,14 @@ def ssim_batch(bank, ia, ib):
         ctx = nat.context(dev)
         with ctx.lock:
             st = lib.ke_ssim_batch(ctx.handle, x.data_ptr(), h, w, c, x.stride(0), x.stride(1), ia_t.data_ptr(),
-                                   ib_t.data_ptr(), n, out.data_ptr(), _stream_ptr(dev))
+                                   ib_t.data_ptr(), n, 1 if gaussian else 0, out.data_ptr(), _stream_ptr(dev))
         if st == nat.KE_E_UNSUPPORTED:
             raise ValueError(nat.last_error())  # the reference (skimage) raises ValueError here
         nat.check(st, "ke_ssim_batch")
     return out
 
 
-def ssim_pairs(a, b) -> np.ndarray:
+def ssim_pairs(a, b, *, gaussian: bool = False) -> np.ndarray:
     """SSIM of host images: a, b uint8 ``[n,h,w]`` 'L' planes (or one ``[h,w]`` pair) or
     ``[n,h,w,c]`` RGB(A) (Pillow luma applied on the GPU) -> float64 ``[n]``."""
     lib = nat.load()
@@ -252,9 +253,9 @@ def ssim_pairs(a, b) -> np.ndarray:
     n, h, w, c = a.shape
     out = np.empty(n, np.float64)
     if n:
-        ctx = nat.context()
+        ctx = nat.group()
         with ctx.lock:
-            st = lib.ke_ssim_pairs_host(ctx.handle, _np_ptr(a), _np_ptr(b), n, h, w, c, _np_ptr(out))
+            st = lib.ke_ssim_pairs_host(ctx.handle, _np_ptr(a), _np_ptr(b), n, h, w, c, 1 if gaussian else 0, _np_ptr(out))
         if st == nat.KE_E_UNSUPPORTED:
             raise ValueError(nat.last_error())
         nat.check(st, "ke_ssim_pairs_host")
@@ -418,8 +419,9 @@ def cluster_pairs(a, b):
 
 
 def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n_set: int = 1 << 30,
-                        seed: int | None = None, planted: float = 0.05, device=None, out=None):
-    """CUDA twin of ``synth.synth_image`` (identical bytes) -> uint8 CUDA tensor [count,h,w,c]."""
+                        seed: int | None = None, planted: float = 0.05, device=None, out=None, stride: int = 1):
+    """CUDA twin of ``synth.synth_image`` (identical bytes) -> uint8 CUDA tensor [count,h,w,c] holding the images
+    ``start, start + stride, ...`` of the set."""
     from . import synth
 
     torch = _torch()
@@ -429,10 +431,106 @@ def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n
         out = torch.empty((count, h, w, c), dtype=torch.uint8, device=dev)
     ctx = nat.context(dev.index)
     with ctx.lock:
-        nat.check(lib.ke_synth_images(ctx.handle, out.data_ptr(), start, count, h, w, c, n_set,
+        nat.check(lib.ke_synth_images(ctx.handle, out.data_ptr(), start, int(stride), count, h, w, c, n_set,
                                       (synth.SEED if seed is None else seed) & U64, int(round(planted * 1000)),
                                       _stream_ptr(dev.index)), "ke_synth_images")
     return out if c > 1 else out[..., 0]
+
+
+def luma_planes(bank, idx):
+    """``convert("L")`` planes of ``bank[idx]`` (Pillow rgb2l; reference src/dup/refine.py:48-49) -> uint8 CUDA tensor
+    ``[len(idx), h, w]``."""
+    torch = _torch()
+    lib = nat.load()
+    x = _as_cuda_u8(bank)
+    m, h, w, c = x.shape
+    idx_t = torch.as_tensor(idx, dtype=torch.int64).to(x.device).contiguous()
+    n = idx_t.numel()
+    if n and (int(idx_t.max()) >= m or int(idx_t.min()) < 0):
+        raise ValueError("image index out of range")
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    if n:
+        dev = x.device.index
+        ctx = nat.context(dev)
+        with ctx.lock:
+            nat.check(lib.ke_luma_planes(ctx.handle, x.data_ptr(), h, w, c, x.stride(0), x.stride(1), idx_t.data_ptr(), n,
+                                         out.data_ptr(), _stream_ptr(dev)), "ke_luma_planes")
+    return out
+
+
+def cluster_pairs_device(a, b, n_nodes: int):
+    """Component label (= smallest member index) of every node that occurs in a pair, -1 for the others: the device
+    union-find (``ke_cluster_pairs``) over CUDA int32/uint32 index tensors.  Returns an int64 CUDA tensor ``[n_nodes]``."""
+    torch = _torch()
+    lib = nat.load()
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    if not (a.is_cuda and b.is_cuda) or a.shape != b.shape or a.dim() != 1:
+        raise ValueError("cluster_pairs_device wants two 1-D CUDA index tensors of equal length")
+    a32 = a.to(torch.int32).contiguous()
+    b32 = b.to(torch.int32).contiguous()
+    label = torch.empty(int(n_nodes), dtype=torch.int32, device=a.device)
+    dev = a.device.index
+    ctx = nat.context(dev)
+    with ctx.lock:
+        nat.check(lib.ke_cluster_pairs(ctx.handle, a32.data_ptr(), b32.data_ptr(), a32.numel(), int(n_nodes), label.data_ptr(),
+                                       _stream_ptr(dev)), "ke_cluster_pairs")
+    return label.to(torch.int64)  # 0xFFFFFFFF reads back as -1
+
+
+def scan_table(phash, file_id=None, size=None, *, threshold: int = 8, band_bits: int = 16, band_count: int = 4,
+               size_ratio: float | None = None, pair_cap: int | None = None, want_edges: bool = False) -> dict:
+    """Table-level duplicate scan (``ke_scan_table_host``): the columns of ``iter_files_for_dup`` (reference
+    src/db/repository.py:416-455) -> members grouped by component.
+
+    phash: int64 (SQLite's signed ``phash_u64``) or uint64 array; file_id / size: int64 arrays or None.
+    Returns ``{"index", "label", "best", "offsets", "stats"}`` (+ ``"edges": (i, j, dist)``): component c is
+    ``index[offsets[c]:offsets[c+1]]`` (table rows, ascending), its label the smallest row, ``best`` the reference's
+    best_hamming per member (src/dup/scanner.py:304-313).  File ids must be distinct."""
+    lib = nat.load()
+    ph = np.ascontiguousarray(phash).reshape(-1)
+    if ph.dtype == np.uint64:
+        ph = ph.view(np.int64)
+    if ph.dtype != np.int64:
+        raise ValueError("phash must be int64 or uint64")
+    n = ph.shape[0]
+    fid = None if file_id is None else np.ascontiguousarray(file_id, np.int64).reshape(-1)
+    sz = None if size is None else np.ascontiguousarray(size, np.int64).reshape(-1)
+    if (fid is not None and fid.shape[0] != n) or (sz is not None and sz.shape[0] != n):
+        raise ValueError("columns must have the same length")
+    ctx = nat.group()
+    stats = nat.ScanStats()
+    mcap, ecap = max(1 << 16, n // 8), (max(1 << 16, n // 8) if want_edges else 0)
+    while True:
+        mi = np.empty(mcap, np.int64)
+        ml = np.empty(mcap, np.int64)
+        mb = np.empty(mcap, np.int32)
+        ei = np.empty(ecap, np.uint32)
+        ej = np.empty(ecap, np.uint32)
+        ed = np.empty(ecap, np.uint8)
+        with ctx.lock:
+            st = lib.ke_scan_table_host(ctx.handle, _np_ptr(ph), _np_ptr(fid) if fid is not None else None,
+                                        _np_ptr(sz) if sz is not None else None, n, int(threshold), int(band_bits),
+                                        int(band_count), float(size_ratio) if size_ratio else 0.0,
+                                        int(pair_cap) if pair_cap else 0, _np_ptr(mi), _np_ptr(ml), _np_ptr(mb), mcap,
+                                        _np_ptr(ei) if ecap else None, _np_ptr(ej) if ecap else None,
+                                        _np_ptr(ed) if ecap else None, ecap, C.byref(stats))
+        if st == nat.KE_E_CAPACITY:
+            mcap = max(mcap, int(stats.members))
+            if want_edges:
+                ecap = max(ecap, int(stats.edges))
+            continue
+        nat.check(st, "ke_scan_table_host")
+        break
+    m = int(stats.members)
+    mi, ml, mb = mi[:m], ml[:m], mb[:m]
+    cuts = np.flatnonzero(np.diff(ml)) + 1 if m else np.zeros(0, np.int64)
+    offsets = np.concatenate([[0], cuts, [m]]).astype(np.int64) if m else np.zeros(1, np.int64)
+    out = {"index": mi, "label": ml, "best": mb, "offsets": offsets, "stats": stats.as_dict()}
+    if want_edges:
+        e = int(stats.edges)
+        out["edges"] = (ei[:e], ej[:e], ed[:e])
+    return out
 
 
 def popc_rate(iters: int = 4096, device: int | None = None):

@@ -6,13 +6,12 @@ Per rank (one process per GPU):
     --  all_gather of the hash shards (NCCL; the only exchange the path needs)
     K2  joins its share of the triangle's tiles over the full table
     --  candidate lists gathered to rank 0 on the host, pair list broadcast back
-    K3  verifies the pairs whose first image it owns (images of the rare cross-shard pairs are
-        sent peer to peer)
+    K3  verifies its pairs: same-shard pairs from its own bank; a cross-shard pair is scored by one of the two owners
+        (by the parity of i + j), the other image arriving as a luma plane in ONE packed all_to_all per step
     --  rank 0 unions the accepted pairs into clusters (host, a few thousand pairs)
 """
 from __future__ import annotations
 
-import os
 import time
 from dataclasses import dataclass, field
 
@@ -93,8 +92,55 @@ class Timer:
         return out
 
 
+def verify_pairs(bank, ci, cj, offsets, *, ssim_batch=None, luma_planes=None, on_local_done=None):
+    """SSIM of the candidate pairs (global table rows ``ci[k] < cj[k]``, the same list on every rank) over image shards:
+    rank r holds the images of rows ``offsets[r] .. offsets[r+1]`` in ``bank``.  Returns (float64 scores for ALL pairs on
+    every rank, counters).
+
+    Same-shard pairs are scored from the rank's own bank.  A cross-shard pair is scored by one of its two owners
+    (``dist.plan_cross_pairs``); the other image travels as a luma plane — a third of the RGB bytes, and SSIM of the
+    planes equals SSIM of the RGB images because the luma is the same fixed-point conversion — in ONE packed
+    ``all_to_all`` per call.  Every rank derives the whole plan from the global candidate list, so no metadata is
+    exchanged.  ``ssim_batch`` / ``luma_planes`` default to the CUDA kernels (the gloo tests inject CPU stand-ins)."""
+    torch = _torch()
+    ssim_batch = ssim_batch or ops.ssim_batch
+    luma_planes = luma_planes or ops.luma_planes
+    rank, size = kdist.world()
+    dev = bank.device
+    h, w = int(bank.shape[1]), int(bank.shape[2])
+    plan = kdist.plan_cross_pairs(ci, cj, offsets, rank, size)
+    my_lo = int(offsets[rank])
+    mine, cross = plan["local"], plan["cross"]
+    scores = torch.zeros(len(ci), dtype=torch.float64, device=dev)
+    if len(mine):
+        scores[torch.from_numpy(mine).to(dev)] = ssim_batch(bank, ci[mine] - my_lo, cj[mine] - my_lo)
+    if on_local_done:
+        on_local_done()
+    n_sent = n_recv = 0
+    if size > 1:
+        send_rows = np.concatenate(plan["send"])
+        recv_rows = np.concatenate(plan["recv"])  # per-source sorted runs in source order = globally sorted
+        n_sent, n_recv = len(send_rows), len(recv_rows)
+        planes = luma_planes(bank, send_rows - my_lo).reshape(len(send_rows), h * w)
+        got = kdist.exchange_rows(planes, [len(x) for x in plan["send"]], [len(x) for x in plan["recv"]])
+        if len(cross):
+            # my end of each cross pair: luma planes of my own images, appended behind the received ones
+            i_mine = plan["own_i"][cross] == rank
+            own_rows = np.where(i_mine, ci[cross], cj[cross])
+            far_rows = np.where(i_mine, cj[cross], ci[cross])
+            own_uni, own_pos = np.unique(own_rows, return_inverse=True)
+            far_pos = np.searchsorted(recv_rows, far_rows)
+            tmp = torch.cat([got, luma_planes(bank, own_uni - my_lo).reshape(len(own_uni), h * w)]).view(-1, h, w)
+            a_idx = np.where(i_mine, len(recv_rows) + own_pos, far_pos)
+            b_idx = np.where(i_mine, far_pos, len(recv_rows) + own_pos)
+            scores[torch.from_numpy(cross).to(dev)] = ssim_batch(tmp, a_idx, b_idx)
+        kdist._dist().all_reduce(scores)  # every pair was scored by exactly one rank: SUM merges
+    return scores, {"ssim_pairs_local": int(len(mine)), "ssim_pairs_cross": int(len(cross)), "planes_sent": int(n_sent),
+                    "planes_received": int(n_recv), "plane_bytes_sent": int(n_sent) * h * w}
+
+
 def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 0.9, require_band: bool = True,
-         chunk_images: int = 2048, n_local: int | None = None) -> ScanOutput:
+         chunk_images: int = 2048) -> ScanOutput:
     """Run the duplicate scan over this rank's shard.
 
     bank: CUDA uint8 [n,h,w,c] holding (or receiving) the rank's decoded images.
@@ -136,7 +182,8 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
     out.phash, out.dhash = ph, dh
 
     # ---- exchange + K2 ----------------------------------------------------------------------
-    table = kdist.all_gather_hashes(ph)
+    table, shard_counts = kdist.all_gather_hashes(ph, return_counts=True)
+    offsets = np.concatenate([[0], np.cumsum(shard_counts)]).astype(np.int64)
     tm.mark("exchange")
     total = table.numel()
     li, lj, ld = ops.hamming_join_device(table, threshold, require_band=require_band, part_index=rank,
@@ -154,47 +201,12 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
     out.counts.update(images_local=int(n), images_total=int(total), candidates=int(len(ci)))
 
     # ---- K3 ---------------------------------------------------------------------------------
-    n_loc = int(n_local if n_local is not None else n)
-    own_i = ci // n_loc
-    own_j = cj // n_loc
-    mine = np.flatnonzero((own_i == rank) & (own_j == rank))
-    scores_dev = torch.zeros(len(ci), dtype=torch.float64, device=dev)
     tm.mark("pre_ssim")
-    if len(mine):
-        s = ops.ssim_batch(bank, ci[mine] - rank * n_loc, cj[mine] - rank * n_loc)
-        scores_dev[torch.from_numpy(mine).to(dev)] = s
-    tm.mark("ssim")
-    cross = np.flatnonzero(own_i != own_j)
-    if size > 1 and len(cross):
-        # the rare cross-shard pairs: rank a (owner of i) scores the pair, rank b ships image j; all transfers are posted
-        # before the first wait
-        dist = kdist._dist()
-        tmp = torch.empty((2 * len(cross), h, w, c), dtype=torch.uint8, device=dev)
-        p2p, sel = [], []
-        for k, q in enumerate(cross.tolist()):
-            a, b = int(own_i[q]), int(own_j[q])
-            if rank == a:
-                tmp[2 * k].copy_(bank[int(ci[q]) - a * n_loc])
-                p2p.append(dist.P2POp(dist.irecv, tmp[2 * k + 1], b))
-                sel.append(k)
-            elif rank == b:
-                p2p.append(dist.P2POp(dist.isend, bank[int(cj[q]) - b * n_loc].contiguous(), a))
-        # plain isend/irecv: batch_isend_irecv measured ~10 ms slower per step here (2 x B200, NCCL 2.28: the grouped
-        # point-to-point launch stalls the step's next collective)
-        if p2p and os.environ.get("KE_P2P_BATCHED"):  # tuning probe
-            for req in dist.batch_isend_irecv(p2p):
-                req.wait()
-        else:
-            for req in [op.op(op.tensor, op.peer) for op in p2p]:
-                req.wait()
-        if sel:
-            s = ops.ssim_batch(tmp, [2 * k for k in sel], [2 * k + 1 for k in sel])
-            scores_dev[torch.from_numpy(cross[sel]).to(dev)] = s
-    if size > 1:
-        kdist._dist().all_reduce(scores_dev)  # every pair was scored by exactly one rank: SUM merges
+    scores_dev, k3 = verify_pairs(bank, ci, cj, offsets, on_local_done=lambda: tm.mark("ssim"))
     scores = scores_dev.cpu().numpy()
     out.bytes_d2h += 8 * len(ci)
     tm.mark("post")
+    out.counts.update(k3)
 
     # ---- host assembly (rank 0) ---------------------------------------------------------------
     if rank == 0:
@@ -211,5 +223,4 @@ def scan(bank, *, host_images=None, threshold: int = 8, ssim_threshold: float = 
         out.bytes_d2h += 16 * n
     torch.cuda.synchronize(dev)
     out.stage_ms.update(tm.result())
-    out.counts["ssim_pairs_local"] = int(len(mine))
     return out

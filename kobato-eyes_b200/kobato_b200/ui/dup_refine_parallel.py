@@ -36,7 +36,8 @@ from ..sig.phash import _decoded_array
 
 log = logging.getLogger("ui.dup_refine")
 
-_GPU_WINDOW = 512  # decoded images resident on the host between GPU launches
+_GPU_WINDOW = 512  # at most this many decoded images resident on the host between GPU launches ...
+_GPU_WINDOW_BYTES = int(os.environ.get("KE_REFINE_WINDOW_MB", "512")) << 20  # ... and at most this many bytes of them
 
 
 def _rebuild_cluster_like(cluster, files):
@@ -66,20 +67,44 @@ def _open_decoded(path) -> np.ndarray:
         return _decoded_array(ImageOps.exif_transpose(opened))
 
 
-def _resize_groups(arrays: Sequence[np.ndarray], size: int):
-    """[decoded arrays of any geometry] -> CUDA uint8 [n, size, size] planes (input order)."""
+def _resize_groups(arrays: Sequence[np.ndarray], size: int, failed: dict | None = None):
+    """[decoded arrays of any geometry] -> CUDA uint8 [n, size, size] planes (input order).
+
+    A geometry group whose launch fails is retried image by image; with ``failed`` given, the images that still fail are
+    recorded there as ``{position: "<ExcType>: <message>"}`` (their planes stay zero) instead of raising — the reference
+    counts a failing file and carries on (src/ui/dup_refine_parallel.py:150-163)."""
     import torch
 
     out = None
     groups: dict[tuple, list[int]] = {}
     for k, a in enumerate(arrays):
         groups.setdefault(a.shape, []).append(k)
-    for members in groups.values():
-        planes = ops.gray_resize_batch(np.stack([arrays[k] for k in members]), size, size, "bilinear")
+
+    def place(members, planes):
+        nonlocal out
         if out is None:
-            out = torch.empty((len(arrays), size, size), dtype=torch.uint8, device=planes.device)
+            out = torch.zeros((len(arrays), size, size), dtype=torch.uint8, device=planes.device)
         out[torch.as_tensor(members, device=planes.device)] = planes
+
+    for members in groups.values():
+        try:
+            place(members, ops.gray_resize_batch(np.stack([arrays[k] for k in members]), size, size, "bilinear"))
+        except Exception:
+            if failed is None:
+                raise
+            for k in members:
+                try:
+                    place([k], ops.gray_resize_batch(arrays[k][None], size, size, "bilinear"))
+                except Exception as exc:
+                    failed[k] = f"{type(exc).__name__}: {exc}"
     return out
+
+
+def _windows(paths: Sequence):
+    """Slices of ``paths`` for one decode + GPU round: at most _GPU_WINDOW files each (the byte bound is applied while
+    decoding, see _decode_window)."""
+    for lo in range(0, len(paths), _GPU_WINDOW):
+        yield paths[lo:lo + _GPU_WINDOW]
 
 
 def tile_ahash_bits_many(arrays: Sequence[np.ndarray], grid: int = 4, tile: int = 8):
@@ -96,24 +121,40 @@ def tile_hamming(a_bits: int, b_bits: int) -> int:
     return (a_bits ^ b_bits).bit_count()
 
 
-def _decode_all(paths, workers, is_cancelled, on_done):
+def _decode_all(paths, workers, is_cancelled, on_done, flush=None):
     """Decode `paths` with a thread pool -> ({path: array}, {path: "<ExcType>: <message>"} in completion order),
-    or None when cancelled.  `on_done()` is called once per finished file (progress)."""
+    or None when cancelled.  `on_done()` is called once per finished file (progress).
+
+    Host memory is bounded by BYTES, not by count (multi-megapixel photographs are ~50 MB each decoded): files are
+    submitted a few per worker at a time and, with ``flush`` given, ``flush(decoded)`` is called — and the arrays
+    dropped — whenever more than _GPU_WINDOW_BYTES of decoded pixels are resident."""
     decoded: dict[Any, np.ndarray] = {}
     errors: dict[Any, str] = {}
+    held = 0
+    step = max(1, workers) * 2
     with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
-        futs = {ex.submit(_open_decoded, p): p for p in paths}
-        for f in as_completed(futs):
-            if is_cancelled and is_cancelled():
-                for ff in futs:
-                    ff.cancel()
-                return None
-            p = futs[f]
-            try:
-                decoded[p] = f.result()
-            except Exception as exc:
-                errors[p] = f"{type(exc).__name__}: {exc}"
-            on_done()
+        for lo in range(0, len(paths), step):
+            futs = {ex.submit(_open_decoded, p): p for p in paths[lo:lo + step]}
+            for f in as_completed(futs):
+                if is_cancelled and is_cancelled():
+                    for ff in futs:
+                        ff.cancel()
+                    return None
+                p = futs[f]
+                try:
+                    decoded[p] = f.result()
+                    held += decoded[p].nbytes
+                except Exception as exc:
+                    errors[p] = f"{type(exc).__name__}: {exc}"
+                on_done()
+            if flush is not None and held > _GPU_WINDOW_BYTES:
+                flush(decoded)
+                decoded = {}
+                held = 0
+    if flush is not None:
+        if decoded:
+            flush(decoded)
+        return {}, errors
     return decoded, errors
 
 
@@ -141,20 +182,34 @@ def refine_by_tilehash_parallel(clusters, grid: int = 4, tile: int = 8, max_bits
     chunks = []
     fail_counts: Counter = Counter()
     fail_samples: dict = {}
-    for lo in range(0, total1, _GPU_WINDOW):
-        res = _decode_all(uniq_paths[lo:lo + _GPU_WINDOW], io_workers, is_cancelled, _on_done)
+    def _sign(decoded):  # one GPU round over the decoded files of a window (path order kept)
+        ok = [p for p in decoded_order if p in decoded]
+        if not ok:
+            return
+        failed: dict[int, str] = {}
+        planes = _resize_groups([decoded[p] for p in ok], grid * tile, failed)
+        for k, key in failed.items():  # a GPU-stage failure is a skipped file, like a decode failure
+            fail_counts[key] += 1
+            fail_samples.setdefault(key, ok[k])
+        good = [k for k in range(len(ok)) if k not in failed]
+        if not good:
+            return
+        import torch
+
+        bits = ops.tile_ahash_bits(planes[torch.as_tensor(good, device=planes.device)], grid, tile)
+        base = sum(c.shape[0] for c in chunks)
+        chunks.append(bits)
+        for row, k in enumerate(good):
+            row_of[ok[k]] = base + row
+
+    for window in _windows(uniq_paths):
+        decoded_order = window
+        res = _decode_all(window, io_workers, is_cancelled, _on_done, flush=_sign)
         if res is None:
             return []
-        decoded, errs = res
-        for path, key in errs.items():
+        for path, key in res[1].items():
             fail_counts[key] += 1
             fail_samples.setdefault(key, path)
-        ok = [p for p in uniq_paths[lo:lo + _GPU_WINDOW] if p in decoded]
-        if ok:
-            base = sum(c.shape[0] for c in chunks)
-            chunks.append(tile_ahash_bits_many([decoded[p] for p in ok], grid, tile))
-            for k, p in enumerate(ok):
-                row_of[p] = base + k
     if fail_counts:
         log.warning("TileHash phase1 skipped %d file(s) due to errors: %s", sum(fail_counts.values()),
                     _format_failure_summary(fail_counts, fail_samples))
@@ -221,18 +276,30 @@ def refine_by_pixels_parallel(clusters, mae_thr: float = 0.006, thumb_size: int 
     row_of: dict[Any, int] = {}
     errors: dict[Any, str] = {}
     chunks = []
-    for lo in range(0, len(paths), _GPU_WINDOW):
-        res = _decode_all(paths[lo:lo + _GPU_WINDOW], worker_count, is_cancelled, lambda: None)
+    def _thumb(decoded):  # one GPU round over the decoded files of a window (path order kept)
+        ok = [p for p in decoded_order if p in decoded]
+        if not ok:
+            return
+        failed: dict[int, str] = {}
+        planes = _resize_groups([decoded[p] for p in ok], thumb_size, failed)
+        for k, key in failed.items():  # a GPU-stage failure counts like a load failure of that file
+            errors[ok[k]] = key
+        good = [k for k in range(len(ok)) if k not in failed]
+        if not good:
+            return
+        import torch
+
+        base = sum(c.shape[0] for c in chunks)
+        chunks.append(planes[torch.as_tensor(good, device=planes.device)])
+        for row, k in enumerate(good):
+            row_of[ok[k]] = base + row
+
+    for window in _windows(paths):
+        decoded_order = window
+        res = _decode_all(window, worker_count, is_cancelled, lambda: None, flush=_thumb)
         if res is None:
             return []
-        decoded, errs = res
-        errors.update(errs)
-        ok = [p for p in paths[lo:lo + _GPU_WINDOW] if p in decoded]
-        if ok:
-            base = sum(c.shape[0] for c in chunks)
-            chunks.append(_resize_groups([decoded[p] for p in ok], thumb_size))
-            for k, p in enumerate(ok):
-                row_of[p] = base + k
+        errors.update(res[1])
 
     keeper_failure_counts: Counter = Counter()
     keeper_failure_samples: dict = {}

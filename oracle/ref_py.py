@@ -165,6 +165,47 @@ def scan_edges(files: Sequence[FileRec], *, hamming_threshold: int = 8, size_rat
     return edges
 
 
+def scan_table(phash, file_id=None, size=None, *, threshold: int = 8, band_bits: int = 16, band_count: int = 4,
+               size_ratio: float | None = None, pair_cap: int | None = None) -> dict:
+    """What ke_scan_table_host returns, restated on ``scan_edges`` (src/dup/scanner.py:227-318) for DISTINCT file ids:
+    members (rows with an edge) grouped by connected component, label = smallest row, best = min edge distance."""
+    ph = np.asarray(phash).reshape(-1)
+    ph = ph.view(np.uint64) if ph.dtype == np.int64 else ph.astype(np.uint64)
+    n = len(ph)
+    ids = np.arange(n, dtype=np.int64) if file_id is None else np.asarray(file_id, np.int64)
+    sizes = np.zeros(n, np.int64) if size is None else np.asarray(size, np.int64)
+    files = [FileRec(file_id=int(k), path=f"{k}.jpg", size=int(sizes[k]), width=None, height=None, phash=int(ph[k]))
+             for k in range(n)]  # rows stand in for ids so that equal ids can be told apart below
+    row_edges = scan_edges(files, hamming_threshold=threshold, size_ratio=size_ratio, band_bits=band_bits,
+                           band_count=band_count, bucket_pair_cap=pair_cap)
+    row_edges = {k: d for k, d in row_edges.items() if ids[k[0]] != ids[k[1]]}
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    best = {}
+    for (i, j), d in row_edges.items():
+        ri, rj = find(i), find(j)
+        if ri != rj:
+            parent[max(ri, rj)] = min(ri, rj)
+        for r in (i, j):
+            best[r] = min(best.get(r, 255), d)
+    members = sorted(best, key=lambda r: (find(r), r))
+    index = np.array(members, np.int64)
+    label = np.array([find(r) for r in members], np.int64)
+    cuts = np.flatnonzero(np.diff(label)) + 1 if len(label) else np.zeros(0, np.int64)
+    offsets = np.concatenate([[0], cuts, [len(label)]]).astype(np.int64) if len(label) else np.zeros(1, np.int64)
+    ei = np.array(sorted(row_edges), np.int64).reshape(-1, 2)
+    return {"index": index, "label": label, "best": np.array([best[r] for r in members], np.int32), "offsets": offsets,
+            "edges": (ei[:, 0].astype(np.uint32), ei[:, 1].astype(np.uint32),
+                      np.array([row_edges[tuple(k)] for k in ei.tolist()], np.uint8)),
+            "stats": {"edges": len(row_edges), "members": len(members), "clusters": max(0, len(offsets) - 1)}}
+
+
 def _ext_priority(path: str) -> int:
     return EXT_PRIORITY.get(PurePath(path).suffix.lower().lstrip("."), 0)
 
@@ -254,6 +295,44 @@ def structural_similarity(im1, im2, *, data_range: float = 1.0, win_size: int = 
     pad = (win_size - 1) // 2
     core = s[tuple(slice(pad, n - pad) for n in s.shape)]
     return float(core.mean(dtype=np.float64))
+
+
+def structural_similarity_gaussian(im1, im2, *, data_range: float = 1.0) -> float:
+    """scikit-image 0.25.2 ``structural_similarity(..., gaussian_weights=True)``: sigma 1.5, truncate 3.5 (11 taps,
+    win_size 11 -> crop 5, cov_norm 121/120), ``skimage.filters.gaussian`` = ``scipy.ndimage.gaussian_filter`` with
+    mode 'reflect' on the float32 images.  NOT the reference's path (src/dup/refine.py:52 keeps the uniform window);
+    restated for the optional ``gaussian`` flag of ke_ssim_batch."""
+    from scipy.ndimage import gaussian_filter
+
+    a = np.asarray(im1, dtype=np.float32)
+    b = np.asarray(im2, dtype=np.float32)
+    if a.shape != b.shape:
+        raise ValueError("Input images must have the same dimensions.")
+    sigma, truncate = 1.5, 3.5
+    win_size = 2 * int(truncate * sigma + 0.5) + 1
+    if any(s < win_size for s in a.shape):
+        raise ValueError("win_size exceeds image extent.")
+
+    def filt(x):
+        return gaussian_filter(x, sigma=sigma, truncate=truncate, mode="reflect")
+
+    npx = win_size ** a.ndim
+    cov_norm = npx / (npx - 1)
+    ux, uy = filt(a), filt(b)
+    uxx, uyy, uxy = filt(a * a), filt(b * b), filt(a * b)
+    vx = cov_norm * (uxx - ux * ux)
+    vy = cov_norm * (uyy - uy * uy)
+    vxy = cov_norm * (uxy - ux * uy)
+    c1 = (0.01 * data_range) ** 2
+    c2 = (0.03 * data_range) ** 2
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux**2 + uy**2 + c1) * (vx + vy + c2))
+    pad = (win_size - 1) // 2
+    core = s[tuple(slice(pad, n - pad) for n in s.shape)]
+    return float(core.mean(dtype=np.float64))
+
+
+def ssim_gaussian_of_planes(pa: np.ndarray, pb: np.ndarray) -> float:
+    return structural_similarity_gaussian(pa.astype(np.float32) / 255.0, pb.astype(np.float32) / 255.0)
 
 
 def ssim_planes(img_a, img_b):

@@ -340,7 +340,7 @@ def test_ssim_scale_properties_at_bench_size():
 
 def test_ssim_both_kernels_agree_with_the_oracle():
     """K3 has two kernels (v1: one output column per thread; v2: four, packed FP32); either may serve any shape."""
-    import os
+    from kobato_b200 import _native as nat
 
     torch = _torch()
     for (h, w, c) in ((256, 256, 1), (64, 80, 1), (7, 7, 1), (300, 520, 1), (96, 128, 3), (512, 512, 3), (40, 271, 4), (33, 1030, 1)):
@@ -349,12 +349,13 @@ def test_ssim_both_kernels_agree_with_the_oracle():
         bank = torch.from_numpy(imgs).cuda()
         ia, ib = list(range(0, n, 2)) + [0], list(range(1, n, 2)) + [0]
         got = {}
+        ctx = nat.context(torch.cuda.current_device())
         for kernel in ("v1", "v2"):
-            os.environ["KE_SSIM_KERNEL"] = kernel
+            ctx.set_option(nat.KE_OPT_SSIM_V1, 1 if kernel == "v1" else 0)
             try:
                 got[kernel] = ops.ssim_batch(bank, ia, ib).cpu().numpy()
             finally:
-                os.environ.pop("KE_SSIM_KERNEL", None)
+                ctx.set_option(nat.KE_OPT_SSIM_V1, 0)
         assert np.abs(got["v1"] - got["v2"]).max() <= 2e-6, (h, w, c)
         for k, (i, j) in enumerate(zip(ia, ib)):
             want = ref_py.ssim_of_planes(oracle.to_l(imgs[i]), oracle.to_l(imgs[j]))
@@ -380,12 +381,12 @@ def test_phash_fast_and_generic_kernels_agree():
             gen = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
         finally:
             ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
-        for kernel in ("v5", "v4", "fast"):  # the library falls back by itself  # the library falls back by itself when a kernel does not take the shape
-            os.environ["KE_PHASH_KERNEL"] = kernel
+        for kernel in (0, 1, 2):  # start of the kernel ladder: v5, v4, fast; the library falls back by itself when a kernel does not take the shape
+            ctx.set_option(nat.KE_OPT_PHASH_LADDER, kernel)
             try:
                 got = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
             finally:
-                os.environ.pop("KE_PHASH_KERNEL", None)
+                ctx.set_option(nat.KE_OPT_PHASH_LADDER, 0)
             assert torch.equal(got[0], gen[0]) and torch.equal(got[1], gen[1]) and torch.equal(got[2], gen[2]), kernel
             assert torch.equal(got[3][0], gen[3][0]) and torch.equal(got[3][1], gen[3][1]), kernel
 
@@ -476,9 +477,9 @@ def test_streaming_kernels_random_batches_match_the_generic_kernels():
         assert torch.equal(got[2][0], ref[2][0]) and torch.equal(got[2][1], ref[2][1]), (it, h, w, c, n)
         side = (32, 64, 128)[it % 3]
         fast = ops.gray_resize_batch(imgs, side, side, "bilinear")
-        os.environ["KE_RESIZE_GENERIC"] = "1"
+        ctx.set_option(nat.KE_OPT_RESIZE_GENERIC, 1)
         try:
             slow = ops.gray_resize_batch(imgs, side, side, "bilinear")
         finally:
-            os.environ.pop("KE_RESIZE_GENERIC", None)
+            ctx.set_option(nat.KE_OPT_RESIZE_GENERIC, 0)
         assert torch.equal(fast, slow), (it, h, w, c, n, side)

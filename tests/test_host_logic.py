@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "kobato_b200.h").read_text()
     declared = set(re.findall(r"\b(ke_[a-z0-9_]+)\s*\(", header))
     lib = nat.load()
-    assert lib.ke_abi_version() == 1
+    assert lib.ke_abi_version() == nat.KE_ABI_VERSION == 2
     assert declared == set(nat.EXPORTS), declared ^ set(nat.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
@@ -228,6 +228,57 @@ def test_scanner_dropin_matches_reference_golden_clusters(golden_scanner, monkey
         got = [{"keeper": c.keeper_id, "members": [[e.file.file_id, e.best_hamming] for e in c.files]}
                for c in scanner.build_clusters(files)]
         assert normalise_clusters(got) == normalise_clusters(case["clusters"]), case["name"]
+
+
+def _oracle_scan_table(hashes, ids, sizes, **kw):
+    """Injected in place of ops.scan_table (ke_scan_table_host): the oracle's restatement of it."""
+    return ref_py.scan_table(hashes, ids, sizes, **kw)
+
+
+def test_scanner_table_path_matches_reference_golden_clusters(golden_scanner, monkeypatch):
+    """The table path (N3: columns -> members grouped by component -> cluster objects for the members only) against the
+    live reference's golden clusters; cases with repeated file ids must route themselves to the legacy path."""
+    table_cases = 0
+    for case in golden_scanner["cases"]:
+        if "pair_cap" in case:
+            monkeypatch.setenv("KE_DUP_BUCKET_PAIR_CAP", str(case["pair_cap"]))
+        else:
+            monkeypatch.delenv("KE_DUP_BUCKET_PAIR_CAP", raising=False)
+        recs = _golden_files(case)
+        files = [kscanner.DuplicateFile(file_id=f["file_id"], path=Path(f["path"]), size=f["size"], width=f["width"],
+                                        height=f["height"], phash=f["phash"]) for f in recs]
+        calls = []
+
+        def scan(*a, **kw):
+            calls.append(1)
+            return _oracle_scan_table(*a, **kw)
+
+        distinct = len({f.file_id for f in files}) == len(files)
+        scanner = kscanner.DuplicateScanner(kscanner.DuplicateScanConfig(**case["cfg"]), scan_table=scan,
+                                            join=None if distinct else _oracle_join)
+        got = [{"keeper": c.keeper_id, "members": [[e.file.file_id, e.best_hamming] for e in c.files]}
+               for c in scanner.build_clusters(files)]
+        assert normalise_clusters(got) == normalise_clusters(case["clusters"]), case["name"]
+        assert bool(calls) == distinct, case["name"]
+        table_cases += distinct
+        if distinct:  # the same through the column entry point: no DuplicateFile exists before a row is a member
+            made = []
+
+            def make_file(row):
+                made.append(row)
+                return files[row]
+
+            ids = np.array([f.file_id for f in files], np.int64)
+            ph = np.array([f.phash for f in files], np.uint64).view(np.int64)  # what SQLite stores
+            sz = np.array([f.size or 0 for f in files], np.int64)
+            cols = scanner.build_clusters_from_columns(ids, ph, sz, make_file=make_file)
+            got2 = [{"keeper": c.keeper_id, "members": [[e.file.file_id, e.best_hamming] for e in c.files]} for c in cols]
+            assert normalise_clusters(got2) == normalise_clusters(case["clusters"]), case["name"]
+            assert len(made) == sum(len(c["members"]) for c in case["clusters"])
+    assert table_cases >= 5
+    with pytest.raises(ValueError):
+        kscanner.DuplicateScanner(kscanner.DuplicateScanConfig(), scan_table=_oracle_scan_table).build_clusters_from_columns(
+            np.array([1, 1]), np.array([5, 5]), None, make_file=lambda r: None)
 
 
 def test_scanner_reference_unit_cases():

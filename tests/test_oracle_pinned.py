@@ -185,6 +185,72 @@ def test_ssim_restatements_agree_and_match_golden(golden_ssim):
         assert abs(cex - py) < 1e-5, (case, cex, py)  # exact arithmetic stays inside the parity bar
 
 
+def test_ssim_restatement_is_pinned_by_an_independent_oracle_and_closed_forms(golden_ssim):
+    """scikit-image itself is not installable here, so the restatement (ref_py, on scipy's uniform_filter) and the C
+    oracle are pinned by things they did not generate: a float64 49-tap evaluation of the published definition that
+    shares no code with them (oracle/ssim_independent.py), and closed forms that need no filter at all."""
+    from oracle import ssim_independent as ind
+
+    def all_three(a, b):
+        return ref_py.ssim_of_planes(a, b), oracle.ssim_u8(a, b), oracle.ssim_u8(a, b, exact=True)
+
+    # (1) brute force on the golden pairs (incl. the C4 shape 256x256 and the edge shapes 7x7, 8x31, 100x37)
+    for case in golden_ssim["cases"]:
+        if "h" not in case:
+            continue
+        a, b = _ssim_pair(case["case"], case["h"], case["w"])
+        want = ind.mssim_bruteforce(a, b)
+        for got in all_three(a, b):
+            assert abs(got - want) <= 1e-5, (case, got, want)
+        assert abs(case["ssim"] - want) <= 1e-5  # the committed golden value too
+    # (2) constant vs constant: S = (2ab + C1) / (a^2 + b^2 + C1) everywhere, variances exactly 0
+    for la, lb, shape in ((0, 0, (7, 7)), (255, 255, (9, 13)), (200, 10, (64, 64)), (17, 18, (31, 8)), (0, 255, (16, 16)),
+                          (128, 128, (256, 256))):
+        a = np.full(shape, la, np.uint8)
+        b = np.full(shape, lb, np.uint8)
+        want = ind.closed_form_constants(la, lb)
+        for got in all_three(a, b) + (ind.mssim_bruteforce(a, b),):
+            assert abs(got - want) <= 1e-6, (la, lb, got, want)
+    # (3) identical images: exactly the definition's 1
+    rng = np.random.default_rng(3)
+    for shape in ((7, 7), (40, 23), (256, 256)):
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        for got in all_three(a, a) + (ind.mssim_bruteforce(a, a),):
+            assert abs(got - 1.0) <= 1e-6
+    # (4) inverted two-level checkerboard: mu_b = 1 - mu_a, var_a = var_b = (p - q)^2 * 25/98, cov = -var
+    for (h, w, p, q) in ((16, 16, 200, 50), (31, 8, 255, 0), (64, 40, 130, 120), (7, 7, 10, 240)):
+        a = ind.checkerboard(h, w, p, q)
+        b = (255 - a.astype(np.int32)).astype(np.uint8)
+        want = ind.closed_form_inverted_checkerboard(h, w, p, q)
+        assert abs(ind.mssim_bruteforce(a, b) - want) <= 1e-12
+        for got in all_three(a, b):
+            assert abs(got - want) <= 1e-5, (h, w, p, q, got, want)
+    # (5) the reference's own behavioural values (tests/dup/test_refine.py:24-46) from the independent oracle
+    from PIL import Image, ImageEnhance
+
+    base = Image.new("RGB", (64, 64), color=(200, 10, 10))
+    pa, pb = ref_py.ssim_planes(base, ImageEnhance.Brightness(base).enhance(1.02))
+    assert ind.mssim_bruteforce(pa, pb) > 0.95
+    pa, pb = ref_py.ssim_planes(Image.new("RGB", (64, 64), (0, 255, 0)), Image.new("RGB", (64, 64), (0, 0, 255)))
+    assert ind.mssim_bruteforce(pa, pb) < 0.95
+
+
+def test_gaussian_window_restatement_sanity():
+    """The optional Gaussian window (skimage gaussian_weights=True; NOT the reference's path): definitional checks of
+    the restatement the CUDA flag is compared with."""
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 256, (40, 33), dtype=np.uint8)
+    assert abs(ref_py.ssim_gaussian_of_planes(a, a) - 1.0) <= 1e-6
+    c, d = np.full((16, 20), 200, np.uint8), np.full((16, 20), 10, np.uint8)
+    want = (2 * (200 / 255) * (10 / 255) + 1e-4) / ((200 / 255) ** 2 + (10 / 255) ** 2 + 1e-4)
+    assert abs(ref_py.ssim_gaussian_of_planes(c, d) - want) <= 1e-6
+    with pytest.raises(ValueError):
+        ref_py.ssim_gaussian_of_planes(a[:10, :10], a[:10, :10])
+    b = np.clip(a.astype(np.int32) + rng.integers(-6, 7, a.shape), 0, 255).astype(np.uint8)
+    g, u = ref_py.ssim_gaussian_of_planes(a, b), ref_py.ssim_of_planes(a, b)
+    assert 0.0 < g < 1.0 and 0.0 < u < 1.0 and abs(g - u) < 0.2
+
+
 def test_ssim_reference_behavioural_pins():
     """tests/dup/test_refine.py:24-46 of the reference, through the restatement."""
     from PIL import Image, ImageEnhance

@@ -28,11 +28,11 @@ for it in range(rounds):
     ok = torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and torch.equal(got[2][0], ref[2][0]) and torch.equal(got[2][1], ref[2][1])
     side = (32, 64, 128)[it % 3]
     a = ops.gray_resize_batch(imgs, side, side, "bilinear")
-    os.environ["KE_RESIZE_GENERIC"] = "1"
+    ctx.set_option(nat.KE_OPT_RESIZE_GENERIC, 1)
     try:
         b = ops.gray_resize_batch(imgs, side, side, "bilinear")
     finally:
-        os.environ.pop("KE_RESIZE_GENERIC", None)
+        ctx.set_option(nat.KE_OPT_RESIZE_GENERIC, 0)
     ok2 = torch.equal(a, b)
     if not (ok and ok2):
         bad += 1
