@@ -35,6 +35,11 @@ METRIC = ("dup-scan images/s (pHash+dHash -> all-pairs Hamming T=8 -> SSIM verif
           "pHash images/s, Hamming pairs/s, SSIM pairs/s")
 H = W = 512
 C = 3
+# ncu figures of the K3 kernel bench.py times (see profiles/): fraction of cycles with an instruction issued per scheduler
+# and warp-instructions per output pixel.  Updated whenever the kernel changes.
+K3_ISSUE_FRAC = 0.789
+K3_INSTR_PER_OUTPUT = 43.6
+K3_ISSUE_SOURCE = "profiles/r1_ncu_k3v2_summary.txt"
 IMG_BYTES = H * W * C
 
 
@@ -164,8 +169,9 @@ def run_reference(args) -> dict:
     ssim_pairs = sum(s["ssim_pairs"] for s in stats)
     ssim_s = sum(s["ssim_s"] for s in stats)
     sample = (f"{args.ref_sample} images/step cycling {args.ref_unique} unique synthetic 512x512 RGB images "
-              f"(hash: process pool x{cores}; scan: single process over {stats[-1]['scan_files']} files; "
-              f"SSIM on <=256 candidate pairs, pool x{cores})")
+              f"(hash: process pool x{cores}; LSH scan: single process over {stats[-1]['scan_files']} hashes; SSIM on "
+              f"{stats[-1]['ssim_pairs']} pairs/step = the GPU step's 3589 candidates per 70000 images, pool x{cores}; "
+              f"{ssim_pairs} SSIM pairs timed in all)")
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
@@ -182,7 +188,7 @@ def run_reference(args) -> dict:
 
 def cpu_baseline_subprocess(args) -> dict | None:
     """Run the reference arm in a fresh process (no CUDA context is forked) on a bounded sample."""
-    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "10", "--warmup", "1",
            "--ref-sample", str(args.ref_sample), "--ref-unique", str(args.ref_unique)]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     try:
@@ -224,13 +230,17 @@ def run_cuda(args) -> dict:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- synthetic shard, generated on the GPU (each rank its own 70k-image set) -------------
+    # ---- synthetic shard, generated on the GPU ------------------------------------------------
+    # ONE global set of world x n images; rank r holds the images r, r + world, r + 2 world, ...  The planted
+    # near-duplicates (the last 5 % of the set) point at uniformly chosen earlier images, so (world-1)/world of the
+    # candidate pairs straddle two ranks and go through the cross-shard SSIM exchange.
     n = args.images
     bank = torch.empty((n, H, W, C), dtype=torch.uint8, device=dev)
-    seed = synth.SEED + 7919 * rank
+    seed = synth.SEED
     for lo in range(0, n, 8192):
         cnt = min(8192, n - lo)
-        ops.synth_images_device(lo, cnt, H, W, C, n_set=n, seed=seed, out=bank[lo:lo + cnt])
+        ops.synth_images_device(rank + lo * world, cnt, H, W, C, n_set=n * world, seed=seed, stride=world,
+                                out=bank[lo:lo + cnt])
     torch.cuda.synchronize(dev)
 
     # ---- device-resident steps (`value`) ------------------------------------------------------
@@ -264,6 +274,47 @@ def run_cuda(args) -> dict:
     value = world * n * args.steps / (ms_total * 1e-3)
     counts = out.counts
 
+    # ---- the scan just timed, checked against the CPU oracle (outside every timed region) -----------------------
+    # hashes of a few of this rank's images, the candidate list on three row stripes of the gathered table, and the SSIM of
+    # a dozen candidates — cross-shard ones first — each image regenerated on the CPU from the same counter-based generator
+    table_all = kdist.all_gather_hashes(out.phash).cpu().numpy().view(np.uint64)
+    scan_check = None
+    if rank == 0:
+        import oracle
+        from oracle import ref_py
+
+        oracle.build()
+
+        def cpu_image(row):  # table row -> (rank, local index) -> global image id of the interleaved set
+            r_, k_ = divmod(int(row), n)
+            return synth.synth_image(k_ * world + r_, H, W, C, n_set=n * world, seed=seed)
+
+        bad_hash = 0
+        for k_ in (0, 1, n // 2, n - 3, n - 2, n - 1):
+            want = oracle.signature(cpu_image(k_))
+            bad_hash += int(want[0] != int(table_all[k_])) + int(want[1] != int(out.dhash[k_].item()) & ((1 << 64) - 1))
+        nt = len(table_all)
+        cand_ok, in_stripes = True, 0
+        for lo_ in (0, nt // 2, nt - 384):
+            wi, wj, wd = oracle.hamming_join(table_all, 8, require_band=True, threads=os.cpu_count() or 1, row_begin=lo_,
+                                             row_end=lo_ + 384)
+            sel = (out.cand_i >= lo_) & (out.cand_i < lo_ + 384)
+            cand_ok = cand_ok and np.array_equal(out.cand_i[sel], wi) and np.array_equal(out.cand_j[sel], wj) and \
+                np.array_equal(out.cand_d[sel], wd)
+            in_stripes += len(wi)
+        cross_sel = np.flatnonzero(out.cand_i // n != out.cand_j // n)
+        same_sel = np.flatnonzero(out.cand_i // n == out.cand_j // n)
+        pick = np.concatenate([cross_sel[:: max(1, len(cross_sel) // 8)][:8], same_sel[:: max(1, len(same_sel) // 4)][:4]])
+        worst = 0.0
+        for q in pick.tolist():
+            want = ref_py.ssim_of_planes(oracle.to_l(cpu_image(out.cand_i[q])), oracle.to_l(cpu_image(out.cand_j[q])))
+            worst = max(worst, abs(float(out.ssim[q]) - want))
+        scan_check = {"hash_mismatches_in_6_images": bad_hash, "candidate_stripes_equal_oracle": bool(cand_ok),
+                      "candidates_in_stripes": int(in_stripes), "candidates_cross_shard": int(len(cross_sel)),
+                      "candidates": int(len(out.cand_i)), "ssim_pairs_checked": int(len(pick)),
+                      "ssim_cross_shard_pairs_checked": int(min(8, len(cross_sel))), "ssim_max_abs_err": worst,
+                      "ok": bool(bad_hash == 0 and cand_ok and worst <= 1e-5)}
+
     # ---- per-kernel timings (CUDA events around single launches, inputs >> L2 or L2-flushed) ---
     def timed(fn, reps=3):
         fn()  # one untimed launch: the first one after a different kernel runs ~10 % long (cold instruction / L2 state)
@@ -285,7 +336,8 @@ def run_cuda(args) -> dict:
                "frac": k1_gbs / hbm_peak,
                # dram read+write per launch: 787 156 B/image measured by `ncu --set full` on an 8192-image launch of
                # the same kernel (profiles/r1_ncu_k1v5_summary.txt), scaled to this launch's image count
-               "traffic": int(n * 787156), "peak_source": peak_src,
+               "traffic": int(n * 787156), "traffic_source": "ncu constant 787156 B/image x images (not measured in this run)",
+               "peak_source": peak_src,
                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                "images_per_s": n / (k1_ms * 1e-3)}
 
@@ -299,20 +351,12 @@ def run_cuda(args) -> dict:
     od = torch.empty(cap, dtype=torch.uint8, device=dev)
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)
 
-    def run_join():
-        nat.check(lib.ke_hamming_join(ctx.handle, hashes.data_ptr(), args.join_n, 8, 0, 16, 4, None, rank, world,
+    def run_join(threshold=8):
+        nat.check(lib.ke_hamming_join(ctx.handle, hashes.data_ptr(), args.join_n, threshold, 0, 16, 4, None, rank, world,
                                       oi.data_ptr(), oj.data_ptr(), od.data_ptr(), cap, cnt.data_ptr(),
                                       int(torch.cuda.current_stream(dev).cuda_stream)), "ke_hamming_join")
 
-    run_join()
-    barrier()
-    k2_ms_local = timed(run_join)
-    k2 = torch.tensor([k2_ms_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(k2, op=torch.distributed.ReduceOp.MAX)
-    k2_ms = float(k2.item())
     pairs_total = args.join_n * (args.join_n - 1) // 2
-    k2_rate = pairs_total / (k2_ms * 1e-3)
     # Integer rooflines at clocks.max.sm.  (a) POPC only: 2 POPC per pair on the measured POPC issue rate.
     # (b) combined XU+ALU bound of the hybrid kernel: POPC role = 2 POPC + 3.5 ALU ops per pair, bit-sliced
     # role = 6.25 ALU ops per pair (200 LOP3 per 32 pairs), ALU pipe = 64 lanes/clk/SM:
@@ -322,13 +366,75 @@ def run_cuda(args) -> dict:
     p_max = popc_rate / 2.0
     q_max = max(0.0, (64.0 - 3.5 * p_max) / 6.25)
     k2_peak = world * ctx.sm_count * (p_max + q_max) * clk
+    by_threshold = {}
+    for T in (4, 8, 12):  # config C3 names all three
+        run_join(T)
+        barrier()
+        t_local = timed(lambda: run_join(T))
+        tt = torch.tensor([t_local], dtype=torch.float64, device=dev)
+        hits = cnt.clone()
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            torch.distributed.all_reduce(hits)
+        rate = pairs_total / (float(tt.item()) * 1e-3)
+        by_threshold[str(T)] = {"ms": float(tt.item()), "pairs_per_s": rate, "frac": rate / k2_peak,
+                                "frac_of_popc_only_roofline": rate / popc_peak, "hits": int(hits.item())}
+    k2_ms, k2_rate = by_threshold["8"]["ms"], by_threshold["8"]["pairs_per_s"]
     roof_k2 = {"kernel": "ke_join_fused_kernel (POPC role + bit-sliced LOP3 role)", "bound": "int-alu (XU POPC pipe + ALU LOP3 pipe)",
                "achieved": k2_rate, "peak": k2_peak, "unit": "pairs/s", "frac": k2_rate / k2_peak,
                "popc_only_peak": popc_peak, "frac_of_popc_only_roofline": k2_rate / popc_peak,
-               "n_hashes": args.join_n, "threshold": 8, "hits": int(cnt.item()), "ms": k2_ms,
+               "n_hashes": args.join_n, "threshold": 8, "hits": by_threshold["8"]["hits"], "ms": k2_ms,
+               "by_threshold": by_threshold,
                "popc_per_clk_per_sm_measured": popc_rate, "sm_clock_mhz_in_microbench": popc_mhz,
                "peak_source": "LP over measured POPC issue rate (XU) and 64 ALU lanes/clk/SM at clocks.max.sm; "
                               "popc_only_peak = sm_count x POPC rate x clock / 2"}
+
+    # Config C5: 10 M hashes (5e13 pairs), T=8, tiles dealt over the ranks, candidates compacted per rank and gathered;
+    # a few row stripes of the result are checked against the CPU oracle OUTSIDE the timed launch.
+    roof_c5 = None
+    if args.c5 or world >= 4:
+        n5 = args.c5_n
+        h5_host = synth.synth_hashes(n5)
+        h5 = torch.from_numpy(h5_host.view(np.int64)).to(dev)
+        cap5 = 1 << 21
+        o5i = torch.empty(cap5, dtype=torch.int32, device=dev)
+        o5j = torch.empty(cap5, dtype=torch.int32, device=dev)
+        o5d = torch.empty(cap5, dtype=torch.uint8, device=dev)
+
+        def run_c5():
+            nat.check(lib.ke_hamming_join(ctx.handle, h5.data_ptr(), n5, 8, 0, 16, 4, None, rank, world, o5i.data_ptr(),
+                                          o5j.data_ptr(), o5d.data_ptr(), cap5, cnt.data_ptr(),
+                                          int(torch.cuda.current_stream(dev).cuda_stream)), "ke_hamming_join")
+
+        barrier()
+        t5_local = timed(run_c5, reps=1)
+        t5 = torch.tensor([t5_local], dtype=torch.float64, device=dev)
+        mine5 = int(cnt.item())
+        if world > 1:
+            torch.distributed.all_reduce(t5, op=torch.distributed.ReduceOp.MAX)
+        key5 = (o5i[:mine5].to(torch.int64) & 0xFFFFFFFF) << 32 | (o5j[:mine5].to(torch.int64) & 0xFFFFFFFF)
+        rows5 = kdist.all_gather_rows(torch.stack([key5, o5d[:mine5].to(torch.int64)], dim=1))
+        check = None
+        if rank == 0:
+            import oracle
+
+            oracle.build()
+            got = rows5[torch.argsort(rows5[:, 0])].cpu().numpy()
+            gi, gj, gd = (got[:, 0] >> 32) & 0xFFFFFFFF, got[:, 0] & 0xFFFFFFFF, got[:, 1]
+            stripes, ok5, checked = [(0, 192), (n5 // 3, n5 // 3 + 192), (n5 - 200_000, n5 - 200_000 + 192)], True, 0
+            for lo5, hi5 in stripes:
+                wi, wj, wd = oracle.hamming_join(h5_host, 8, threads=os.cpu_count() or 1, row_begin=lo5, row_end=hi5)
+                sel = (gi >= lo5) & (gi < hi5)
+                ok5 = ok5 and np.array_equal(gi[sel], wi) and np.array_equal(gj[sel], wj) and np.array_equal(gd[sel], wd)
+                checked += len(wi)
+            check = {"stripes": stripes, "pairs_in_stripes": int(checked), "equal_to_oracle": bool(ok5),
+                     "sorted_unique": bool(np.all(np.diff(got[:, 0]) > 0))}
+        p5 = n5 * (n5 - 1) // 2
+        r5 = p5 / (float(t5.item()) * 1e-3)
+        roof_c5 = {"workload": f"C5: {n5} hashes all-pairs (T=8), tiles over {world} GPU(s), candidates compacted and gathered",
+                   "ms": float(t5.item()), "pairs_per_s": r5, "frac": r5 / k2_peak, "frac_of_popc_only_roofline": r5 / popc_peak,
+                   "peak": k2_peak, "hits": int(rows5.shape[0]), "oracle_check": check}
+        del h5, o5i, o5j, o5d, rows5
 
     # K3 at config C4's shape: 256x256 'L' crops, bank >> L2, pairs sharded by index
     m_bank = args.ssim_bank
@@ -337,7 +443,7 @@ def run_cuda(args) -> dict:
         c_ = min(16384, m_bank - lo)
         ops.synth_images_device(lo, c_, 256, 256, 1, n_set=m_bank, seed=seed + 1, planted=0.5, out=crops[lo:lo + c_])
     g = torch.Generator(device="cpu").manual_seed(synth.SEED + 2 + rank)
-    n_pairs = args.ssim_pairs // world
+    n_pairs = args.ssim_pairs // world  # C4: 5 M pairs of 256x256 'L' crops in all, sharded by pair index
     ia = torch.randint(0, m_bank, (n_pairs,), generator=g).to(dev)
     ib = torch.randint(0, m_bank, (n_pairs,), generator=g).to(dev)
     bank_l = crops[..., 0]
@@ -352,7 +458,11 @@ def run_cuda(args) -> dict:
     k3_gbs = k3_bytes / (k3_ms_local * 1e-3) / 1e9
     roof_k3 = {"kernel": "ke_ssim4_kernel<1> (4 output columns per thread, packed FP32)", "bound": "hbm", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k3_gbs / hbm_peak, "pairs_per_s": world * n_pairs / (k3_ms * 1e-3), "shape": "256x256 L",
-               "pairs": world * n_pairs, "bank_images": m_bank, "ms": k3_ms, "peak_source": peak_src}
+               "pairs": world * n_pairs, "bank_images": m_bank, "ms": k3_ms, "peak_source": peak_src,
+               # the kernel is bound by instruction issue, not by HBM: both fractions side by side.  The issue
+               # numbers are ncu's for this kernel at this shape (profiles/, `smsp__issue_active`, instructions / outputs)
+               "issue_frac_ncu": K3_ISSUE_FRAC, "instr_per_output_ncu": K3_INSTR_PER_OUTPUT,
+               "issue_source": K3_ISSUE_SOURCE}
     del crops, bank_l, ia, ib, hashes
 
     # N1 (the refinement the UI runs after a scan): tile aHash at the UI default (grid 8 x tile 8 -> 64x64
@@ -380,26 +490,51 @@ def run_cuda(args) -> dict:
         host[lo:hi].copy_(bank[lo:hi])
     torch.cuda.synchronize(dev)
     dev_bank = bank[:n_e2e]
-    e2e_steps = max(1, min(args.steps, 3))
+
+    # host-feed roofline: the bare pinned host->device copy of the same bytes in the same chunks, on all ranks at once,
+    # nothing else running.  e2e cannot beat it; `h2d_frac` says how close the scan's feed comes.
+    def bare_h2d():
+        for lo in range(0, n_e2e, 2048):
+            hi = min(n_e2e, lo + 2048)
+            dev_bank[lo:hi].copy_(host[lo:hi], non_blocking=True)
+
+    bare_h2d()
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(3):
+        bare_h2d()
+    p1.record()
+    barrier()
+    probe_ms = torch.tensor([p0.elapsed_time(p1) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(probe_ms, op=torch.distributed.ReduceOp.MAX)
+    probe_gbs = n_e2e * IMG_BYTES / (float(probe_ms.item()) * 1e-3) / 1e9  # per GPU, all ranks copying
+
+    e2e_steps = max(1, min(args.steps, 10))
     e2e_warm = max(1, min(args.warmup, 2))
     for _ in range(e2e_warm):
-        pipeline.scan(dev_bank, host_images=host, threshold=8, ssim_threshold=0.9, n_local=n_e2e)
+        pipeline.scan(dev_bank, host_images=host, threshold=8, ssim_threshold=0.9)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(e2e_steps):
-        eo = pipeline.scan(dev_bank, host_images=host, threshold=8, ssim_threshold=0.9, n_local=n_e2e)
+        eo = pipeline.scan(dev_bank, host_images=host, threshold=8, ssim_threshold=0.9)
     t1.record()
     barrier()
     e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = world * n_e2e * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    e2e_step_s = float(e2e_ms.item()) * 1e-3 / e2e_steps
+    e2e_value = world * n_e2e / e2e_step_s
     clocks.__exit__(None, None, None)
     gc.enable()
+    h2d_gbs = n_e2e * IMG_BYTES / e2e_step_s / 1e9
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(eo.bytes_h2d),
            "d2h_bytes_per_step": int(eo.bytes_d2h), "images_per_step_per_gpu": int(n_e2e), "steps": e2e_steps,
+           "h2d_gbs_per_gpu": h2d_gbs, "h2d_probe_gbs_per_gpu": probe_gbs, "h2d_frac": h2d_gbs / probe_gbs,
+           "h2d_probe": f"bare pinned cudaMemcpyAsync of the same {n_e2e} images in 2048-image chunks, {world} rank(s) at once",
            "api": "kobato_b200.pipeline.scan(host_images=pinned uint8 [n,512,512,3]) -> hashes, candidates, SSIM, clusters"}
 
     result = {
@@ -409,10 +544,14 @@ def run_cuda(args) -> dict:
         "config": {"workload": "C2: 70k synthetic 512x512 RGB images per GPU: batched pHash+dHash + all-pairs Hamming "
                                "(T=8, band predicate) + SSIM verify (>=0.9)", "images_per_gpu": n, "h": H, "w": W, "c": C,
                    "hamming_threshold": 8, "ssim_threshold": 0.9, "l2": "inputs (55 GB/GPU) exceed L2; no flush needed",
-                   "parallelism": f"image shards x{world}; join tiles t%{world}; SSIM pairs by owner"},
-        "counts": counts,
+                   "planting": "one global set of n_gpus x 70000 images dealt round-robin: (n_gpus-1)/n_gpus of the "
+                               "candidate pairs straddle two ranks",
+                   "parallelism": f"image shards x{world}; join tiles t%{world}; SSIM pairs by owner, cross-shard pairs by "
+                                  "(i+j) parity with one packed all_to_all of luma planes"},
+        "counts": counts, "scan_check": scan_check,
         "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-        "roofline": roof_k1, "roofline_join": roof_k2, "roofline_ssim": roof_k3, "roofline_n1": roof_n1,
+        "roofline": roof_k1, "roofline_join": roof_k2, "roofline_join_c5": roof_c5, "roofline_ssim": roof_k3,
+        "roofline_n1": roof_n1,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
@@ -433,7 +572,9 @@ def main():
     ap.add_argument("--images", type=int, default=70000, help="images per GPU (C2: 70000)")
     ap.add_argument("--join-n", type=int, default=1_000_000, help="hash count for the K2 roofline run (C3)")
     ap.add_argument("--ssim-bank", type=int, default=65536, help="256x256 crops in the K3 roofline bank")
-    ap.add_argument("--ssim-pairs", type=int, default=1_000_000, help="pairs in the K3 roofline run")
+    ap.add_argument("--ssim-pairs", type=int, default=5_000_000, help="pairs in the K3 roofline run over all GPUs (C4: 5 M)")
+    ap.add_argument("--c5", action="store_true", help="also time config C5 (10 M-hash join) below 4 GPUs")
+    ap.add_argument("--c5-n", type=int, default=10_000_000, help="hash count of the C5 join")
     ap.add_argument("--ref-sample", type=int, default=4096, help="images per reference-arm step")
     ap.add_argument("--ref-unique", type=int, default=256, help="unique synthetic images behind the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -75,26 +75,40 @@ class CpuReference:
         self.pool.close()
         self.pool.join()
 
-    def step(self, sample: int, threshold: int = 8, ssim_threshold: float = 0.9, max_ssim_pairs: int = 256):
-        """One bounded step; returns per-stage seconds and counts."""
+    def step(self, sample: int, threshold: int = 8, ssim_threshold: float = 0.9, pairs_per_image: float = 3589 / 70000):
+        """One bounded step; returns per-stage seconds and counts.
+
+        The three stages keep the proportions of the GPU arm's step: every image of the sample is hashed, the LSH scan
+        runs over a table of ``sample`` hashes (the pool's own hashes plus synthetic ones with the same 5 % of planted
+        near-duplicates), and ``round(sample * pairs_per_image)`` pairs are SSIM-verified — the candidate rate the GPU
+        step sees on the 70 000-image set (3 589 pairs per 70 000 images); the pool's own edges first, then further
+        pairs of pool images (SSIM cost does not depend on the content)."""
+        from kobato_b200 import synth
         from oracle import ref_py
 
         t0 = time.perf_counter()
         sigs = self.pool.map(_hash, range(sample), chunksize=16)
         t1 = time.perf_counter()
-        # distinct ids; images cycle through the unique pool, so exact repeats are excluded from
-        # the scan by hashing only one representative per unique image plus its index
+        # distinct ids; images cycle through the unique pool, so beyond the pool the table is filled with synthetic
+        # hashes (exact repeats of the pool's images would otherwise make every bucket a giant cluster)
         first = min(sample, self.unique)
-        files = [ref_py.FileRec(i + 1, f"f{i}.png", 1000 + i, self.w, self.h, sigs[i][0] & ref_py.U64)
-                 for i in range(first)]
+        table = [sigs[i][0] & ref_py.U64 for i in range(first)]
+        if sample > first:
+            table += [int(x) for x in synth.synth_hashes(sample - first, seed=synth.SEED + 17, planted=0.05)]
+        files = [ref_py.FileRec(i + 1, f"f{i}.png", 1000 + i, self.w, self.h, table[i]) for i in range(sample)]
         edges = ref_py.scan_edges(files, hamming_threshold=threshold)
         clusters = ref_py.build_clusters(files, hamming_threshold=threshold)
         t2 = time.perf_counter()
-        pairs = [(a - 1, b - 1) for (a, b) in list(edges)[:max_ssim_pairs]]
+        want = max(1, int(round(sample * pairs_per_image)))
+        pairs = [(a - 1, b - 1) for (a, b) in edges if a <= first and b <= first][:want]
+        k = 0
+        while len(pairs) < want:  # fill up with further pool pairs
+            pairs.append((k % self.unique, (k * 7 + 1) % self.unique))
+            k += 1
         scores = self.pool.map(_ssim, pairs, chunksize=2) if pairs else []
         t3 = time.perf_counter()
         return {
             "hash_s": t1 - t0, "scan_s": t2 - t1, "ssim_s": t3 - t2, "total_s": t3 - t0,
-            "images": sample, "scan_files": first, "edges": len(edges), "clusters": len(clusters),
+            "images": sample, "scan_files": sample, "edges": len(edges), "clusters": len(clusters),
             "ssim_pairs": len(pairs), "accepted": int(sum(s >= ssim_threshold for s in scores)),
         }
