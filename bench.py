@@ -341,6 +341,21 @@ def run_cuda(args) -> dict:
                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                "images_per_s": n / (k1_ms * 1e-3)}
 
+    # K1 on larger photographs (the reference feeds images up to 4096 px, src/utils/image_io.py:60-138): the same
+    # kernel with its resample fragments in shared memory (1024 px) / L2 (2048 px); banks of 6 GB >> L2
+    roof_k1_large = {}
+    for (hh, ww) in ((1024, 1024), (1536, 2048)):
+        cnt_l = max(64, int(6e9) // (hh * ww * C))
+        big = torch.empty((cnt_l, hh, ww, C), dtype=torch.uint8, device=dev)
+        for lo in range(0, cnt_l, 256):
+            c_ = min(256, cnt_l - lo)
+            ops.synth_images_device(lo, c_, hh, ww, C, n_set=cnt_l, seed=seed + 5, out=big[lo:lo + c_])
+        ms_l = timed(lambda: ops.phash_dhash_batch(big))
+        gbs_l = cnt_l * (hh * ww * C + 16) / (ms_l * 1e-3) / 1e9
+        roof_k1_large[f"{ww}x{hh}x{C}"] = {"images": cnt_l, "ms": ms_l, "images_per_s": cnt_l / (ms_l * 1e-3), "achieved": gbs_l,
+                                           "unit": "GB/s", "frac": gbs_l / hbm_peak}
+        del big
+
     # K2 at config C3: 1 M synthetic hashes, T=8, tiles split over the ranks (strong scaling)
     popc_rate, popc_mhz = ops.popc_rate(4096, local)
     hashes = torch.from_numpy(synth.synth_hashes(args.join_n).view(np.int64)).to(dev)
@@ -526,6 +541,7 @@ def run_cuda(args) -> dict:
     e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_stage = {k: round(v, 3) for k, v in eo.stage_ms.items()}
     e2e_step_s = float(e2e_ms.item()) * 1e-3 / e2e_steps
     e2e_value = world * n_e2e / e2e_step_s
     clocks.__exit__(None, None, None)
@@ -534,6 +550,7 @@ def run_cuda(args) -> dict:
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(eo.bytes_h2d),
            "d2h_bytes_per_step": int(eo.bytes_d2h), "images_per_step_per_gpu": int(n_e2e), "steps": e2e_steps,
            "h2d_gbs_per_gpu": h2d_gbs, "h2d_probe_gbs_per_gpu": probe_gbs, "h2d_frac": h2d_gbs / probe_gbs,
+           "stages_ms_last_step": e2e_stage,
            "h2d_probe": f"bare pinned cudaMemcpyAsync of the same {n_e2e} images in 2048-image chunks, {world} rank(s) at once",
            "api": "kobato_b200.pipeline.scan(host_images=pinned uint8 [n,512,512,3]) -> hashes, candidates, SSIM, clusters"}
 
@@ -550,7 +567,7 @@ def run_cuda(args) -> dict:
                                   "(i+j) parity with one packed all_to_all of luma planes"},
         "counts": counts, "scan_check": scan_check,
         "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-        "roofline": roof_k1, "roofline_join": roof_k2, "roofline_join_c5": roof_c5, "roofline_ssim": roof_k3,
+        "roofline": roof_k1, "roofline_phash_large": roof_k1_large, "roofline_join": roof_k2, "roofline_join_c5": roof_c5, "roofline_ssim": roof_k3,
         "roofline_n1": roof_n1,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
     }

@@ -50,6 +50,17 @@ int ctx_create_one(int device, ke_ctx** out) {
     KE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) KE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->stage_ev) KE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    {
+        // per-call scratch (join queue / bit-sliced table, SSIM partials, union-find arrays) comes from the device's default
+        // stream-ordered pool: keep what it has handed out instead of returning it to the driver at every synchronisation
+        // (the default release threshold of 0 turns every cudaMallocAsync after a sync into a fresh physical allocation)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return KE_OK;
 }
@@ -111,7 +122,6 @@ extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
     KE_REQUIRE(ctx != nullptr, "ke_ctx_set_option: ctx is NULL");
     switch (option) {
         case KE_OPT_PHASH_GENERIC:
-        case KE_OPT_PHASH_LADDER:
         case KE_OPT_SSIM_V1:
         case KE_OPT_RESIZE_GENERIC: break;
         case KE_OPT_JOIN_MODE: KE_REQUIRE(value >= 0 && value <= 3, "ke_ctx_set_option: join mode must be 0..3"); break;
@@ -121,7 +131,6 @@ extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
         ke_ctx* c = ctx->dev_ctx[k];
         switch (option) {
             case KE_OPT_PHASH_GENERIC: c->force_generic_phash = value ? 1 : 0; break;
-            case KE_OPT_PHASH_LADDER: c->phash_ladder = value; break;
             case KE_OPT_SSIM_V1: c->force_ssim_v1 = value ? 1 : 0; break;
             case KE_OPT_RESIZE_GENERIC: c->force_generic_resize = value ? 1 : 0; break;
             default: c->join_mode = value;

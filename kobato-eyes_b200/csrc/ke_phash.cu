@@ -6,7 +6,16 @@
 // the threshold) -> 8x8 low block compared with the mean of its 63 AC terms -> 64-bit hash;
 // dHash = left<right compares on the 8x9 plane.
 //
-// One persistent CTA (256 threads) walks images; per image it streams row chunks:
+// Two kernels:
+//   * ke_phash_v5_kernel (default; "tensor-core kernel (v5)" below): persistent CTAs, raw rows by 1-D TMA bulk copies into
+//     a ring of sub-chunks, luma warps (dp2a), and eight tap warps that run BOTH Lanczos resamples exactly on the
+//     tensor pipe (mma.sync u8 x s8 over balanced base-256 tap digits), then the FP64 DCT.  It takes every batch of
+//     contiguous rows: any width (the resample band's B fragments sit in registers up to ~512 pixels, in shared memory
+//     up to ~1100, in L2 beyond), any byte alignment (the copies move the 16-byte aligned superset of a sub-chunk and
+//     the luma warps funnel-shift), 'L' / RGB / RGBA.
+//   * ke_phash_kernel (generic): one CTA of 256 threads per image stream, dp4a taps on CUDA cores, plain loads when the
+//     rows are strided.  It takes everything else (row_stride != w * c) and is the in-library reference the parity
+//     tests compare v5 with (KE_OPT_PHASH_GENERIC).  Its steps:
 //   1. raw rows HBM -> shared memory with one 1-D TMA bulk copy (cp.async.bulk + mbarrier;
 //      16-byte aligned superset of the chunk), issued one chunk ahead of the compute;
 //   2. luma: L = (R*19595 + G*38470 + B*7471 + 0x8000) >> 16 with dp4a on the packed bytes
@@ -20,6 +29,9 @@
 //      of the 32x32 outputs; 72 threads own the 8x9 outputs), so no [H,32] plane is ever stored.
 // After the last chunk: vertical rounding, FP64 DCT (8x32 * 32x32 * 32x8), warp-shuffle mean
 // of the AC terms, ballot -> hash bits (first element = MSB).
+//
+// The aligned-superset copies of v5 read up to 15 bytes in front of the first and behind the last image of an
+// unaligned batch: inside the caller's allocation (device allocations are at least 256-byte granular), never written.
 //
 // Algorithmic HBM bytes per image: h*w*c read + 16 written.
 #include <algorithm>
@@ -45,16 +57,9 @@ constexpr int kPrec = 22;
 struct HTable {           // horizontal pass, one per input width
     uint4* d_coef = nullptr;   // packed byte-plane tap words, outputs back to back
     int4* d_items = nullptr;   // work items {out, word_begin, word_count, 0}
-    int4* d_bal = nullptr;     // the same word-steps cut into kWarps lists of equal length (fast kernel)
     int* d_meta = nullptr;     // [kOuts] first pixel word, [kOuts] offset into d_coef, [kWarps+1] list starts
     int n_items = 0;
-    int n_bal = 0;
     int coef_words = 0;
-    // lanes=outputs kernel: warp-tasks of 32 lane-tasks (output, first 16-pixel group, <= 8 groups)
-    uint4* d_lt_coef = nullptr;  // [(task*8 + group)*3 + plane][lane] -> 4 tap words
-    int2* d_lt_meta = nullptr;   // [task][lane] -> {output or -1, first group}
-    int* d_lt_ng = nullptr;      // [task] -> groups to process (uniform per warp-task)
-    int n_wtasks = 0;
     // tensor-core kernel (v5): per tap warp a run of mma.m16n8k32 B fragments [k-step][tile][lane]
     uint2* d_mma_b = nullptr;
     int mma_words = 0;           // uint2 words in d_mma_b (0: this width is not served by v5)
@@ -85,11 +90,7 @@ void ke_tables_free(KeTableCache* cache) {
     for (auto& kv : cache->h) {
         cudaFree(kv.second.d_coef);
         cudaFree(kv.second.d_items);
-        cudaFree(kv.second.d_bal);
         cudaFree(kv.second.d_meta);
-        cudaFree(kv.second.d_lt_coef);
-        cudaFree(kv.second.d_lt_meta);
-        cudaFree(kv.second.d_lt_ng);
         cudaFree(kv.second.d_mma_b);
     }
     for (auto& kv : cache->v) {
@@ -119,7 +120,7 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         return KE_OK;
     }
     std::vector<uint4> coef;
-    std::vector<int> meta(2 * kOuts + kWarps + 1);
+    std::vector<int> meta(2 * kOuts);
     std::vector<int> nwords(kOuts);
     const int outs[2] = {kOutW, kDW};
     int o_base = 0;
@@ -170,111 +171,6 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         }
     }
     std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return a.z > b.z; });
-    // Balanced lists: the concatenated word-steps of all outputs, cut into kWarps equal ranges.
-    std::vector<int4> bal;
-    {
-        long long total = 0;
-        for (int o = 0; o < kOuts; ++o) total += nwords[o];
-        for (int wv = 0; wv < kWarps; ++wv) {
-            meta[2 * kOuts + wv] = (int)bal.size();
-            const long long lo = total * wv / kWarps, hi = total * (wv + 1) / kWarps;
-            long long base = 0;
-            for (int o = 0; o < kOuts; ++o) {
-                const long long b = std::max(lo, base), e = std::min(hi, base + nwords[o]);
-                if (e > b) bal.push_back(make_int4(o, (int)(b - base), (int)(e - b), 0));
-                base += nwords[o];
-            }
-        }
-        meta[2 * kOuts + kWarps] = (int)bal.size();
-    }
-    // Lane-task tables: every output's taps, aligned to 16-pixel groups, cut into segments of <= 8
-    // groups; 32 lane-tasks (segment-major order) form one warp-task.
-    std::vector<uint4> lt_coef;
-    std::vector<int2> lt_meta;
-    std::vector<int> lt_ng;
-    {
-        int ob = 0;
-        for (int tbl = 0; tbl < 2; ++tbl) {
-            const int ow = outs[tbl];
-            const int ks = ke_resample_ksize(w, ow);
-            std::vector<int32_t> kk((size_t)ks * ow), bd(2 * (size_t)ow);
-            int rc = ke_resample_table(w, ow, kk.data(), bd.data(), ks);
-            if (rc) return rc;
-            int max_seg = 1;
-            std::vector<int> gfirst(ow), ngr(ow);
-            for (int o = 0; o < ow; ++o) {
-                gfirst[o] = bd[2 * o] / 16;
-                ngr[o] = (bd[2 * o] + bd[2 * o + 1] - 1) / 16 - gfirst[o] + 1;
-                max_seg = std::max(max_seg, (ngr[o] + 7) / 8);
-            }
-            struct LT { int o, g0, len; };
-            std::vector<LT> lts;
-            for (int sgi = 0; sgi < max_seg; ++sgi)
-                for (int o = 0; o < ow; ++o) {
-                    const int nseg = (ngr[o] + 7) / 8;
-                    if (sgi >= nseg) continue;
-                    const int b = ngr[o] * sgi / nseg, e = ngr[o] * (sgi + 1) / nseg;
-                    lts.push_back({o, gfirst[o] + b, e - b});
-                }
-            // LDS.128 is served 8 lanes at a time: inside each quarter-warp, lanes reading DIFFERENT
-            // 16-byte groups must fall into different (group % 8) bank sets.  Greedily deal every
-            // block of 32 lane-tasks into 4 quarters with distinct residues (equal groups may share).
-            for (size_t base = 0; base < lts.size(); base += 32) {
-                const size_t cnt = std::min<size_t>(32, lts.size() - base);
-                std::vector<LT> blk(lts.begin() + base, lts.begin() + base + cnt), placed(32, LT{-1, 0, 0});
-                std::vector<int> fill(4, 0);
-                std::vector<std::vector<int>> used(4);  // groups already present per quarter
-                for (const LT& lt : blk) {
-                    int best = -1;
-                    for (int q = 0; q < 4 && best < 0; ++q) {
-                        if (fill[q] >= 8) continue;
-                        bool ok = true;
-                        for (int gq : used[q])
-                            if (gq != lt.g0 && (gq & 7) == (lt.g0 & 7)) ok = false;
-                        if (ok) best = q;
-                    }
-                    if (best < 0)
-                        for (int q = 0; q < 4 && best < 0; ++q)
-                            if (fill[q] < 8) best = q;
-                    placed[best * 8 + fill[best]++] = lt;
-                    used[best].push_back(lt.g0);
-                }
-                for (size_t l = 0; l < 32; ++l)
-                    if (base + l < lts.size() + 0) { /* written back below */ }
-                lts.resize(std::max(lts.size(), base + 32), LT{-1, 0, 0});
-                for (size_t l = 0; l < 32; ++l) lts[base + l] = placed[l];
-            }
-            for (size_t base = 0; base < lts.size(); base += 32) {
-                const int task = (int)lt_ng.size();
-                int ng = 1;
-                for (size_t l = base; l < std::min(lts.size(), base + 32); ++l)
-                    if (lts[l].o >= 0) ng = std::max(ng, lts[l].len);
-                lt_ng.push_back(ng);
-                lt_meta.resize((size_t)(task + 1) * 32, make_int2(-1, 0));
-                lt_coef.resize((size_t)(task + 1) * 8 * 3 * 32, make_uint4(0, 0, 0, 0));
-                for (int lane = 0; lane < 32 && base + lane < lts.size(); ++lane) {
-                    const LT& lt = lts[base + lane];
-                    if (lt.o < 0) continue;  // idle lane (kept at {-1, group 0}: reads row start, adds nothing)
-                    lt_meta[(size_t)task * 32 + lane] = make_int2(ob + lt.o, lt.g0);
-                    const int first = bd[2 * lt.o], count = bd[2 * lt.o + 1];
-                    for (int g = 0; g < lt.len; ++g)
-                        for (int p = 0; p < 3; ++p) {
-                            uint32_t wd[4] = {0, 0, 0, 0};
-                            for (int b = 0; b < 16; ++b) {
-                                const int x = (lt.g0 + g) * 16 + b, tap = x - first;
-                                const int32_t k = (tap >= 0 && tap < count) ? kk[(size_t)lt.o * ks + tap] : 0;
-                                const uint32_t byte = p == 0 ? ((uint32_t)k & 0xFFu)
-                                                      : p == 1 ? (((uint32_t)k >> 8) & 0xFFu) : ((uint32_t)(k >> 16) & 0xFFu);
-                                wd[b >> 2] |= byte << (8 * (b & 3));
-                            }
-                            lt_coef[((size_t)(task * 8 + g) * 3 + p) * 32 + lane] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-                        }
-                }
-            }
-            ob += ow;
-        }
-    }
-
     // Tensor-core tables (v5).  The horizontal pass is the banded product  luma[rows, w] x taps[w, 41 x 3 digits]:
     // taps are written in balanced base-256 digits k = d0 + 256 d1 + 65536 d2, every d in [-128, 127], so one
     // mma.m16n8k32.s32.u8.s8 per (16 rows, 8 columns, 32 pixels) accumulates a digit plane exactly.
@@ -283,7 +179,7 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
     // {a.d0, a.d1, b.d0, b.d1, a.d2, b.d2, 0, 0}; warp 7 carries the pairs (6,7) and (8,-).
     std::vector<uint2> mma_b;
     int mma_k0[8], mma_nk[8], mma_boff[8];
-    bool mma_ok = (w % 16 == 0);
+    bool mma_ok = true;  // any width: taps are zero outside an output's support, so the padding of the last k-step adds nothing
     if (mma_ok) {
         std::vector<int32_t> kkP, bdP, kkD, bdD;
         const int ksP = ke_resample_ksize(w, kOutW), ksD = ke_resample_ksize(w, kDW);
@@ -349,17 +245,11 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         }
     }
     HTable t;
-    t.n_wtasks = (int)lt_ng.size();
-    t.n_bal = (int)bal.size();
     t.n_items = (int)items.size();
     t.coef_words = (int)coef.size();
     int rc;
     if ((rc = upload(coef, &t.d_coef))) return rc;
     if ((rc = upload(items, &t.d_items))) return rc;
-    if ((rc = upload(bal, &t.d_bal))) return rc;
-    if ((rc = upload(lt_coef, &t.d_lt_coef))) return rc;
-    if ((rc = upload(lt_meta, &t.d_lt_meta))) return rc;
-    if ((rc = upload(lt_ng, &t.d_lt_ng))) return rc;
     if ((rc = upload(meta, &t.d_meta))) return rc;
     if (mma_ok) {
         if ((rc = upload(mma_b, &t.d_mma_b))) return rc;
@@ -468,22 +358,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-    // producer side: nobody else can use this lane's issue slots productively, so sleep between polls
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(800);
-    }
-}
-
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
     // consumer side: poll politely so the spinning warps do not take issue slots from the producers
     const uint32_t addr = smem_u32(bar);
@@ -524,13 +398,8 @@ struct PhashArgs {
     // tables
     const uint4* coef;
     const int4* items;
-    const int4* bal;
     const int* meta;
-    int n_items, n_bal, coef_words;
-    const uint4* lt_coef;
-    const int2* lt_meta;
-    const int* lt_ng;
-    int n_wtasks;
+    int n_items, coef_words;
     const uint2* mma_b;
     int mma_words;
     int mma_k0[8], mma_nk[8], mma_boff[8];
@@ -837,88 +706,8 @@ __global__ void __launch_bounds__(kThreads) ke_phash_kernel(const PhashArgs a) {
 }
 
 
-// Vertical taps of one chunk, in registers.  Output row yy of the 32x32 plane is owned by warp
-// (yy % 8) (lane = output column): the ~8 output rows whose tap range meets a 32-row chunk are
-// consecutive, so every warp has work in every chunk (a contiguous block of 4 rows per warp left 6
-// of 8 warps idle).  The 8x9 plane: warp = output row, lane = (column, row phase 0..2); the three
-// phases are summed with shuffles when the image is finished.
 template <int NW = kWarps>
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
-
-template <int NW>
-struct VertState {
-    static constexpr int Q = kOutH / NW;   // 32x32 plane rows owned by a warp: warp, warp+NW, ...
-    static constexpr int D = kDH / NW;     // 8x9 plane rows owned by a warp
-    int32_t acc[Q];
-    int32_t dacc[D];
-    int ymin[Q], ylen[Q], dmin[D], dlen[D];
-};
-
-template <int NW>
-__device__ __forceinline__ void vertical_init(const PhashArgs& a, VertState<NW>& v, int lane, int warp) {
-#pragma unroll
-    for (int q = 0; q < VertState<NW>::Q; ++q) {
-        v.ymin[q] = __ldg(a.b32 + 2 * (q * NW + warp));
-        v.ylen[q] = __ldg(a.b32 + 2 * (q * NW + warp) + 1);
-    }
-#pragma unroll
-    for (int d = 0; d < VertState<NW>::D; ++d) {
-        v.dmin[d] = __ldg(a.b8 + 2 * (d * NW + warp));
-        v.dlen[d] = __ldg(a.b8 + 2 * (d * NW + warp) + 1);
-    }
-}
-
-template <int NW>
-__device__ __forceinline__ void vertical_reset(VertState<NW>& v, int lane) {
-#pragma unroll
-    for (int q = 0; q < VertState<NW>::Q; ++q) v.acc[q] = 1 << (kPrec - 1);
-#pragma unroll
-    for (int d = 0; d < VertState<NW>::D; ++d) v.dacc[d] = (lane < kDW) ? (1 << (kPrec - 1)) : 0;  // rounding term once
-}
-
-template <int NW, int HP = kOuts>
-__device__ __forceinline__ void vertical_chunk(const PhashArgs& a, VertState<NW>& v, const uint8_t* s_hrow, int r0,
-                                               int rows, int lane, int warp) {
-#pragma unroll
-    for (int q = 0; q < VertState<NW>::Q; ++q) {
-        const int lo = max(v.ymin[q], r0), hi = min(v.ymin[q] + v.ylen[q], r0 + rows);
-        if (lo < hi) {
-            const int* kk = a.kk32 + (q * NW + warp) * a.ks32 - v.ymin[q];
-            const uint8_t* hp = s_hrow + lane - r0 * HP;
-            int32_t acc = v.acc[q];
-#pragma unroll 8
-            for (int y = lo; y < hi; ++y) acc += (int32_t)hp[y * HP] * __ldg(kk + y);
-            v.acc[q] = acc;
-        }
-    }
-    if (lane < 3 * kDW) {
-        const int x = lane % kDW, ph = lane / kDW;
-#pragma unroll
-        for (int d = 0; d < VertState<NW>::D; ++d) {
-            const int lo = max(v.dmin[d], r0), hi = min(v.dmin[d] + v.dlen[d], r0 + rows);
-            const int* kk = a.kk8 + (d * NW + warp) * a.ks8 - v.dmin[d];
-            const uint8_t* hp = s_hrow + kOutW + x - r0 * HP;
-            int32_t acc = v.dacc[d];
-#pragma unroll 4
-            for (int y = lo + ph; y < hi; y += 3) acc += (int32_t)hp[y * HP] * __ldg(kk + y);
-            v.dacc[d] = acc;
-        }
-    }
-}
-
-// planes from the vertical accumulators (all compute threads call this)
-template <int NW>
-__device__ __forceinline__ void vertical_finish(VertState<NW>& v, uint8_t* s_x32, uint8_t* s_x98, int lane, int warp) {
-#pragma unroll
-    for (int q = 0; q < VertState<NW>::Q; ++q) s_x32[(q * NW + warp) * 32 + lane] = clip8(v.acc[q]);
-#pragma unroll
-    for (int d = 0; d < VertState<NW>::D; ++d) {
-        // lanes x, x+9, x+18 hold the three row phases of output (d*NW+warp, x)
-        const int32_t s0 = v.dacc[d];
-        const int32_t s1 = __shfl_sync(0xffffffffu, s0, (lane + kDW) & 31), s2 = __shfl_sync(0xffffffffu, s0, (lane + 2 * kDW) & 31);
-        if (lane < kDW) s_x98[(d * NW + warp) * kDW + lane] = clip8(s0 + s1 + s2);
-    }
-}
 
 // DCT low block + hash bits from s_x32 / s_x98 (all NW compute warps call this)
 template <int NW>
@@ -974,50 +763,7 @@ __device__ __forceinline__ void dct_and_bits(const PhashArgs& a, long long im, c
     }
 }
 
-// ------------------------------------------------------------------ the fast kernel
-//
-// Same arithmetic, restructured for the common geometry (contiguous rows, w*c % 16 == 0, a
-// 64- or 32-row chunk fits shared memory).  288 threads: warps 0..7 compute, warp 8 is the TMA
-// producer.  Raw rows arrive in sub-chunks of `sub_rows` rows through a 2-deep ring of
-// full/empty mbarriers, so loads run ahead of the compute across chunk and image boundaries and
-// the compute warps only ever synchronise among themselves (named barrier 1).  In the horizontal
-// pass every lane owns RPL rows (lane, lane+32, ...), so one warp-uniform LDS.128 of tap words
-// feeds 3*RPL dp4a.
-
-constexpr int kFastThreads = kThreads + 32;
-constexpr int kMaxItems = 160;
 constexpr int kMaxSlots = 8;
-
-struct FastLayout {
-    int raw, coef, luma, acc, hrow, x32, x98, tmat, ymat, meta, items, bar, total;
-};
-
-__host__ __device__ inline FastLayout fast_layout(int coef_words, int sub_bytes, int chunk_rows, int pitch_words,
-                                                  int n_slots) {
-    FastLayout L;
-    int off = 0;
-    auto take = [&](int bytes, int align) {
-        off = (off + align - 1) / align * align;
-        int at = off;
-        off += bytes;
-        return at;
-    };
-    L.raw = take(n_slots * sub_bytes, 128);
-    L.coef = take(coef_words * 16, 16);
-    L.luma = take(chunk_rows * pitch_words * 4, 16);
-    L.acc = take(chunk_rows * kOuts * 4, 16);
-    L.hrow = take(chunk_rows * kOuts, 16);
-    L.x32 = take(1024, 16);
-    L.x98 = take(80, 16);
-    L.tmat = take(8 * 32 * 8, 16);
-    L.ymat = take(64 * 8, 16);
-    L.meta = take((2 * kOuts + kWarps + 1) * 4, 16);
-    L.items = take(kMaxItems * 16, 16);
-    L.bar = take(2 * kMaxSlots * 8, 8);
-    L.total = off;
-    return L;
-}
-
 
 // luma of `rows` raw rows (row r at raw + r*row_bytes) -> luma rows (word pitch `pitch_words`).
 // warp -> rows, lanes -> 4-pixel groups: conflict-free LDS.32 x3 / STS.32 x1, no divisions.
@@ -1115,443 +861,9 @@ __device__ __forceinline__ void luma_rows_rgb16(const uint8_t* __restrict__ raw,
     }
 }
 
-template <int C, int RPL>
-__global__ void __launch_bounds__(kFastThreads) ke_phash_fast_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, const int dbg) {
-    constexpr int CR = 32 * RPL;  // rows per chunk
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int row_bytes = a.w * C;
-    const int sub_bytes = sub_rows * row_bytes;
-    const int n_slots = 1 << slot_shift;
-    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
-    const FastLayout L = fast_layout(a.coef_words, sub_bytes, CR, a.pitch_words, n_slots);
-    uint8_t* s_raw = smem + L.raw;
-    uint4* s_coef = reinterpret_cast<uint4*>(smem + L.coef);
-    uint32_t* s_luma = reinterpret_cast<uint32_t*>(smem + L.luma);
-    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
-    uint8_t* s_hrow = smem + L.hrow;
-    uint8_t* s_x32 = smem + L.x32;
-    uint8_t* s_x98 = smem + L.x98;
-    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
-    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
-    int* s_meta = reinterpret_cast<int*>(smem + L.meta);
-    int4* s_items = reinterpret_cast<int4*>(smem + L.items);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // [kMaxSlots]
-    uint64_t* s_empty = s_full + kMaxSlots;                        // [kMaxSlots]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_sub = (a.h + sub_rows - 1) / sub_rows;  // sub-chunks per image
-    const int subs_per_chunk = CR / sub_rows;
-
-    if (tid == 0) {
-        for (int b = 0; b < n_slots; ++b) {
-            mbar_init(&s_full[b], 1);
-            mbar_init(&s_empty[b], kWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < a.coef_words; i += kFastThreads) s_coef[i] = a.coef[i];
-    for (int i = tid; i < 2 * kOuts + kWarps + 1; i += kFastThreads) s_meta[i] = a.meta[i];
-    for (int i = tid; i < a.n_bal; i += kFastThreads) s_items[i] = a.bal[i];
-    for (int i = tid; i < CR * kOuts; i += kFastThreads) s_acc[i] = 1u << (kPrec - 1);
-    __syncthreads();
-
-    if (warp == kWarps) {
-        // ===== TMA producer: one lane streams every sub-chunk of every image of this CTA =====
-        if (lane == 0) {
-            uint32_t seq = 0;
-            for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-                const uint8_t* src = a.img + im * a.img_stride;
-                for (int s = 0; s < n_sub; ++s, ++seq) {
-                    const int b = seq & slot_mask;
-                    const int rows = min(sub_rows, a.h - s * sub_rows);
-                    mbar_wait_backoff(&s_empty[b], ((seq >> slot_shift) & 1u) ^ 1u);
-                    if (dbg & 1) {  // tuning probe: no HBM traffic, stale shared memory is hashed
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[b])) : "memory");
-                        continue;
-                    }
-                    mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
-                    bulk_g2s(s_raw + b * sub_bytes, src + (long long)s * sub_bytes, (uint32_t)(rows * row_bytes),
-                             &s_full[b]);
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== compute warps =====
-    uint32_t seq = 0;
-    VertState<kWarps> vs;
-    vertical_init(a, vs, lane, warp);
-    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-        vertical_reset(vs, lane);
-
-        for (int r0 = 0; r0 < a.h; r0 += CR) {
-            const int rows = min(CR, a.h - r0);
-            // ---- luma of this chunk, sub-chunk by sub-chunk as the copies land
-            for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
-                const int b = seq & slot_mask;
-                const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
-                mbar_wait(&s_full[b], (seq >> slot_shift) & 1u);
-                luma_rows_fast<C>(s_raw + b * sub_bytes, s_luma + s * sub_rows * a.pitch_words, srows, a.w,
-                                  a.pitch_words, warp, lane);
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[b])) : "memory");
-            }
-            compute_sync();
-            if (dbg & 2) continue;  // tuning probe: loads + luma only
-
-            // ---- horizontal taps: lane -> rows (lane, lane+32, ...), tap words warp-uniform
-            for (int it = s_meta[2 * kOuts + warp]; it < ((dbg & 4) ? 0 : s_meta[2 * kOuts + warp + 1]); ++it) {
-                const int4 item = s_items[it];
-                const int o = item.x;
-                const uint4* __restrict__ cf = s_coef + s_meta[kOuts + o] + item.y;
-                const uint32_t* __restrict__ px = s_luma + lane * a.pitch_words + s_meta[o] + item.y;
-                uint32_t d0[RPL], d1[RPL];
-                int32_t d2[RPL];
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) d0[r] = 0u, d1[r] = 0u, d2[r] = 0;
-#pragma unroll 4
-                for (int t = 0; t < item.z; ++t) {
-                    const uint4 cw = cf[t];
-#pragma unroll
-                    for (int r = 0; r < RPL; ++r) {
-                        const uint32_t p = px[r * 32 * a.pitch_words + t];
-                        d0[r] = dp4a_uu(p, cw.x, d0[r]);
-                        d1[r] = dp4a_uu(p, cw.y, d1[r]);
-                        d2[r] = dp4a_us(p, cw.z, d2[r]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < RPL; ++r)
-                    if (lane + 32 * r < rows)
-                        atomicAdd(&s_acc[(lane + 32 * r) * kOuts + o], d0[r] + (d1[r] << 8) + ((uint32_t)d2[r] << 16));
-            }
-            compute_sync();
-
-            // ---- round, clip, reset accumulators
-            for (int i = tid; i < rows * kOuts; i += kThreads) {
-                s_hrow[i] = clip8((int32_t)s_acc[i]);
-                s_acc[i] = 1u << (kPrec - 1);
-            }
-            compute_sync();
-
-            // ---- vertical taps, streamed into registers
-            vertical_chunk(a, vs, s_hrow, r0, rows, lane, warp);
-        }
-
-        // ---- planes, DCT, hash bits (identical to the generic kernel)
-        vertical_finish(vs, s_x32, s_x98, lane, warp);
-        compute_sync();
-        dct_and_bits<kWarps>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
-        // s_x32 / s_x98 / s_y are rewritten only after the next image's chunk barriers
-    }
-}
-
-// Picks (RPL, sub_rows, ring slots) for the fast kernel; false when the geometry needs the generic one.
-// Order = measured on B200 at 512x512x3 (tools/sweep_phash.sh): the kernel is issue / shared-memory
-// bound, not load bound, so the smallest footprint (most L1 left, two CTAs per SM) wins and a
-// deeper ring does not help.
-template <int C>
-bool fast_config(const PhashArgs& a, int& rpl, int& sub_rows, int& slot_shift, FastLayout& L) {
-    const long long row_bytes = (long long)a.w * C;
-    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || a.n_bal > kMaxItems) return false;
-    struct Cand { int rpl, sub, shift; };
-    const Cand cands[] = {{1, 8, 1}, {2, 8, 1}, {1, 4, 1}, {1, 2, 1}, {1, 1, 1}};
-#ifdef KE_TUNING_PROBES
-    if (const char* env = getenv("KE_PHASH_CFG")) {  // tuning override: "rpl,sub_rows,slot_shift"
-        Cand cd{0, 0, 0};
-        if (sscanf(env, "%d,%d,%d", &cd.rpl, &cd.sub, &cd.shift) == 3 && (cd.rpl == 1 || cd.rpl == 2) && cd.sub >= 1 &&
-            (32 * cd.rpl) % cd.sub == 0 && cd.shift >= 1 && cd.shift <= 3) {
-            L = fast_layout(a.coef_words, (int)(cd.sub * row_bytes), 32 * cd.rpl, a.pitch_words, 1 << cd.shift);
-            if (L.total <= 227 * 1024) {
-                rpl = cd.rpl, sub_rows = cd.sub, slot_shift = cd.shift;
-                return true;
-            }
-        }
-    }
-#endif
-    for (int budget : {113 * 1024, 227 * 1024}) {
-        for (const Cand& cd : cands) {
-            const long long sub_bytes = cd.sub * row_bytes;
-            if (sub_bytes > (1 << 20)) continue;
-            L = fast_layout(a.coef_words, (int)sub_bytes, 32 * cd.rpl, a.pitch_words, 1 << cd.shift);
-            if (L.total <= budget) {
-                rpl = cd.rpl;
-                sub_rows = cd.sub;
-                slot_shift = cd.shift;
-                return true;
-            }
-        }
-    }
-    return false;
-}
-
-template <int C, int RPL>
-int launch_fast(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, const FastLayout& L, cudaStream_t s) {
-    KE_CUDA(cudaFuncSetAttribute(ke_phash_fast_kernel<C, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int per_sm = 0;
-    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_fast_kernel<C, RPL>, kFastThreads, L.total));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > a.n) grid = a.n;
-    ke_phash_fast_kernel<C, RPL><<<(unsigned)grid, kFastThreads, L.total, s>>>(a, sub_rows, slot_shift, 0);
-    ctx->launches++;
-    KE_CUDA(cudaGetLastError());
-    return KE_OK;
-}
-
-
-// ------------------------------------------------------------------ lanes = outputs tap pass (used by v4)
-//
-// Horizontal taps with the tap words in REGISTERS: lane = (output, segment of <= 8 sixteen-pixel
-// groups), warps walk rows.  Per row and pass of P <= 4 groups a lane issues P LDS.128 of pixels
-// (consecutive lanes read consecutive 16-byte groups: conflict free) and 12*P dp4a; no tap word
-// ever crosses shared memory, which was the limiter of the lanes=rows layout.
-
-template <int P>
-__device__ __forceinline__ void v3_pass(const PhashArgs& a, int task, int g, int2 lm, int lane, const uint8_t* s_luma,
-                                        int pitch_bytes, uint32_t* s_acc, int row_lo, int row_hi) {
-    uint4 c[P][3];
-#pragma unroll
-    for (int gg = 0; gg < P; ++gg)
-#pragma unroll
-        for (int p = 0; p < 3; ++p) c[gg][p] = __ldg(a.lt_coef + ((size_t)(task * 8 + g + gg) * 3 + p) * 32 + lane);
-    const uint8_t* px = s_luma + (size_t)(lm.y + g) * 16;
-    // two rows per iteration: 12 independent dp4a chains hide the accumulate latency
-    for (int r = row_lo; r < row_hi; r += 2) {
-        const bool two = r + 1 < row_hi;
-        const uint8_t* p0 = px + (size_t)r * pitch_bytes;
-        const uint8_t* p1 = two ? p0 + pitch_bytes : p0;
-        uint32_t d0 = 0u, d1 = 0u, e0 = 0u, e1 = 0u, f0 = 0u, f1 = 0u, h0 = 0u, h1 = 0u;
-        int32_t d2 = 0, e2 = 0, f2 = 0, h2 = 0;
-#pragma unroll
-        for (int gg = 0; gg < P; ++gg) {
-            const uint4 x = *reinterpret_cast<const uint4*>(p0 + gg * 16);
-            const uint4 y = *reinterpret_cast<const uint4*>(p1 + gg * 16);
-            d0 = dp4a_uu(x.x, c[gg][0].x, d0), d1 = dp4a_uu(x.x, c[gg][1].x, d1), d2 = dp4a_us(x.x, c[gg][2].x, d2);
-            f0 = dp4a_uu(y.x, c[gg][0].x, f0), f1 = dp4a_uu(y.x, c[gg][1].x, f1), f2 = dp4a_us(y.x, c[gg][2].x, f2);
-            e0 = dp4a_uu(x.y, c[gg][0].y, e0), e1 = dp4a_uu(x.y, c[gg][1].y, e1), e2 = dp4a_us(x.y, c[gg][2].y, e2);
-            h0 = dp4a_uu(y.y, c[gg][0].y, h0), h1 = dp4a_uu(y.y, c[gg][1].y, h1), h2 = dp4a_us(y.y, c[gg][2].y, h2);
-            d0 = dp4a_uu(x.z, c[gg][0].z, d0), d1 = dp4a_uu(x.z, c[gg][1].z, d1), d2 = dp4a_us(x.z, c[gg][2].z, d2);
-            f0 = dp4a_uu(y.z, c[gg][0].z, f0), f1 = dp4a_uu(y.z, c[gg][1].z, f1), f2 = dp4a_us(y.z, c[gg][2].z, f2);
-            e0 = dp4a_uu(x.w, c[gg][0].w, e0), e1 = dp4a_uu(x.w, c[gg][1].w, e1), e2 = dp4a_us(x.w, c[gg][2].w, e2);
-            h0 = dp4a_uu(y.w, c[gg][0].w, h0), h1 = dp4a_uu(y.w, c[gg][1].w, h1), h2 = dp4a_us(y.w, c[gg][2].w, h2);
-        }
-        if (lm.x >= 0) {
-            atomicAdd(&s_acc[r * kOuts + lm.x], (d0 + e0) + ((d1 + e1) << 8) + ((uint32_t)(d2 + e2) << 16));
-            if (two) atomicAdd(&s_acc[(r + 1) * kOuts + lm.x], (f0 + h0) + ((f1 + h1) << 8) + ((uint32_t)(f2 + h2) << 16));
-        }
-    }
-}
-
-// ------------------------------------------------------------------ warp-specialised kernel (v4)
-//
-// The CUDA-core fallback of v5 (dp4a taps instead of tensor-pipe MMAs) for the widths v5 does not take.  Running
-// load+luma (HBM bound on its own) and the tap phases (dp4a bound) one after the other overlaps them only by
-// accident, so the roles are split inside the CTA and decoupled through shared-memory rings:
-//     warps 8..9   luma warps        raw rows -> raw ring (1-D TMA issued by warp 8 / lane 0, a few
-//                                    sub-chunks ahead) -> luma chunk ring (2 x 32 rows)
-//     warps 0..7   tap warps         luma ring -> horizontal taps (v3 layout) -> clip -> vertical -> DCT
-// so the memory stream runs continuously behind the arithmetic.
-
-constexpr int kV4Tap = 8, kV4Luma = 2;
-constexpr int kV4Threads = (kV4Tap + kV4Luma) * 32;  // no producer warp: luma warp 0 / lane 0 issues the copies
-
-struct V4Layout {
-    int raw, luma, acc, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
-};
-
-__host__ __device__ inline V4Layout v4_layout(int sub_bytes, int pitch_bytes, int n_slots) {
-    V4Layout L;
-    int off = 0;
-    auto take = [&](int bytes, int align) {
-        off = (off + align - 1) / align * align;
-        int at = off;
-        off += bytes;
-        return at;
-    };
-    L.luma_bytes = (32 * pitch_bytes + 8 * 16 + 64 + 127) / 128 * 128;  // one chunk + slack for padded groups
-    L.raw = take(n_slots * sub_bytes, 128);
-    L.luma = take(2 * L.luma_bytes, 128);
-    L.acc = take(32 * kOuts * 4, 16);
-    L.hrow = take(32 * kOuts, 16);
-    L.x32 = take(1024, 16);
-    L.x98 = take(80, 16);
-    L.tmat = take(8 * 32 * 8, 16);
-    L.ymat = take(64 * 8, 16);
-    L.bar = take((2 * kMaxSlots + 4) * 8, 8);
-    L.total = off;
-    return L;
-}
-
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-template <int C>
-__global__ void __launch_bounds__(kV4Threads, 2) ke_phash_v4_kernel(const PhashArgs a, const int sub_rows,
-                                                                   const int slot_shift, const int pitch_bytes) {
-    constexpr int CR = 32, NW = kV4Tap;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int row_bytes = a.w * C;
-    const int sub_bytes = sub_rows * row_bytes;
-    const int n_slots = 1 << slot_shift;
-    const uint32_t slot_mask = (uint32_t)n_slots - 1u;
-    const V4Layout L = v4_layout(sub_bytes, pitch_bytes, n_slots);
-    uint8_t* s_raw = smem + L.raw;
-    uint8_t* s_luma = smem + L.luma;
-    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem + L.acc);
-    uint8_t* s_hrow = smem + L.hrow;
-    uint8_t* s_x32 = smem + L.x32;
-    uint8_t* s_x98 = smem + L.x98;
-    double* s_t = reinterpret_cast<double*>(smem + L.tmat);
-    double* s_y = reinterpret_cast<double*>(smem + L.ymat);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.bar);  // raw ring
-    uint64_t* s_empty = s_full + kMaxSlots;
-    uint64_t* l_full = s_empty + kMaxSlots;  // luma chunk ring [2]
-    uint64_t* l_empty = l_full + 2;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_sub = (a.h + sub_rows - 1) / sub_rows;
-    const int subs_per_chunk = CR / sub_rows;
-    const int pitch_words = pitch_bytes >> 2;
-
-    if (tid == 0) {
-        for (int b = 0; b < n_slots; ++b) {
-            mbar_init(&s_full[b], 1);
-            mbar_init(&s_empty[b], kV4Luma);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&l_full[b], kV4Luma);
-            mbar_init(&l_empty[b], kV4Tap);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < CR * kOuts; i += kV4Threads) s_acc[i] = 1u << (kPrec - 1);
-    for (int i = tid; i < 2 * L.luma_bytes / 4; i += kV4Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
-    __syncthreads();
-
-    if (warp >= kV4Tap) {
-        // ===== luma warps: raw rows -> (TMA) raw ring -> luma chunk ring =====
-        const int lw = warp - kV4Tap;
-        const long long my_images = blockIdx.x < a.n ? (a.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const long long total_seq = my_images * n_sub;
-        long long issued = 0;
-        auto issue_upto = [&](long long upto) {  // lane 0 of luma warp 0 only
-            for (; issued < upto && issued < total_seq; ++issued) {
-                const long long k = issued / n_sub;
-                const int s = (int)(issued - k * n_sub);
-                const int b = (int)(issued & slot_mask);
-                const int rows = min(sub_rows, a.h - s * sub_rows);
-                mbar_wait(&s_empty[b], (((uint32_t)(issued >> slot_shift)) & 1u) ^ 1u);
-                mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
-                bulk_g2s(s_raw + b * sub_bytes, a.img + (blockIdx.x + k * gridDim.x) * a.img_stride + (long long)s * sub_bytes,
-                         (uint32_t)(rows * row_bytes), &s_full[b]);
-            }
-        };
-        if (lw == 0 && lane == 0) issue_upto(n_slots - 1);
-        long long seq = 0;
-        uint32_t chunk = 0;
-        for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-            for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
-                const int lb = chunk & 1;
-                mbar_wait(&l_empty[lb], ((chunk >> 1) & 1u) ^ 1u);  // tap warps are done with this buffer
-                uint32_t* dst = reinterpret_cast<uint32_t*>(s_luma + lb * L.luma_bytes);
-                for (int s = 0; s < subs_per_chunk && r0 + s * sub_rows < a.h; ++s, ++seq) {
-                    if (lw == 0 && lane == 0) issue_upto(seq + n_slots);  // keep the ring n_slots-1 ahead
-                    __syncwarp();
-                    const int b = (int)(seq & slot_mask);
-                    const int srows = min(sub_rows, a.h - (r0 + s * sub_rows));
-                    mbar_wait(&s_full[b], ((uint32_t)(seq >> slot_shift)) & 1u);
-                    luma_rows_fast<C, kV4Luma>(s_raw + b * sub_bytes, dst + s * sub_rows * pitch_words, srows, a.w,
-                                               pitch_words, lw, lane);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive1(&s_empty[b]);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive1(&l_full[lb]);  // release: the chunk's luma rows are written
-            }
-        }
-        return;
-    }
-
-    // ===== tap warps =====
-    uint32_t chunk = 0;
-    VertState<NW> vs;
-    vertical_init(a, vs, lane, warp);
-    for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
-        vertical_reset(vs, lane);
-        for (int r0 = 0; r0 < a.h; r0 += CR, ++chunk) {
-            const int rows = min(CR, a.h - r0);
-            const int lb = chunk & 1;
-            const uint8_t* luma = s_luma + lb * L.luma_bytes;
-            mbar_wait(&l_full[lb], (chunk >> 1) & 1u);
-            for (int item = warp; item < a.n_wtasks * 4; item += NW) {
-                const int task = item >> 2, rg = item & 3;
-                const int row_lo = rg * 8, row_hi = min(row_lo + 8, rows);
-                if (row_lo >= row_hi) continue;
-                const int2 lm = __ldg(a.lt_meta + task * 32 + lane);
-                const int ng = __ldg(a.lt_ng + task);
-                for (int g = 0; g < ng; g += 4) {
-                    switch (min(4, ng - g)) {
-                        case 4: v3_pass<4>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                        case 3: v3_pass<3>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                        case 2: v3_pass<2>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                        default: v3_pass<1>(a, task, g, lm, lane, luma, pitch_bytes, s_acc, row_lo, row_hi); break;
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
-            compute_sync<NW>();
-            for (int i = tid; i < rows * kOuts; i += NW * 32) {
-                s_hrow[i] = clip8((int32_t)s_acc[i]);
-                s_acc[i] = 1u << (kPrec - 1);
-            }
-            compute_sync<NW>();
-            vertical_chunk(a, vs, s_hrow, r0, rows, lane, warp);
-            // s_hrow / s_acc are next written after the next chunk's two tap barriers
-        }
-        vertical_finish(vs, s_x32, s_x98, lane, warp);
-        compute_sync<NW>();
-        dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
-    }
-}
-
-template <int C>
-bool v4_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, V4Layout& L) {
-    const long long row_bytes = (long long)a.w * C;
-    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.n_wtasks < 1) return false;
-    pitch_bytes = a.w;
-    for (int sub : {8, 4, 2, 1}) {
-        if (sub * row_bytes > (1 << 20)) continue;
-        for (int shift : {2, 1}) {
-            L = v4_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift);
-            if (L.total <= 110 * 1024) {
-                sub_rows = sub;
-                slot_shift = shift;
-                return true;
-            }
-        }
-    }
-    return false;
-}
-
-template <int C>
-int launch_v4(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, const V4Layout& L,
-              cudaStream_t s) {
-    KE_CUDA(cudaFuncSetAttribute(ke_phash_v4_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int per_sm = 0;
-    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_v4_kernel<C>, kV4Threads, L.total));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > a.n) grid = a.n;
-    ke_phash_v4_kernel<C><<<(unsigned)grid, kV4Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes);
-    ctx->launches++;
-    KE_CUDA(cudaGetLastError());
-    return KE_OK;
-}
-
 
 // ------------------------------------------------------------------ tensor-core kernel (v5)
 //
@@ -1588,7 +900,7 @@ struct V5Layout {
     int raw, luma, bfrag, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
 };
 
-__host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, int n_slots, int mma_words /* of warps 4..7 */,
+__host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, int n_slots, int mma_words /* in shared memory */,
                                                   int nlb /* luma chunk buffers */) {
     V5Layout L;
     int off = 0;
@@ -1599,7 +911,7 @@ __host__ __device__ inline V5Layout v5_layout(int sub_bytes, int pitch_bytes, in
         return at;
     };
     L.luma_bytes = (32 * pitch_bytes + 127) / 128 * 128;
-    L.raw = take(n_slots * sub_bytes, 128);
+    L.raw = take(n_slots * slot_bytes, 128);
     L.luma = take(nlb * L.luma_bytes, 128);
     L.bfrag = take(mma_words * 8, 16);
     L.hrow = take(2 * kHCols * kHP, 16);
@@ -1710,18 +1022,99 @@ __device__ __forceinline__ void v5_taps_wide_reg(uint32_t a_addr, const uint2 (&
     }
 }
 
-template <int C>
-__global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows,
-                                                                   const int slot_shift, const int pitch_bytes,
-                                                                   const int nlb, const int dbg) {
+// Where the horizontal B fragments of a warp group live: registers (wide target only, <= kNKP k-steps), shared memory,
+// or global memory (L2-resident, for bands too long for shared memory next to the luma ring).
+enum { kBReg = 0, kBSmem = 1, kBGmem = 2 };
+
+struct V5Config {
+    int sub_rows, slot_shift, pitch_bytes, nlb;
+    int slot_bytes;  // stride of a raw slot: sub_rows * row_bytes, + slack for the aligned superset when !aligned
+    int aligned;     // base, images and rows on 16-byte boundaries and w % 16 == 0: exact copies, vector luma path
+    int wide_b, narrow_b;  // kBReg / kBSmem / kBGmem
+    int smem_words;  // uint2 words of B fragments kept in shared memory
+    int dbg;
+    V5Layout L;
+};
+
+// Wide-target taps with the B fragments behind a pointer (shared or global memory): bands of more than kNKP k-steps.
+__device__ __forceinline__ void v5_taps_wide_mem(uint32_t a_addr, const uint2* __restrict__ bw, int nk, int pitch_bytes,
+                                                 uint8_t* __restrict__ hrow, int out0, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        int32_t c[3][4];
+#pragma unroll
+        for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[tl][i] = tl == 0 ? (1 << (kPrec - 1)) : 0;
+#pragma unroll 4
+        for (int k = 0; k < nk; ++k) {
+            uint32_t a0[4];
+            ldmatrix_x4(a0, a_addr + k * 32 + rb * 16 * pitch_bytes);
+#pragma unroll
+            for (int tl = 0; tl < 3; ++tl) mma_u8s8(c[tl], a0, bw[(k * 3 + tl) * 32]);
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int32_t v0 = c[0][2 * hf] + (c[1][2 * hf] << 8) + (c[2][2 * hf] << 16);
+            const int32_t v1 = c[0][2 * hf + 1] + (c[1][2 * hf + 1] << 8) + (c[2][2 * hf + 1] << 16);
+            const int row = rb * 16 + hf * 8 + g;
+            hrow[(out0 + 2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
+            hrow[(out0 + 2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
+        }
+    }
+}
+
+// Luma of the rows lw, lw + NLW, ... of a raw sub-chunk that starts `off` bytes into a 16-byte aligned slot, for ANY
+// byte alignment of the rows (widths that are not a multiple of 16, odd image strides, sliced batches): aligned 32-bit
+// loads + funnel shifts.  RGB / L: a lane takes 4 pixels per step (word stride 3 / 1 between lanes: no bank conflicts);
+// RGBA: one pixel per lane.  Pixels past the row end are converted too (they land in the ring's padding, where every tap
+// is zero).
+template <int C, int NLW>
+__device__ __noinline__ void luma_rows_any(const uint8_t* __restrict__ slot, int off, uint8_t* __restrict__ luma, int rows,
+                                              int w, int row_bytes, int pitch_bytes, int lw, int lane) {
+    for (int r = lw; r < rows; r += NLW) {
+        const int o = off + r * row_bytes;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(slot + (o & ~3));
+        const uint32_t sh = (uint32_t)(o & 3) * 8u;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(luma + r * pitch_bytes);
+        if (C == 3) {
+            const int nq = (w + 3) >> 2;
+            for (int q = lane; q < nq; q += 32) {
+                const uint32_t* p = src + 3 * q;
+                const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3];
+                dst[q] = luma4_rgb(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh));
+            }
+        } else if (C == 4) {
+            constexpr uint32_t RG = 19595u | (38470u << 16), B_ = 7471u;
+            for (int x = lane; x < w; x += 32) {
+                const uint32_t px = __funnelshift_r(src[x], src[x + 1], sh);
+                luma[r * pitch_bytes + x] = (uint8_t)(dp2a_hi(B_, px, dp2a_lo(RG, px, 0x8000u)) >> 16);
+            }
+        } else {
+            const int nq = (w + 3) >> 2;
+            for (int q = lane; q < nq; q += 32) dst[q] = __funnelshift_r(src[q], src[q + 1], sh);
+        }
+    }
+}
+
+// BMEM = false: wide-target fragments in registers, narrow-target ones in shared memory (widths up to ~512: the
+// benchmark geometry; identical to the round-1 kernel).  BMEM = true: both behind pointers into shared or global memory.
+template <int C, bool BMEM>
+__global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const V5Config cfg) {
     constexpr int CR = 32, NW = kV5Tap;
     extern __shared__ __align__(128) uint8_t smem[];
+    const int sub_rows = cfg.sub_rows, slot_shift = cfg.slot_shift, pitch_bytes = cfg.pitch_bytes, nlb = cfg.nlb, dbg = cfg.dbg;
     const int row_bytes = a.w * C;
     const int sub_bytes = sub_rows * row_bytes;
+    const int slot_bytes = cfg.slot_bytes;
     const int n_slots = 1 << slot_shift;
     const uint32_t slot_mask = (uint32_t)n_slots - 1u;
-    const int b_first = a.mma_boff[4];  // the wide-target warps' fragments live in registers, not here
-    const V5Layout L = v5_layout(sub_bytes, pitch_bytes, n_slots, a.mma_words - b_first, nlb);
+    // B fragments in shared memory: [wide-target warps 0..3 when cfg.wide_b == kBSmem][narrow-target warps 4..7 when
+    // cfg.narrow_b == kBSmem], in table order
+    const int b_first = cfg.wide_b == kBSmem ? 0 : a.mma_boff[4];
+    const int b_last = cfg.narrow_b == kBSmem ? a.mma_words : a.mma_boff[4];
+    const V5Layout& L = cfg.L;
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
@@ -1752,7 +1145,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < a.mma_words - b_first; i += kV5Threads) s_b[i] = __ldg(a.mma_b + b_first + i);
+    for (int i = tid; i < b_last - b_first; i += kV5Threads) s_b[i] = __ldg(a.mma_b + b_first + i);
     for (int i = tid; i < nlb * L.luma_bytes / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_luma)[i] = 0u;
     for (int i = tid; i < 2 * kHCols * kHP / 4; i += kV5Threads) reinterpret_cast<uint32_t*>(s_hrow)[i] = 0u;
     __syncthreads();
@@ -1770,9 +1163,15 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             const uint32_t k = q / (uint32_t)n_sub, sq = q - k * (uint32_t)n_sub;
             const int b = (int)(q & slot_mask);
             const int rows = min(sub_rows, a.h - (int)sq * sub_rows);
-            mbar_expect_tx(&s_full[b], (uint32_t)(rows * row_bytes));
-            bulk_g2s(s_raw + b * sub_bytes, a.img + (blockIdx.x + (long long)k * gridDim.x) * a.img_stride + (long long)sq * sub_bytes,
-                     (uint32_t)(rows * row_bytes), &s_full[b]);
+            const uint8_t* src = a.img + (blockIdx.x + (long long)k * gridDim.x) * a.img_stride + (long long)sq * sub_bytes;
+            uint32_t bytes = (uint32_t)(rows * row_bytes);
+            if (!cfg.aligned) {  // the 16-byte aligned superset of the sub-chunk (bulk copies move whole 16-byte units)
+                const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+                src -= lead;
+                bytes = (lead + bytes + 15u) & ~15u;
+            }
+            mbar_expect_tx(&s_full[b], bytes);
+            bulk_g2s(s_raw + b * slot_bytes, src, bytes, &s_full[b]);
         };
         auto release = [&](uint32_t seq_, int b) {  // lane 0, after the warp's reads of slot b (ordered by __syncwarp)
             uint32_t old;  // acq_rel: the warp's reads are ordered before the count, the refill after the last count
@@ -1783,7 +1182,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             for (uint32_t q = 0; q < (uint32_t)n_slots && q < total_seq; ++q) issue(q);
         // early release: when a warp's share of a sub-chunk (<= 2 rows of <= 512 pixels) fits its registers the
         // raw slot is handed back right after the loads, before the arithmetic
-        const bool early = a.w <= 512 && !(dbg & 16);  // 16 pixels (RGB, L) or 4 x 4 pixels (RGBA) per lane cover a row
+        const bool early = cfg.aligned && a.w <= 512 && !(dbg & 16);  // 16 pixels (RGB, L) or 4 x 4 pixels (RGBA) per lane cover a row
         const int ng = a.w >> 4;
         const bool act = lane < ng;
         uint32_t seq = 0;
@@ -1806,7 +1205,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                         // of the last pair costs more in the luma warps than the earlier refill gains)
                         for (int rr = lw; rr < srows; rr += 2 * kV5Luma) {
                             const bool r_two = rr + kV5Luma < srows;
-                            const uint8_t* s0 = s_raw + b * sub_bytes + rr * row_bytes;
+                            const uint8_t* s0 = s_raw + b * slot_bytes + rr * row_bytes;
                             const uint8_t* s1 = s0 + kV5Luma * row_bytes;
                             uint8_t* d0 = dst8 + (s * sub_rows + rr) * pitch_bytes;
                             uint8_t* d1 = d0 + kV5Luma * pitch_bytes;
@@ -1845,14 +1244,22 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                         }
                         __syncwarp();  // (a warp without rows in a short last sub-chunk still counts as a reader)
                         if (lane == 0) release(seq, b);
-                    } else {
+                    } else if (cfg.aligned) {
                         if (C == 3)
-                            luma_rows_rgb16<kV5Luma>(s_raw + b * sub_bytes, dst8 + s * sub_rows * pitch_bytes, srows, a.w,
+                            luma_rows_rgb16<kV5Luma>(s_raw + b * slot_bytes, dst8 + s * sub_rows * pitch_bytes, srows, a.w,
                                                      row_bytes, pitch_bytes, lw, lane);
                         else
-                            luma_rows_fast<C, kV5Luma>(s_raw + b * sub_bytes,
+                            luma_rows_fast<C, kV5Luma>(s_raw + b * slot_bytes,
                                                        reinterpret_cast<uint32_t*>(dst8) + s * sub_rows * pitch_words, srows,
                                                        a.w, pitch_words, lw, lane);
+                        __syncwarp();
+                        if (lane == 0) release(seq, b);
+                    } else {
+                        // rows at any byte alignment: where the sub-chunk starts inside its slot follows from its address
+                        const long long g0 = im * a.img_stride + (long long)(r0 + s * sub_rows) * row_bytes;
+                        const int lead = (int)(reinterpret_cast<uintptr_t>(a.img + g0) & 15u);
+                        luma_rows_any<C, kV5Luma>(s_raw + b * slot_bytes, lead, dst8 + s * sub_rows * pitch_bytes, srows, a.w,
+                                                  row_bytes, pitch_bytes, lw, lane);
                         __syncwarp();
                         if (lane == 0) release(seq, b);
                     }
@@ -1877,12 +1284,17 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         // the vertical pass of exactly those eight columns (both 16-row halves of the 32x32 plane).  It reads back only
         // what it wrote itself, so it never meets another tap warp before the image is finished.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kV5WideRegs));
-        uint2 breg[kNKP][3];
+        uint2 breg[BMEM ? 1 : kNKP][3];
+        if (!BMEM) {
 #pragma unroll
-        for (int k = 0; k < kNKP; ++k)
+            for (int k = 0; k < (BMEM ? 1 : kNKP); ++k)
 #pragma unroll
-            for (int tl = 0; tl < 3; ++tl)
-                breg[k][tl] = k < a.mma_nk[warp] ? __ldg(a.mma_b + a.mma_boff[warp] + (k * 3 + tl) * 32 + lane) : make_uint2(0u, 0u);
+                for (int tl = 0; tl < 3; ++tl)
+                    breg[k][tl] = k < a.mma_nk[warp] ? __ldg(a.mma_b + a.mma_boff[warp] + (k * 3 + tl) * 32 + lane) : make_uint2(0u, 0u);
+        }
+        // BMEM: bands of more than kNKP k-steps (widths above ~512) — fragments from shared memory, or from global memory
+        // (L2) when they do not fit next to the luma ring
+        const uint2* bmem = (cfg.wide_b == kBSmem ? s_b + (a.mma_boff[warp] - b_first) : a.mma_b + a.mma_boff[warp]) + lane;
         uint8_t* hrow = s_hrow;  // columns 8q..8q+7 of plane 0 are this warp's private scratch
         const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + (8 * warp + g) * kHP);
         int32_t vc[2][3][4];
@@ -1898,7 +1310,11 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             int ci = 0;
             for (int r0 = 0; r0 < a.h; r0 += CR, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
                 mbar_wait_sleep(&l_full[lb], lph, poll_ns);
-                v5_taps_wide_reg(smem_u32(s_luma + lb * L.luma_bytes) + a_off, breg, nk, pitch_bytes, hrow, 8 * warp, lane);
+                {
+                    const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
+                    if constexpr (!BMEM) v5_taps_wide_reg(a_addr, breg, nk, pitch_bytes, hrow, 8 * warp, lane);
+                    else v5_taps_wide_mem(a_addr, bmem, nk, pitch_bytes, hrow, 8 * warp, lane);
+                }
                 __syncwarp();  // the eight columns are written
                 if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
                 if (!(dbg & 4)) {
@@ -1934,6 +1350,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     // are cheap, and no tap warp waits for another before the image is finished.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5NarrowRegs));
     const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
+    if (BMEM && cfg.narrow_b == kBGmem) bw = a.mma_b + a.mma_boff[warp] + lane;
     uint8_t* scr = s_hrow + kHCols * kHP;                 // plane 1
     const int scr_col = 8 * (warp - 4);                   // this warp's private columns scr_col .. scr_col + 7
     const uint32_t* col = reinterpret_cast<const uint32_t*>(scr + (scr_col + g) * kHP);
@@ -1979,41 +1396,55 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 }
 
 template <int C>
-bool v5_config(const PhashArgs& a, int& sub_rows, int& slot_shift, int& pitch_bytes, int& nlb, V5Layout& L) {
+bool v5_config(const PhashArgs& a, V5Config& cfg) {
     const long long row_bytes = (long long)a.w * C;
-    if (!a.use_bulk || (row_bytes & 15) || (a.img_stride & 15) || (a.w & 15) || a.mma_words < 1 || !a.vmma) return false;
-    for (int q = 0; q < 4; ++q)
-        if (a.mma_nk[q] > kNKP) return false;  // wide-target B fragments must fit the register file
-    pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
+    if (a.row_stride != row_bytes || a.mma_words < 1 || !a.vmma) return false;  // strided rows: generic kernel
+    cfg.aligned = (row_bytes & 15) == 0 && (a.img_stride & 15) == 0 && (a.w & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a.img) & 15) == 0;
+    int nk_wide = 0, nk_narrow = 0;
+    for (int q = 0; q < 4; ++q) nk_wide = std::max(nk_wide, a.mma_nk[q]), nk_narrow = std::max(nk_narrow, a.mma_nk[4 + q]);
+    cfg.pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
+    cfg.dbg = 0;
     int want_sub = 16, want_shift = 1, want_nlb = 2;
 #ifdef KE_TUNING_PROBES
     if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d,%d", &want_sub, &want_shift, &want_nlb);  // tuning override
 #endif
-    if (want_nlb < 2 || want_nlb > kMaxLumaBufs) want_nlb = 2;
-    for (int sub : {want_sub, 8, 4, 2, 1}) {
-        if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
-        for (int shift : {want_shift, 2, 1}) {
-            if (shift < 1 || shift > 3) continue;
-            for (int bufs : {want_nlb, 2}) {
-                L = v5_layout((int)(sub * row_bytes), pitch_bytes, 1 << shift, a.mma_words - a.mma_boff[4], bufs);
-                if (L.total <= 113 * 1024 && a.n * ((a.h + sub - 1) / sub) < (1ll << 31)) {
-                    sub_rows = sub;
-                    slot_shift = shift;
-                    nlb = bufs;
-                    return true;
+    if (want_nlb < 1 || want_nlb > kMaxLumaBufs) want_nlb = 2;
+    const int wide_words = a.mma_boff[4], narrow_words = a.mma_words - a.mma_boff[4];
+    // Preference: two CTAs per SM (<= 113 KB) with the fragments on chip, then one CTA per SM (<= 227 KB), moving the
+    // fragments out to global memory (L2) and the luma ring down to one buffer only when nothing else fits.
+    struct Place { int wide, narrow; };
+    const Place places[] = {{nk_wide <= kNKP ? kBReg : kBSmem, kBSmem}, {nk_wide <= kNKP ? kBReg : kBGmem, kBSmem},
+                            {nk_wide <= kNKP ? kBReg : kBGmem, kBGmem}};
+    for (int budget : {113 * 1024, 227 * 1024})
+        for (const Place& pl : places)
+            for (int bufs : {want_nlb, 2, 1})
+                for (int sub : {want_sub, 8, 4, 2, 1}) {
+                    if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
+                    if (a.n * ((a.h + sub - 1) / sub) >= (1ll << 31)) continue;
+                    for (int shift : {want_shift, 2, 1}) {
+                        if (shift < 1 || shift > 3) continue;
+                        // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the
+                        // luma loads that run a few words past the last pixel
+                        const int slot = (int)((sub * row_bytes + (cfg.aligned ? 0 : 64) + 127) / 128 * 128);
+                        const int words = (pl.wide == kBSmem ? wide_words : 0) + (pl.narrow == kBSmem ? narrow_words : 0);
+                        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs);
+                        if (L.total > budget) continue;
+                        cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot;
+                        cfg.wide_b = pl.wide, cfg.narrow_b = pl.narrow, cfg.smem_words = words, cfg.L = L;
+                        return true;
+                    }
                 }
-            }
-        }
-    }
     return false;
 }
 
 template <int C>
-int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int pitch_bytes, int nlb, const V5Layout& L,
-              cudaStream_t s) {
-    KE_CUDA(cudaFuncSetAttribute(ke_phash_v5_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+int launch_v5(ke_ctx* ctx, const PhashArgs& a, V5Config& cfg, cudaStream_t s) {
+    const bool bmem = !(cfg.wide_b == kBReg && cfg.narrow_b == kBSmem);
+    auto kernel = bmem ? ke_phash_v5_kernel<C, true> : ke_phash_v5_kernel<C, false>;
+    KE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.L.total));
     int per_sm = 0;
-    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke_phash_v5_kernel<C>, kV5Threads, L.total));
+    KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kV5Threads, cfg.L.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > a.n) grid = a.n;
@@ -2022,7 +1453,8 @@ int launch_v5(ke_ctx* ctx, const PhashArgs& a, int sub_rows, int slot_shift, int
     if (const char* dbg_env = getenv("KE_PHASH_DBG")) dbg = atoi(dbg_env) & 0xFF;  // bit 2: no horizontal MMA, 4: no vertical pass, ...
     if (const char* ns_env = getenv("KE_PHASH_SLEEP")) ns = atoi(ns_env);
 #endif
-    ke_phash_v5_kernel<C><<<(unsigned)grid, kV5Threads, L.total, s>>>(a, sub_rows, slot_shift, pitch_bytes, nlb, dbg | (ns << 8));
+    cfg.dbg = dbg | (ns << 8);
+    kernel<<<(unsigned)grid, kV5Threads, cfg.L.total, s>>>(a, cfg);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;
@@ -2047,28 +1479,12 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // (two CTAs per SM); shrink further until it fits the 227 KB hardware limit.
     const long long row_bytes = (long long)a.w * C;
     a.pitch_words = ((a.w + 3) / 4) | 1;
-    // Kernel ladder, fastest first; each config function says whether its kernel takes the shape:
-    //   v5 (tensor-pipe resamples, 7.5 M img/s at 512x512x3) -> v4 (same rings, dp4a taps: 2.2 M) -> fast (lanes = rows,
-    //   widths that are not a multiple of 16: 2.0 M) -> generic (strided / unaligned / very wide rows).
-    const int ladder = ctx->phash_ladder;  // KE_OPT_PHASH_LADDER (tests): 0 = from the top, 1 = skip v5, 2 = skip v5 and v4
-    if (!ctx->force_generic_phash && ladder == 0) {
-        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0, nlb = 2;
-        V5Layout VL;
-        if (v5_config<C>(a, sub_rows, slot_shift, pitch_bytes, nlb, VL))
-            return launch_v5<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, nlb, VL, s);
-    }
-    if (!ctx->force_generic_phash && ladder <= 1) {
-        int sub_rows = 0, slot_shift = 1, pitch_bytes = 0;
-        V4Layout VL;
-        if (v4_config<C>(a, sub_rows, slot_shift, pitch_bytes, VL))
-            return launch_v4<C>(ctx, a, sub_rows, slot_shift, pitch_bytes, VL, s);
-    }
-    {
-        int rpl = 0, sub_rows = 0, slot_shift = 1;
-        FastLayout FL;
-        if (!ctx->force_generic_phash && fast_config<C>(a, rpl, sub_rows, slot_shift, FL))
-            return rpl == 2 ? launch_fast<C, 2>(ctx, a, sub_rows, slot_shift, FL, s)
-                            : launch_fast<C, 1>(ctx, a, sub_rows, slot_shift, FL, s);
+    // Two kernels: the streaming tensor-pipe kernel (v5) takes every batch of contiguous rows whose resample band fits
+    // its fragment budget — any width, any byte alignment; the generic kernel takes the rest (strided rows, very wide
+    // images) and is the in-library reference the parity tests compare v5 with (KE_OPT_PHASH_GENERIC).
+    if (!ctx->force_generic_phash) {
+        V5Config cfg;
+        if (v5_config<C>(a, cfg)) return launch_v5<C>(ctx, a, cfg, s);
     }
     int rc_rows = 32;
     SmemLayout L;
@@ -2129,12 +1545,6 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     a.use_bulk = (row_stride == (int64_t)w * c) && ((reinterpret_cast<uintptr_t>(d_img) & 15) == 0);
     a.coef = ht->d_coef;
     a.items = ht->d_items;
-    a.bal = ht->d_bal;
-    a.n_bal = ht->n_bal;
-    a.lt_coef = ht->d_lt_coef;
-    a.lt_meta = ht->d_lt_meta;
-    a.lt_ng = ht->d_lt_ng;
-    a.n_wtasks = ht->n_wtasks;
     a.mma_b = ht->d_mma_b;
     a.mma_words = ht->mma_words;
     for (int i = 0; i < 8; ++i) a.mma_k0[i] = ht->mma_k0[i], a.mma_nk[i] = ht->mma_nk[i], a.mma_boff[i] = ht->mma_boff[i];

@@ -16,12 +16,11 @@ KE_OPT_PHASH_GENERIC = 1
 KE_OPT_JOIN_MODE = 2
 KE_OPT_SSIM_V1 = 3
 KE_OPT_RESIZE_GENERIC = 4
-KE_OPT_PHASH_LADDER = 5
 KE_ABI_VERSION = 2
 
 _LIB_PATH = Path(__file__).resolve().parent / "libkobato_b200.so"
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()  # re-entrant: group() builds Context objects (which call load()) while holding it
 
 
 class KobatoNativeError(RuntimeError):

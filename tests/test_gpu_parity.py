@@ -363,32 +363,45 @@ def test_ssim_both_kernels_agree_with_the_oracle():
         assert abs(got["v2"][-1] - 1.0) < 1e-6
 
 
-def test_phash_fast_and_generic_kernels_agree():
-    """K1 has two kernels (fast: aligned contiguous rows; generic: everything else); on geometries both
-    accept they must produce identical planes and hashes."""
+def test_phash_streaming_and_generic_kernels_agree():
+    """K1 has two kernels (v5: the streaming tensor-pipe kernel, every batch of contiguous rows; generic: strided rows
+    and the reference inside the library): identical planes, hashes and margins on every geometry — widths that are not a
+    multiple of 16 or 4, rows / images off the 16-byte grid, bands whose fragments live in registers (<= ~512 px), in
+    shared memory (~1024 px) and in L2 (2048, 4096 px), upscales, one-row and one-column-block images."""
     torch = _torch()
     from kobato_b200 import _native as nat
-
-    import os
 
     ctx = nat.context(torch.cuda.current_device())
     for (h, w, c, n) in ((512, 512, 3, 300), (96, 160, 3, 40), (200, 64, 4, 20), (130, 256, 1, 20), (1100, 1024, 3, 6),
                          (70, 100, 3, 9), (512, 512, 1, 64), (512, 512, 4, 64), (300, 256, 3, 40), (31, 48, 3, 17), (640, 480, 3, 20), (8, 16, 3, 5), (17, 512, 3, 300), (33, 512, 1, 40), (512, 16, 4, 33), (100, 496, 3, 7),
-                         (1, 32, 3, 3), (47, 512, 4, 1), (2048, 32, 3, 3)):
+                         (1, 32, 3, 3), (47, 512, 4, 1), (2048, 32, 3, 3),
+                         (33, 47, 3, 11), (100, 33, 1, 7), (61, 501, 3, 9), (45, 250, 4, 5), (64, 7, 3, 4), (9, 9, 1, 3),
+                         (300, 1536, 3, 5), (256, 2048, 3, 4), (130, 1000, 1, 6), (96, 4096, 1, 2), (77, 1201, 3, 3),
+                         (64, 3000, 4, 2), (1536, 2048, 3, 2)):
         imgs = ops.synth_images_device(0, n, h, w, c, n_set=n)
+        got = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
+        if w > 2048:  # beyond the generic kernel's shared-memory reach: the CPU oracle is the reference
+            host = imgs.cpu().numpy()
+            for k in range(n):
+                wp, wd, wm, p32, p98 = oracle.signature(host[k])
+                assert np.array_equal(got[3][0][k].cpu().numpy(), p32) and np.array_equal(got[3][1][k].cpu().numpy(), p98), (h, w, c)
+                assert int(got[0][k].item()) & U64 == wp and int(got[1][k].item()) & U64 == wd, (h, w, c)
+            continue
         ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
         try:
             gen = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
         finally:
             ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
-        for kernel in (0, 1, 2):  # start of the kernel ladder: v5, v4, fast; the library falls back by itself when a kernel does not take the shape
-            ctx.set_option(nat.KE_OPT_PHASH_LADDER, kernel)
-            try:
-                got = ops.phash_dhash_batch(imgs, want_margin=True, want_planes=True)
-            finally:
-                ctx.set_option(nat.KE_OPT_PHASH_LADDER, 0)
-            assert torch.equal(got[0], gen[0]) and torch.equal(got[1], gen[1]) and torch.equal(got[2], gen[2]), kernel
-            assert torch.equal(got[3][0], gen[3][0]) and torch.equal(got[3][1], gen[3][1]), kernel
+        assert torch.equal(got[3][0], gen[3][0]) and torch.equal(got[3][1], gen[3][1]), (h, w, c)
+        assert torch.equal(got[0], gen[0]) and torch.equal(got[1], gen[1]) and torch.equal(got[2], gen[2]), (h, w, c)
+        if n > 2:  # a batch that starts off the 16-byte grid (a slice of a larger tensor)
+            flat = torch.empty(imgs.numel() + 64, dtype=torch.uint8, device=imgs.device)
+            for shift in (1, 4, 13):
+                view = flat[shift:shift + imgs.numel()].view(imgs.shape)
+                view.copy_(imgs)
+                off = ops.phash_dhash_batch(view, want_planes=True)
+                assert torch.equal(off[0], gen[0]) and torch.equal(off[1], gen[1]), (h, w, c, shift)
+                assert torch.equal(off[2][0], gen[3][0]) and torch.equal(off[2][1], gen[3][1]), (h, w, c, shift)
 
 
 @pytest.mark.parametrize("mode", [2, 3])

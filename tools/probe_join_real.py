@@ -66,9 +66,9 @@ k2 = timed(lambda: ops.hamming_join_device(real, 8, require_band=True, part_inde
 
 def both():
     side.wait_stream(torch.cuda.current_stream())
+    ops.phash_dhash_batch(bank)  # asynchronous on the main stream; the join's count read-back below only waits for `side`
     with torch.cuda.stream(side):
         ops.hamming_join_device(real, 8, require_band=True, part_index=0, part_count=world, capacity=1 << 24)
-    ops.phash_dhash_batch(bank)
     torch.cuda.current_stream().wait_stream(side)
 
 
