@@ -156,6 +156,19 @@ int ke_luma_planes(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, int c, int6
                    const int64_t* d_idx, int64_t n, uint8_t* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * N2 — the matching half of dup.refine._compute_orb_ratio (src/dup/refine.py:55-68):
+ *     matches = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db);  ratio = len(matches) / min(len(kpa), len(kpb))
+ * batched over pairs.  d_desc holds 256-bit ORB descriptors (32 bytes each, 16-byte aligned); pair p matches the
+ * d_cnt_a[p] query descriptors starting at row d_off_a[p] against the d_cnt_b[p] train descriptors at row d_off_b[p]
+ * (max_a / max_b = the largest such counts).  A match is a MUTUAL nearest neighbour in Hamming distance, the first index
+ * winning ties on either side — OpenCV's cross-check.  d_n_matches[p] = len(matches); d_match_train / d_match_dist
+ * (nullable, [n_pairs][max_a]) = trainIdx / distance of query i or -1.  The FAST/Harris detector and the rBRIEF
+ * descriptor stay with OpenCV on the host. */
+int ke_orb_match_pairs(ke_ctx* ctx, const uint8_t* d_desc, const int64_t* d_off_a, const int32_t* d_cnt_a,
+                       const int64_t* d_off_b, const int32_t* d_cnt_b, int64_t n_pairs, int max_a, int max_b,
+                       int32_t* d_n_matches, int32_t* d_match_train, int32_t* d_match_dist, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * N1 — the refinement the shipped UI runs after a scan (SURVEY §8f "next" row): tile aHash and
  * small-gray pixel MAE of ui.dup_refine_parallel (src/ui/dup_refine_parallel.py).
  *

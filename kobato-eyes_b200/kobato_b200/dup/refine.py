@@ -79,8 +79,9 @@ def _compute_ssim(img_a: Image.Image, img_b: Image.Image) -> float:
     return float(ops.ssim_pairs(pa, pb)[0])
 
 
-def _compute_orb_ratio(img_a: Image.Image, img_b: Image.Image) -> float:
-    """ORB + brute-force Hamming cross-check ratio (reference :55-68).  Host / OpenCV by scope."""
+def _orb_descriptors(img_a: Image.Image, img_b: Image.Image):
+    """ORB detect + describe of both images (reference :57-61; OpenCV on the host): ``(len(kpa), da, len(kpb), db)``
+    with ``None`` descriptors where the reference returns 0.0 early."""
     import cv2
 
     ga, gb = np.asarray(img_a.convert("L")), np.asarray(img_b.convert("L"))
@@ -88,11 +89,23 @@ def _compute_orb_ratio(img_a: Image.Image, img_b: Image.Image) -> float:
     kpa, da = orb.detectAndCompute(ga, None)
     kpb, db = orb.detectAndCompute(gb, None)
     if da is None or db is None or not kpa or not kpb:
+        return 0, None, 0, None
+    return len(kpa), da, len(kpb), db
+
+
+def _orb_ratio_from_matches(n_matches: int, n_kpa: int, n_kpb: int) -> float:
+    return float(n_matches / min(n_kpa, n_kpb)) if n_matches and n_kpa and n_kpb else 0.0
+
+
+def _compute_orb_ratio(img_a: Image.Image, img_b: Image.Image) -> float:
+    """ORB + brute-force Hamming cross-check ratio (reference :55-68): detector / descriptor by OpenCV on the host, the
+    cross-checked brute-force match (``cv2.BFMatcher(NORM_HAMMING, crossCheck=True)``) on the GPU."""
+    from .. import ops
+
+    n_kpa, da, n_kpb, db = _orb_descriptors(img_a, img_b)
+    if da is None:
         return 0.0
-    matches = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db)
-    if not matches:
-        return 0.0
-    return float(len(matches) / min(len(kpa), len(kpb)))
+    return _orb_ratio_from_matches(int(ops.orb_match_pairs([da], [db])[0]), n_kpa, n_kpb)
 
 
 def _decide(file_id_a, file_id_b, ssim_value, orb_ratio, errors, cfg: RefinementThresholds) -> RefinedMatch:
@@ -160,7 +173,7 @@ def _refine_chunk(pairs, cfg: RefinementThresholds, max_workers, use_orb) -> lis
             logger.warning("SSIM refinement failed for %s and %s: %s", pa, pb, exc)
         if use_orb:
             try:
-                rec["orb"] = _compute_orb_ratio(ia, ib)
+                rec["orb_desc"] = _orb_descriptors(ia, ib)  # matched below, all pairs of the round in one launch
             except Exception as exc:
                 logger.warning("ORB refinement failed for %s and %s: %s", pa, pb, exc)
                 rec["orb_failed"] = True
@@ -168,6 +181,18 @@ def _refine_chunk(pairs, cfg: RefinementThresholds, max_workers, use_orb) -> lis
 
     with ThreadPoolExecutor(max_workers=workers) as pool:
         prepared = list(pool.map(prepare, pairs))
+
+    if use_orb:
+        todo = [k for k, rec in enumerate(prepared) if rec is not None and "orb_desc" in rec]
+        try:
+            counts = ops.orb_match_pairs([prepared[k]["orb_desc"][1] for k in todo], [prepared[k]["orb_desc"][3] for k in todo])
+            for k, m in zip(todo, counts.tolist()):
+                n_kpa, _, n_kpb, _ = prepared[k]["orb_desc"]
+                prepared[k]["orb"] = _orb_ratio_from_matches(int(m), n_kpa, n_kpb)
+        except Exception as exc:
+            logger.warning("ORB refinement failed for %d pair(s): %s", len(todo), exc)
+            for k in todo:
+                prepared[k]["orb_failed"] = True
 
     ssim_values: list[float | None] = [None] * len(pairs)
     groups: dict[tuple[int, int], list[int]] = {}

@@ -437,6 +437,62 @@ def synth_images_device(start: int, count: int, h: int, w: int, c: int = 3, *, n
     return out if c > 1 else out[..., 0]
 
 
+def orb_match_pairs(desc_a: list, desc_b: list, *, want_matches: bool = False):
+    """``len(cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db))`` for a batch of descriptor-set pairs
+    (reference src/dup/refine.py:64-67): ``desc_a[p]`` / ``desc_b[p]`` are uint8 ``[n, 32]`` ORB descriptor arrays (or
+    None / empty -> 0 matches).  Returns an int32 numpy array ``[n_pairs]``; with ``want_matches`` also the list of
+    ``(queryIdx, trainIdx, distance)`` triples per pair, sorted by queryIdx."""
+    torch = _torch()
+    lib = nat.load()
+    n_pairs = len(desc_a)
+    if len(desc_b) != n_pairs:
+        raise ValueError("desc_a and desc_b must have the same length")
+    counts = np.zeros(n_pairs, np.int32)
+    live, rows, off_a, off_b, cnt_a, cnt_b = [], [], [], [], [], []
+    at = 0
+    for p, (da, db) in enumerate(zip(desc_a, desc_b)):
+        if da is None or db is None or len(da) == 0 or len(db) == 0:
+            continue
+        da = np.ascontiguousarray(da, np.uint8)
+        db = np.ascontiguousarray(db, np.uint8)
+        if da.ndim != 2 or db.ndim != 2 or da.shape[1] != 32 or db.shape[1] != 32:
+            raise ValueError("descriptors must be uint8 [n, 32]")
+        live.append(p)
+        off_a.append(at), cnt_a.append(len(da))
+        at += len(da)
+        off_b.append(at), cnt_b.append(len(db))
+        at += len(db)
+        rows += [da, db]
+    matches = [[] for _ in range(n_pairs)] if want_matches else None
+    if not live:
+        return (counts, matches) if want_matches else counts
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_desc = torch.from_numpy(np.concatenate(rows)).to(dev)
+    t_off_a = torch.tensor(off_a, dtype=torch.int64, device=dev)
+    t_off_b = torch.tensor(off_b, dtype=torch.int64, device=dev)
+    t_cnt_a = torch.tensor(cnt_a, dtype=torch.int32, device=dev)
+    t_cnt_b = torch.tensor(cnt_b, dtype=torch.int32, device=dev)
+    max_a, max_b = max(cnt_a), max(cnt_b)
+    out = torch.empty(len(live), dtype=torch.int32, device=dev)
+    m_train = torch.empty((len(live), max_a), dtype=torch.int32, device=dev) if want_matches else None
+    m_dist = torch.empty((len(live), max_a), dtype=torch.int32, device=dev) if want_matches else None
+    ctx = nat.context(dev.index)
+    with ctx.lock:
+        nat.check(lib.ke_orb_match_pairs(ctx.handle, d_desc.data_ptr(), t_off_a.data_ptr(), t_cnt_a.data_ptr(),
+                                         t_off_b.data_ptr(), t_cnt_b.data_ptr(), len(live), max_a, max_b, out.data_ptr(),
+                                         m_train.data_ptr() if want_matches else None,
+                                         m_dist.data_ptr() if want_matches else None, _stream_ptr(dev.index)),
+                  "ke_orb_match_pairs")
+    counts[np.asarray(live)] = out.cpu().numpy()
+    if want_matches:
+        tr, ds = m_train.cpu().numpy(), m_dist.cpu().numpy()
+        for k, p in enumerate(live):
+            q = np.flatnonzero(tr[k, :cnt_a[k]] >= 0)
+            matches[p] = [(int(i), int(tr[k, i]), int(ds[k, i])) for i in q]
+        return counts, matches
+    return counts
+
+
 def luma_planes(bank, idx):
     """``convert("L")`` planes of ``bank[idx]`` (Pillow rgb2l; reference src/dup/refine.py:48-49) -> uint8 CUDA tensor
     ``[len(idx), h, w]``."""

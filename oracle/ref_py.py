@@ -355,6 +355,26 @@ def compute_ssim(img_a, img_b) -> float:
     return ssim_of_planes(*ssim_planes(img_a, img_b))
 
 
+def orb_cross_check(da: np.ndarray, db: np.ndarray) -> list[tuple[int, int, int]]:
+    """What ``cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db)`` returns (src/dup/refine.py:64) as sorted
+    ``(queryIdx, trainIdx, distance)`` triples: the MUTUAL nearest neighbours in Hamming distance, the first index winning
+    a tie on either side (OpenCV modules/features2d matchers.cpp + core batch_distance.cpp, restated; pinned against the
+    live cv2 by tests/test_oracle_pinned.py)."""
+    da = np.ascontiguousarray(da, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    if len(da) == 0 or len(db) == 0:
+        return []
+    dist = np.bitwise_count(da[:, None, :] ^ db[None, :, :]).sum(-1).astype(np.int64)  # [queries, trains]
+    t_of_q = dist.argmin(1)  # argmin returns the first minimum
+    q_of_t = dist.argmin(0)
+    return [(int(i), int(t_of_q[i]), int(dist[i, t_of_q[i]])) for i in range(len(da)) if q_of_t[t_of_q[i]] == i]
+
+
+def orb_match_counts(desc_a, desc_b) -> np.ndarray:
+    """``len(matches)`` per pair — the CPU stand-in for kobato_b200.ops.orb_match_pairs."""
+    return np.array([0 if a is None or b is None else len(orb_cross_check(a, b)) for a, b in zip(desc_a, desc_b)], np.int32)
+
+
 def refine_decision(ssim_value, orb_ratio, *, ssim_thr: float = 0.9, orb_thr: float = 0.15, errors=()):
     """src/dup/refine.py:100-117 -> (is_duplicate, reason)."""
     hits = []

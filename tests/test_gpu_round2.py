@@ -221,6 +221,59 @@ def test_cluster_pairs_device_matches_the_host_union_find():
     assert np.array_equal(label, want)
 
 
+# --------------------------------------------------------------------------------- N2 ORB matcher
+
+
+def test_orb_matcher_equals_opencv_cross_check():
+    """ke_orb_match_pairs against the LIVE cv2.BFMatcher(NORM_HAMMING, crossCheck=True) — match lists, distances and
+    counts — on tie-heavy random descriptor sets, on real ORB descriptors of synthetic images, and through the drop-in
+    dup.refine._compute_orb_ratio / refine_pairs_batch (the reference's ratio, src/dup/refine.py:55-68)."""
+    import cv2
+    from PIL import Image
+
+    from kobato_b200.dup import refine as krefine
+
+    rng = np.random.default_rng(1)
+    A, B = [], []
+    for trial in range(200):
+        na, nb = int(rng.integers(1, 500)), int(rng.integers(1, 500))
+        bits = int(rng.integers(1, 9))
+        da = rng.integers(0, 1 << bits, (na, 32)).astype(np.uint8)
+        db = rng.integers(0, 1 << bits, (nb, 32)).astype(np.uint8)
+        if trial % 3 == 0:
+            db[: min(na, nb)] = da[: min(na, nb)]
+        A.append(da)
+        B.append(db)
+    A += [None, np.zeros((0, 32), np.uint8)]
+    B += [B[0], B[1]]
+    counts, matches = ops.orb_match_pairs(A, B, want_matches=True)
+    for p in range(200):
+        want = sorted((m.queryIdx, m.trainIdx, int(m.distance)) for m in
+                      cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(A[p], B[p]))
+        assert matches[p] == want and counts[p] == len(want), p
+    assert counts[200] == 0 and counts[201] == 0
+    assert np.array_equal(ops.orb_match_pairs(A, B), counts)
+
+    def live_ratio(ia, ib):  # the reference's function body, on the host
+        orb = cv2.ORB_create()
+        kpa, da = orb.detectAndCompute(np.asarray(ia.convert("L")), None)
+        kpb, db = orb.detectAndCompute(np.asarray(ib.convert("L")), None)
+        if da is None or db is None or not kpa or not kpb:
+            return 0.0
+        m = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db)
+        return float(len(m) / min(len(kpa), len(kpb))) if m else 0.0
+
+    imgs = [Image.fromarray(synth.synth_image(40 + k, 240, 320, 3)) for k in range(4)]
+    imgs.append(Image.fromarray(np.roll(np.asarray(imgs[0]), 5, axis=1)))
+    imgs.append(Image.new("RGB", (64, 64), (10, 200, 10)))
+    some = 0
+    for a, b in ((0, 4), (0, 1), (2, 3), (1, 5), (4, 0)):
+        got, want = krefine._compute_orb_ratio(imgs[a], imgs[b]), live_ratio(imgs[a], imgs[b])
+        assert got == want, (a, b, got, want)
+        some += want > 0
+    assert some >= 2
+
+
 # --------------------------------------------------------------------------------- plumbing
 
 

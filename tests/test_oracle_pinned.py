@@ -300,6 +300,35 @@ def test_cluster_matches_restatement():
 # (importable only through oracle/skimage_shim: scikit-image is absent from this image)
 
 
+def test_orb_cross_check_restatement_equals_live_opencv():
+    """N2's oracle: the restated cross-check (mutual nearest neighbours, first index wins ties) equals
+    cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match on descriptor sets with many ties, and on real ORB descriptors."""
+    import cv2
+
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        na, nb = int(rng.integers(1, 60)), int(rng.integers(1, 60))
+        bits = int(rng.integers(1, 4))  # few distinct byte values -> many equal distances
+        da = rng.integers(0, 1 << bits, (na, 32)).astype(np.uint8)
+        db = rng.integers(0, 1 << bits, (nb, 32)).astype(np.uint8)
+        if trial % 3 == 0:
+            db[: min(na, nb)] = da[: min(na, nb)]
+        want = sorted((m.queryIdx, m.trainIdx, int(m.distance)) for m in
+                      cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db))
+        assert ref_py.orb_cross_check(da, db) == want, trial
+    from kobato_b200 import synth
+
+    orb = cv2.ORB_create()
+    a = synth.synth_image(3, 256, 256, 1)
+    b = np.roll(a, 3, axis=1)
+    _, da = orb.detectAndCompute(a, None)
+    _, db = orb.detectAndCompute(b, None)
+    if da is not None and db is not None:
+        want = sorted((m.queryIdx, m.trainIdx, int(m.distance)) for m in
+                      cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(da, db))
+        assert ref_py.orb_cross_check(da, db) == want and len(want) > 5
+
+
 @pytest.mark.reference
 def test_reference_refine_and_cluster_tests_run_through_the_skimage_shim():
     """The reference's OWN tests for the SSIM / clustering half of the path (tests/dup/test_refine.py,
@@ -336,6 +365,9 @@ def test_dropin_refine_and_cluster_equal_the_live_reference(tmp_path, monkeypatc
     ref_refine = importlib.import_module("dup.refine")
     ref_cluster = importlib.import_module("dup.cluster")
     monkeypatch.setattr(krefine, "_compute_ssim", lambda a, b: ref_py.compute_ssim(a, b))
+    from kobato_b200 import ops as kops
+
+    monkeypatch.setattr(kops, "orb_match_pairs", lambda a, b, **kw: ref_py.orb_match_counts(a, b))  # GPU matcher stand-in
 
     rng = np.random.default_rng(9)
     paths = []
