@@ -244,9 +244,14 @@ def run_cuda(args) -> dict:
     torch.cuda.synchronize(dev)
 
     # ---- device-resident steps (`value`) ------------------------------------------------------
+    # the clock sampler starts BEFORE the warm-up: loading NVML and the first query of each kind take driver locks for
+    # tens of milliseconds, which showed up as a one-off stall inside the first timed step when it was started there
+    clocks = ClockSampler(local)
+    clocks.__enter__()
     for _ in range(args.warmup):
         pipeline.scan(bank, threshold=8, ssim_threshold=0.9)
     barrier()
+    clocks.rows.clear()  # keep only the samples taken while the clock runs
     # a generational GC pass of the interpreter in the middle of a step showed up as a one-off ~25 ms launch gap:
     # collect now, keep the collector off while the clock runs
     import gc
@@ -256,14 +261,14 @@ def run_cuda(args) -> dict:
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {}
-    clocks = ClockSampler(local)
-    clocks.__enter__()
+    step_ms = []  # device time of every step's stages (outliers stay visible next to the mean)
     if True:
         e0.record()
         for _ in range(args.steps):
             out = pipeline.scan(bank, threshold=8, ssim_threshold=0.9)
             for k, v in out.stage_ms.items():
                 stage[k] = stage.get(k, 0.0) + v
+            step_ms.append(round(sum(v for k, v in out.stage_ms.items() if k != "host_assembly"), 3))
         e1.record()
         barrier()
     launches = ctx.launches - launches0
@@ -566,7 +571,7 @@ def run_cuda(args) -> dict:
                    "parallelism": f"image shards x{world}; join tiles t%{world}; SSIM pairs by owner, cross-shard pairs by "
                                   "(i+j) parity with one packed all_to_all of luma planes"},
         "counts": counts, "scan_check": scan_check,
-        "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+        "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "device_ms_of_each_step": step_ms,
         "roofline": roof_k1, "roofline_phash_large": roof_k1_large, "roofline_join": roof_k2, "roofline_join_c5": roof_c5, "roofline_ssim": roof_k3,
         "roofline_n1": roof_n1,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),

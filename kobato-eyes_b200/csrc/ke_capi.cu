@@ -122,6 +122,7 @@ extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
     KE_REQUIRE(ctx != nullptr, "ke_ctx_set_option: ctx is NULL");
     switch (option) {
         case KE_OPT_PHASH_GENERIC:
+        case KE_OPT_PHASH_CFG:
         case KE_OPT_SSIM_V1:
         case KE_OPT_RESIZE_GENERIC: break;
         case KE_OPT_JOIN_MODE: KE_REQUIRE(value >= 0 && value <= 3, "ke_ctx_set_option: join mode must be 0..3"); break;
@@ -131,6 +132,7 @@ extern "C" int ke_ctx_set_option(ke_ctx* ctx, int option, int value) {
         ke_ctx* c = ctx->dev_ctx[k];
         switch (option) {
             case KE_OPT_PHASH_GENERIC: c->force_generic_phash = value ? 1 : 0; break;
+            case KE_OPT_PHASH_CFG: c->phash_cfg = value; break;
             case KE_OPT_SSIM_V1: c->force_ssim_v1 = value ? 1 : 0; break;
             case KE_OPT_RESIZE_GENERIC: c->force_generic_resize = value ? 1 : 0; break;
             default: c->join_mode = value;

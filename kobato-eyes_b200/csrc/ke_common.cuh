@@ -68,6 +68,7 @@ struct ke_ctx {
     KeResizeCache* resize_tables = nullptr;
     KeResizeMmaCache* resize_mma = nullptr;
     int force_generic_phash = 0;   // KE_OPT_PHASH_GENERIC
+    int phash_cfg = 0;             // KE_OPT_PHASH_CFG
     int force_ssim_v1 = 0;         // KE_OPT_SSIM_V1
     int force_generic_resize = 0;  // KE_OPT_RESIZE_GENERIC
     int join_mode = 0;  // KE_OPT_JOIN_MODE: 0 auto, 1 POPC kernel only, 2 hybrid (POPC + bit-sliced), 3 bit-sliced only  // KE_OPT_PHASH_GENERIC: route every geometry through the generic K1 kernel

@@ -1396,7 +1396,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
 }
 
 template <int C>
-bool v5_config(const PhashArgs& a, V5Config& cfg) {
+bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     const long long row_bytes = (long long)a.w * C;
     if (a.row_stride != row_bytes || a.mma_words < 1 || !a.vmma) return false;  // strided rows: generic kernel
     cfg.aligned = (row_bytes & 15) == 0 && (a.img_stride & 15) == 0 && (a.w & 15) == 0 &&
@@ -1405,36 +1405,43 @@ bool v5_config(const PhashArgs& a, V5Config& cfg) {
     for (int q = 0; q < 4; ++q) nk_wide = std::max(nk_wide, a.mma_nk[q]), nk_narrow = std::max(nk_narrow, a.mma_nk[4 + q]);
     cfg.pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
     cfg.dbg = 0;
-    int want_sub = 16, want_shift = 1, want_nlb = 2;
-#ifdef KE_TUNING_PROBES
-    if (const char* env = getenv("KE_PHASH_CFG5")) sscanf(env, "%d,%d,%d", &want_sub, &want_shift, &want_nlb);  // tuning override
-#endif
-    if (want_nlb < 1 || want_nlb > kMaxLumaBufs) want_nlb = 2;
     const int wide_words = a.mma_boff[4], narrow_words = a.mma_words - a.mma_boff[4];
-    // Preference: two CTAs per SM (<= 113 KB) with the fragments on chip, then one CTA per SM (<= 227 KB), moving the
-    // fragments out to global memory (L2) and the luma ring down to one buffer only when nothing else fits.
-    struct Place { int wide, narrow; };
-    const Place places[] = {{nk_wide <= kNKP ? kBReg : kBSmem, kBSmem}, {nk_wide <= kNKP ? kBReg : kBGmem, kBSmem},
-                            {nk_wide <= kNKP ? kBReg : kBGmem, kBGmem}};
-    for (int budget : {113 * 1024, 227 * 1024})
-        for (const Place& pl : places)
-            for (int bufs : {want_nlb, 2, 1})
-                for (int sub : {want_sub, 8, 4, 2, 1}) {
-                    if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20)) continue;
-                    if (a.n * ((a.h + sub - 1) / sub) >= (1ll << 31)) continue;
-                    for (int shift : {want_shift, 2, 1}) {
-                        if (shift < 1 || shift > 3) continue;
-                        // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the
-                        // luma loads that run a few words past the last pixel
-                        const int slot = (int)((sub * row_bytes + (cfg.aligned ? 0 : 64) + 127) / 128 * 128);
-                        const int words = (pl.wide == kBSmem ? wide_words : 0) + (pl.narrow == kBSmem ? narrow_words : 0);
-                        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs);
-                        if (L.total > budget) continue;
-                        cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot;
-                        cfg.wide_b = pl.wide, cfg.narrow_b = pl.narrow, cfg.smem_words = words, cfg.L = L;
-                        return true;
-                    }
-                }
+    const int wide_chip = nk_wide <= kNKP ? kBReg : kBSmem;
+    auto fits = [&](int budget, int wide, int narrow, int bufs, int sub, int shift) -> bool {
+        if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20) || shift < 1 || shift > 3 || bufs < 1 ||
+            bufs > kMaxLumaBufs)
+            return false;
+        if (a.n * ((a.h + sub - 1) / sub) >= (1ll << 31)) return false;
+        // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the luma loads that
+        // run a few words past the last pixel
+        const int slot = (int)((sub * row_bytes + (cfg.aligned ? 0 : 64) + 127) / 128 * 128);
+        const int words = (wide == kBSmem ? wide_words : 0) + (narrow == kBSmem ? narrow_words : 0);
+        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs);
+        if (L.total > budget) return false;
+        cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot;
+        cfg.wide_b = wide, cfg.narrow_b = narrow, cfg.smem_words = words, cfg.L = L;
+        return true;
+    };
+    if (forced) {  // KE_OPT_PHASH_CFG (tests / tuning): sub_rows | slot_shift << 8 | luma buffers << 12 | placement << 16
+        const int place = (forced >> 16) & 3;  // 0: on chip, 1: wide fragments in L2, 2: both in L2
+        return fits(227 * 1024, place == 0 ? wide_chip : (nk_wide <= kNKP ? kBReg : kBGmem), place == 2 ? kBGmem : kBSmem,
+                    (forced >> 12) & 15, forced & 255, (forced >> 8) & 15);
+    }
+    // What matters, in this order (measured on 512 / 1024 / 2048-pixel rows): copies of at least ~12 KB (smaller bulk
+    // copies are latency bound), a double-buffered luma ring, the fragments on chip, two CTAs per SM.
+    const long long min_slot = std::min<long long>(12 * 1024, 32 * row_bytes);
+    struct Try { int budget, wide, narrow, bufs; bool big_slots; };
+    const Try order[] = {
+        {113 * 1024, wide_chip, kBSmem, 2, true}, {227 * 1024, wide_chip, kBSmem, 2, true},
+        {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBSmem, 2, true}, {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBGmem, 2, true},
+        {113 * 1024, wide_chip, kBSmem, 2, false}, {227 * 1024, wide_chip, kBSmem, 2, false},
+        {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBGmem, 2, false}, {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBGmem, 1, false}};
+    for (const Try& t : order)
+        for (int sub : {16, 8, 4, 2, 1}) {
+            if (t.big_slots && sub * row_bytes < min_slot) continue;
+            for (int shift : {1, 2})
+                if (fits(t.budget, t.wide, t.narrow, t.bufs, sub, shift)) return true;
+        }
     return false;
 }
 
@@ -1484,7 +1491,11 @@ int launch_phash(ke_ctx* ctx, PhashArgs& a, cudaStream_t s) {
     // images) and is the in-library reference the parity tests compare v5 with (KE_OPT_PHASH_GENERIC).
     if (!ctx->force_generic_phash) {
         V5Config cfg;
-        if (v5_config<C>(a, cfg)) return launch_v5<C>(ctx, a, cfg, s);
+        if (v5_config<C>(a, cfg, ctx->phash_cfg)) return launch_v5<C>(ctx, a, cfg, s);
+        if (ctx->phash_cfg) {
+            ke_set_error("ke_phash_batch: the pinned staging configuration 0x%x does not fit this geometry", ctx->phash_cfg);
+            return KE_E_UNSUPPORTED;
+        }
     }
     int rc_rows = 32;
     SmemLayout L;

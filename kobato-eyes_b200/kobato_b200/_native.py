@@ -16,6 +16,7 @@ KE_OPT_PHASH_GENERIC = 1
 KE_OPT_JOIN_MODE = 2
 KE_OPT_SSIM_V1 = 3
 KE_OPT_RESIZE_GENERIC = 4
+KE_OPT_PHASH_CFG = 5
 KE_ABI_VERSION = 2
 
 _LIB_PATH = Path(__file__).resolve().parent / "libkobato_b200.so"
