@@ -1100,21 +1100,26 @@ __device__ __noinline__ void luma_rows_any(const uint8_t* __restrict__ slot, int
 
 // BMEM = false: wide-target fragments in registers, narrow-target ones in shared memory (widths up to ~512: the
 // benchmark geometry; identical to the round-1 kernel).  BMEM = true: both behind pointers into shared or global memory.
-template <int C, bool BMEM>
-__global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const V5Config cfg) {
+// ALIGNED = true: base, images and rows on 16-byte boundaries and w % 16 == 0 (exact copies, vector luma path).
+// The staging geometry comes as SCALAR kernel parameters and the shared-memory layout is recomputed in the kernel: with
+// the same values read from a parameter struct the compiler kept them off the uniform datapath and the 512x512 RGB case
+// lost 15 % (measured: 10.7 ms against 9.2 ms per 70 000 images).
+template <int C, bool BMEM, bool ALIGNED>
+__global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift,
+                                                                   const int pitch_bytes, const int nlb, const int dbg,
+                                                                   const V5Config cfg) {
     constexpr int CR = 32, NW = kV5Tap;
     extern __shared__ __align__(128) uint8_t smem[];
-    const int sub_rows = cfg.sub_rows, slot_shift = cfg.slot_shift, pitch_bytes = cfg.pitch_bytes, nlb = cfg.nlb, dbg = cfg.dbg;
     const int row_bytes = a.w * C;
     const int sub_bytes = sub_rows * row_bytes;
-    const int slot_bytes = cfg.slot_bytes;
+    const int slot_bytes = ALIGNED ? sub_bytes : cfg.slot_bytes;  // aligned rows: slots are exactly one sub-chunk apart
     const int n_slots = 1 << slot_shift;
     const uint32_t slot_mask = (uint32_t)n_slots - 1u;
     // B fragments in shared memory: [wide-target warps 0..3 when cfg.wide_b == kBSmem][narrow-target warps 4..7 when
     // cfg.narrow_b == kBSmem], in table order
-    const int b_first = cfg.wide_b == kBSmem ? 0 : a.mma_boff[4];
-    const int b_last = cfg.narrow_b == kBSmem ? a.mma_words : a.mma_boff[4];
-    const V5Layout& L = cfg.L;
+    const int b_first = (BMEM && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
+    const int b_last = (BMEM && cfg.narrow_b != kBSmem) ? a.mma_boff[4] : a.mma_words;
+    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb);
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
@@ -1165,7 +1170,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             const int rows = min(sub_rows, a.h - (int)sq * sub_rows);
             const uint8_t* src = a.img + (blockIdx.x + (long long)k * gridDim.x) * a.img_stride + (long long)sq * sub_bytes;
             uint32_t bytes = (uint32_t)(rows * row_bytes);
-            if (!cfg.aligned) {  // the 16-byte aligned superset of the sub-chunk (bulk copies move whole 16-byte units)
+            if constexpr (!ALIGNED) {  // the 16-byte aligned superset of the sub-chunk (bulk copies move whole 16-byte units)
                 const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
                 src -= lead;
                 bytes = (lead + bytes + 15u) & ~15u;
@@ -1182,7 +1187,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
             for (uint32_t q = 0; q < (uint32_t)n_slots && q < total_seq; ++q) issue(q);
         // early release: when a warp's share of a sub-chunk (<= 2 rows of <= 512 pixels) fits its registers the
         // raw slot is handed back right after the loads, before the arithmetic
-        const bool early = cfg.aligned && a.w <= 512 && !(dbg & 16);  // 16 pixels (RGB, L) or 4 x 4 pixels (RGBA) per lane cover a row
+        const bool early = ALIGNED && a.w <= 512 && !(dbg & 16);  // 16 pixels (RGB, L) or 4 x 4 pixels (RGBA) per lane cover a row
         const int ng = a.w >> 4;
         const bool act = lane < ng;
         uint32_t seq = 0;
@@ -1244,7 +1249,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                         }
                         __syncwarp();  // (a warp without rows in a short last sub-chunk still counts as a reader)
                         if (lane == 0) release(seq, b);
-                    } else if (cfg.aligned) {
+                    } else if constexpr (ALIGNED) {
                         if (C == 3)
                             luma_rows_rgb16<kV5Luma>(s_raw + b * slot_bytes, dst8 + s * sub_rows * pitch_bytes, srows, a.w,
                                                      row_bytes, pitch_bytes, lw, lane);
@@ -1414,7 +1419,7 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
         if (a.n * ((a.h + sub - 1) / sub) >= (1ll << 31)) return false;
         // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the luma loads that
         // run a few words past the last pixel
-        const int slot = (int)((sub * row_bytes + (cfg.aligned ? 0 : 64) + 127) / 128 * 128);
+        const int slot = cfg.aligned ? (int)(sub * row_bytes) : (int)((sub * row_bytes + 64 + 127) / 128 * 128);
         const int words = (wide == kBSmem ? wide_words : 0) + (narrow == kBSmem ? narrow_words : 0);
         const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs);
         if (L.total > budget) return false;
@@ -1427,28 +1432,31 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
         return fits(227 * 1024, place == 0 ? wide_chip : (nk_wide <= kNKP ? kBReg : kBGmem), place == 2 ? kBGmem : kBSmem,
                     (forced >> 12) & 15, forced & 255, (forced >> 8) & 15);
     }
-    // What matters, in this order (measured on 512 / 1024 / 2048-pixel rows): copies of at least ~12 KB (smaller bulk
-    // copies are latency bound), a double-buffered luma ring, the fragments on chip, two CTAs per SM.
-    const long long min_slot = std::min<long long>(12 * 1024, 32 * row_bytes);
-    struct Try { int budget, wide, narrow, bufs; bool big_slots; };
-    const Try order[] = {
-        {113 * 1024, wide_chip, kBSmem, 2, true}, {227 * 1024, wide_chip, kBSmem, 2, true},
-        {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBSmem, 2, true}, {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBGmem, 2, true},
-        {113 * 1024, wide_chip, kBSmem, 2, false}, {227 * 1024, wide_chip, kBSmem, 2, false},
-        {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBGmem, 2, false}, {227 * 1024, nk_wide <= kNKP ? kBReg : kBGmem, kBGmem, 1, false}};
-    for (const Try& t : order)
-        for (int sub : {16, 8, 4, 2, 1}) {
-            if (t.big_slots && sub * row_bytes < min_slot) continue;
-            for (int shift : {1, 2})
-                if (fits(t.budget, t.wide, t.narrow, t.bufs, sub, shift)) return true;
-        }
+    // What matters (measured, tools/probe_phash_large.py: 512 / 1024 / 2048 / 4000-pixel rows): a double-buffered luma
+    // ring, raw sub-chunks of >= 12 KB (small bulk copies are latency bound: 2-row copies cost half the bandwidth at 2048
+    // pixels) and, where both still fit, two CTAs per SM (RGBA at 512: 13.9 ms with two CTAs and 8-row sub-chunks, 17.6 ms
+    // with one CTA and 16-row ones); where the resample fragments sit hardly matters (they are L2-resident and read with
+    // the same pattern by every CTA), so they move out of shared memory whenever that buys a larger sub-chunk.
+    struct Place { int budget, wide, narrow; };
+    const int wide_l2 = nk_wide <= kNKP ? kBReg : kBGmem;
+    // two CTAs per SM with everything on chip, as long as a sub-chunk of >= 12 KB (or 16 rows) still fits beside them
+    const long long min_slot = std::min<long long>(12 * 1024, 16 * row_bytes);
+    for (int sub : {16, 8, 4, 2, 1})
+        if (sub * row_bytes >= min_slot && fits(113 * 1024, wide_chip, kBSmem, 2, sub, 1)) return true;
+    // else one CTA per SM: the largest sub-chunk that fits, fragments moved out to L2 where that is what it takes
+    const Place places[] = {{227 * 1024, wide_chip, kBSmem}, {227 * 1024, wide_l2, kBSmem}, {227 * 1024, wide_l2, kBGmem}};
+    for (int bufs : {2, 1})
+        for (int sub : {16, 8, 4, 2, 1})
+            for (const Place& pl : places)
+                if (fits(pl.budget, pl.wide, pl.narrow, bufs, sub, 1)) return true;
     return false;
 }
 
 template <int C>
 int launch_v5(ke_ctx* ctx, const PhashArgs& a, V5Config& cfg, cudaStream_t s) {
     const bool bmem = !(cfg.wide_b == kBReg && cfg.narrow_b == kBSmem);
-    auto kernel = bmem ? ke_phash_v5_kernel<C, true> : ke_phash_v5_kernel<C, false>;
+    auto kernel = cfg.aligned ? (bmem ? ke_phash_v5_kernel<C, true, true> : ke_phash_v5_kernel<C, false, true>)
+                              : (bmem ? ke_phash_v5_kernel<C, true, false> : ke_phash_v5_kernel<C, false, false>);
     KE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.L.total));
     int per_sm = 0;
     KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kV5Threads, cfg.L.total));
@@ -1461,7 +1469,7 @@ int launch_v5(ke_ctx* ctx, const PhashArgs& a, V5Config& cfg, cudaStream_t s) {
     if (const char* ns_env = getenv("KE_PHASH_SLEEP")) ns = atoi(ns_env);
 #endif
     cfg.dbg = dbg | (ns << 8);
-    kernel<<<(unsigned)grid, kV5Threads, cfg.L.total, s>>>(a, cfg);
+    kernel<<<(unsigned)grid, kV5Threads, cfg.L.total, s>>>(a, cfg.sub_rows, cfg.slot_shift, cfg.pitch_bytes, cfg.nlb, cfg.dbg, cfg);
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
     return KE_OK;

@@ -19,7 +19,10 @@ KE_OPT_RESIZE_GENERIC = 4
 KE_OPT_PHASH_CFG = 5
 KE_ABI_VERSION = 2
 
-_LIB_PATH = Path(__file__).resolve().parent / "libkobato_b200.so"
+import os as _os
+
+# KE_LIB_PATH: an alternative build of the same library (A/B timing of kernel variants from tools/); never a fallback
+_LIB_PATH = Path(_os.environ.get("KE_LIB_PATH") or Path(__file__).resolve().parent / "libkobato_b200.so")
 _lib = None
 _lock = threading.RLock()  # re-entrant: group() builds Context objects (which call load()) while holding it
 

@@ -48,6 +48,15 @@ def main():
         gbs = args.images * 786448 / (min(t) * 1e-3) / 1e9
         print(f"phash: {args.images} images 512x512x3: ms={t} -> {args.images / (min(t) * 1e-3):.3e} img/s, {gbs:.1f} GB/s")
         del bank
+    if "phash_large" in only:  # the streaming kernel with its fragments in shared memory (1024 px) / L2 (2048 px)
+        for (h, w) in ((1024, 1024), (1536, 2048)):
+            n = max(64, int(3e9) // (h * w * 3))
+            bank = ops.synth_images_device(0, n, h, w, 3, n_set=n)
+            ops.phash_dhash_batch(bank[:8])
+            t = timed(lambda: ops.phash_dhash_batch(bank), args.reps)
+            gbs = n * (h * w * 3 + 16) / (min(t) * 1e-3) / 1e9
+            print(f"phash: {n} images {w}x{h}x3: ms={t} -> {n / (min(t) * 1e-3):.3e} img/s, {gbs:.1f} GB/s")
+            del bank
     if "n1" in only:
         bank = ops.synth_images_device(0, args.images, 512, 512, 3, n_set=args.images)
         for side, grid, tile in ((64, 8, 8), (32, 4, 8), (128, 16, 8)):
