@@ -337,11 +337,11 @@ def run_cuda(args) -> dict:
     k1_ms = stage["phash"] / args.steps  # live, inside the timed region: one launch per step
     k1_bytes = n * (IMG_BYTES + 16)
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
-    roof_k1 = {"kernel": "ke_phash_v5_kernel<3> (512x512x3; TMA ring + dp2a luma + mma.sync u8xs8 resample)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roof_k1 = {"kernel": "ke_phash_v5_kernel<3,0,1> (512x512x3; TMA ring + dp2a luma + mma.sync u8xs8 resample)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k1_gbs / hbm_peak,
-               # dram read+write per launch: 787 156 B/image measured by `ncu --set full` on an 8192-image launch of
-               # the same kernel (profiles/r1_ncu_k1v5_summary.txt), scaled to this launch's image count
-               "traffic": int(n * 787156), "traffic_source": "ncu constant 787156 B/image x images (not measured in this run)",
+               # dram read+write per launch: 787 184 B/image measured by `ncu --set full` on an 8192-image launch of
+               # the same kernel (profiles/r2_ncu_k1_512_summary.txt: 6 448 615 352 B), scaled to this launch's image count
+               "traffic": int(n * 787184), "traffic_source": "ncu constant 787184 B/image x images (not measured in this run)",
                "peak_source": peak_src,
                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                "images_per_s": n / (k1_ms * 1e-3)}

@@ -135,19 +135,20 @@ def plan_cross_pairs(ci: np.ndarray, cj: np.ndarray, offsets: np.ndarray, rank: 
             "send": send, "recv": recv, "own_i": own_i, "own_j": own_j, "scorer": scorer}
 
 
-def exchange_rows(rows, send_counts, recv_counts):
+def exchange_rows(rows, send_counts, recv_counts, async_op: bool = False):
     """ONE ``all_to_all_single``: ``rows`` = [sum(send_counts), k] with the rows for rank 0 first, then rank 1, ...;
-    returns [sum(recv_counts), k] ordered by source rank."""
+    returns [sum(recv_counts), k] ordered by source rank — or ``(buffer, work)`` with ``async_op`` (``work.wait()`` before
+    the buffer is read; ``work`` is None when nothing was launched)."""
     import torch
 
     dist = _dist()
     rank, size = world()
     out = torch.empty((int(sum(recv_counts)),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
-    if size == 1:
-        return out
-    dist.all_to_all_single(out, rows.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
-                           input_split_sizes=[int(c) for c in send_counts])
-    return out
+    work = None
+    if size > 1:
+        work = dist.all_to_all_single(out, rows.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
+                                      input_split_sizes=[int(c) for c in send_counts], async_op=async_op)
+    return (out, work) if async_op else out
 
 
 def all_gather_varlen(local):

@@ -359,13 +359,33 @@ class DuplicateScanner:
         """Members grouped by component -> ordered ``DuplicateCluster`` list (reference :320-356)."""
         index, best, offsets = scan["index"].tolist(), scan["best"].tolist(), scan["offsets"].tolist()
         clusters: list[DuplicateCluster] = []
+        keys: list[tuple] = []
         for lo, hi in zip(offsets[:-1], offsets[1:]):
             if hi - lo < 2:
                 continue
-            entries = [DuplicateClusterEntry(file=file_of(index[q]), best_hamming=best[q]) for q in range(lo, hi)]
-            clusters.append(_ordered_cluster(entries))
-        clusters.sort(key=_cluster_key)
-        return clusters
+            cluster, key = _ordered_cluster_keyed([DuplicateClusterEntry(file=file_of(index[q]), best_hamming=best[q])
+                                                   for q in range(lo, hi)])
+            clusters.append(cluster)
+            keys.append(key)
+        order = sorted(range(len(clusters)), key=keys.__getitem__)
+        return [clusters[k] for k in order]
+
+    def scan_columns(self, file_id, phash, size=None) -> "ClusterTable":
+        """The scan of ``build_clusters_from_columns`` WITHOUT any per-row Python object: a ``ClusterTable`` of arrays
+        (table rows grouped by cluster, ``best_hamming`` per member).  At 10 M rows the members alone are ~1 M; building a
+        ``DuplicateFile`` + ``DuplicateClusterEntry`` for each costs more host time than the whole join takes on eight
+        GPUs, so callers that page through the result (the reference's tree view shows clusters on demand) materialise
+        clusters lazily: ``table.cluster(c, make_file)``."""
+        cfg = self._config
+        if cfg.cosine_threshold is not None:
+            raise ValueError("the cosine gate needs embeddings: use build_clusters(files)")
+        ids = np.ascontiguousarray(file_id, np.int64).reshape(-1)
+        if not _all_distinct(ids):
+            raise ValueError("scan_columns needs distinct file ids")
+        if len(ids) == 0:
+            return ClusterTable(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(1, np.int64), {})
+        scan = self._scan_columns(phash, ids, size)
+        return ClusterTable(scan["index"], scan["best"], scan["offsets"], scan["stats"])
 
     # -- per-candidate gates (reference :358-400) ----------------------------------------
 
@@ -445,16 +465,56 @@ def assemble_clusters(candidates: Sequence, edges: Mapping[tuple[int, int], Dupl
     return clusters
 
 
+def _file_keys(f):
+    """Everything the keeper choice and the two sorts read from a file (reference :323-356, :402-415), derived ONCE:
+    ``Path`` parsing is the expensive part and the reference's keys repeat it per comparison key."""
+    p = Path(f.path)
+    name = p.name.lower()
+    return (-(f.size or 0), -_resolution(f), -_ext_priority(f), p.suffix.lower(), name, f.file_id)
+
+
+def _ordered_cluster_keyed(entries: list):
+    """Keeper choice and the keeper-first entry order of the reference (:336-352), plus the cluster's sort key (:354-355)."""
+    keyed = [(_file_keys(e.file), e) for e in entries]
+    keeper_id = min(keyed, key=lambda t: t[0])[1].file.file_id
+    # entry order: keeper first, then (-size, -resolution, -ext priority, name, id) — the keeper key without the suffix
+    keyed.sort(key=lambda t: (0 if t[1].file.file_id == keeper_id else 1, t[0][0], t[0][1], t[0][2], t[0][4], t[0][5]))
+    files = [e for _, e in keyed]
+    max_size = -min(k[0] for k, _ in keyed)
+    return DuplicateCluster(files=files, keeper_id=keeper_id), (-max_size, Path(files[0].file.path).as_posix().lower())
+
+
 def _ordered_cluster(entries: list) -> DuplicateCluster:
-    """Keeper choice and the keeper-first entry order of the reference (:336-352)."""
-    keeper_id = DuplicateScanner._choose_keeper(entries)
-    entries.sort(key=lambda e: (0 if e.file.file_id == keeper_id else 1, -(e.file.size or 0), -_resolution(e.file),
-                                -_ext_priority(e.file), Path(e.file.path).name.lower(), e.file.file_id))
-    return DuplicateCluster(files=entries, keeper_id=keeper_id)
+    return _ordered_cluster_keyed(entries)[0]
 
 
 def _cluster_key(c: DuplicateCluster):
     return (-(max(e.file.size or 0 for e in c.files)), Path(c.files[0].file.path).as_posix().lower())
+
+
+class ClusterTable:
+    """Result of ``DuplicateScanner.scan_columns``: clusters as arrays.  ``rows[offsets[c]:offsets[c+1]]`` are the table
+    rows of cluster c (ascending; clusters by ascending smallest row), ``best[...]`` their ``best_hamming``."""
+
+    def __init__(self, rows: np.ndarray, best: np.ndarray, offsets: np.ndarray, stats: dict):
+        self.rows, self.best, self.offsets, self.stats = rows, best, offsets, stats
+
+    def __len__(self) -> int:
+        return len(self.offsets) - 1
+
+    def members(self, c: int):
+        lo, hi = int(self.offsets[c]), int(self.offsets[c + 1])
+        return self.rows[lo:hi], self.best[lo:hi]
+
+    def cluster(self, c: int, make_file) -> DuplicateCluster:
+        """Materialise cluster c the way ``build_clusters`` would (keeper choice, entry order)."""
+        rows, best = self.members(c)
+        return _ordered_cluster([DuplicateClusterEntry(file=make_file(int(r)), best_hamming=int(b))
+                                 for r, b in zip(rows.tolist(), best.tolist())])
+
+    def clusters(self, make_file) -> list[DuplicateCluster]:
+        """All clusters, in the reference's order (largest file first, then path)."""
+        return DuplicateScanner._clusters_of({"index": self.rows, "best": self.best, "offsets": self.offsets}, make_file)
 
 
 def _all_distinct(ids: np.ndarray) -> bool:
@@ -466,4 +526,5 @@ def _all_distinct(ids: np.ndarray) -> bool:
     return np.unique(ids).size == ids.size
 
 
-__all__ = ["DuplicateFile", "DuplicateCluster", "DuplicateClusterEntry", "DuplicateScanConfig", "DuplicateScanner"]
+__all__ = ["DuplicateFile", "DuplicateCluster", "DuplicateClusterEntry", "DuplicateScanConfig", "DuplicateScanner",
+           "ClusterTable"]

@@ -112,17 +112,21 @@ def verify_pairs(bank, ci, cj, offsets, *, ssim_batch=None, luma_planes=None, on
     my_lo = int(offsets[rank])
     mine, cross = plan["local"], plan["cross"]
     scores = torch.zeros(len(ci), dtype=torch.float64, device=dev)
-    if len(mine):
-        scores[torch.from_numpy(mine).to(dev)] = ssim_batch(bank, ci[mine] - my_lo, cj[mine] - my_lo)
-    if on_local_done:
-        on_local_done()
     n_sent = n_recv = 0
+    pending = got = recv_rows = None
     if size > 1:
+        # the travelling planes leave FIRST (asynchronous all_to_all), the same-shard pairs are scored while they fly
         send_rows = np.concatenate(plan["send"])
         recv_rows = np.concatenate(plan["recv"])  # per-source sorted runs in source order = globally sorted
         n_sent, n_recv = len(send_rows), len(recv_rows)
         planes = luma_planes(bank, send_rows - my_lo).reshape(len(send_rows), h * w)
-        got = kdist.exchange_rows(planes, [len(x) for x in plan["send"]], [len(x) for x in plan["recv"]])
+        got, pending = kdist.exchange_rows(planes, [len(x) for x in plan["send"]], [len(x) for x in plan["recv"]], async_op=True)
+    if len(mine):
+        scores[torch.from_numpy(mine).to(dev)] = ssim_batch(bank, ci[mine] - my_lo, cj[mine] - my_lo)
+    if on_local_done:
+        on_local_done()
+    if size > 1:
+        own_planes = None
         if len(cross):
             # my end of each cross pair: luma planes of my own images, appended behind the received ones
             i_mine = plan["own_i"][cross] == rank
@@ -130,7 +134,11 @@ def verify_pairs(bank, ci, cj, offsets, *, ssim_batch=None, luma_planes=None, on
             far_rows = np.where(i_mine, cj[cross], ci[cross])
             own_uni, own_pos = np.unique(own_rows, return_inverse=True)
             far_pos = np.searchsorted(recv_rows, far_rows)
-            tmp = torch.cat([got, luma_planes(bank, own_uni - my_lo).reshape(len(own_uni), h * w)]).view(-1, h, w)
+            own_planes = luma_planes(bank, own_uni - my_lo).reshape(len(own_uni), h * w)
+        if pending is not None:
+            pending.wait()
+        if len(cross):
+            tmp = torch.cat([got, own_planes]).view(-1, h, w)
             a_idx = np.where(i_mine, len(recv_rows) + own_pos, far_pos)
             b_idx = np.where(i_mine, far_pos, len(recv_rows) + own_pos)
             scores[torch.from_numpy(cross).to(dev)] = ssim_batch(tmp, a_idx, b_idx)
