@@ -65,6 +65,10 @@ cfg = kscanner.DuplicateScanConfig(hamming_threshold=8, size_ratio=0.5)
 # (1) the array-level result: no per-row Python object at all
 t0 = time.perf_counter()
 table = kscanner.DuplicateScanner(cfg, scan_table=timed_scan).scan_columns(ids, h.view(np.int64), sizes)
+first_wall = time.perf_counter() - t0  # includes growing the scratch buffers to this table size
+lib_s.pop()
+t0 = time.perf_counter()
+table = kscanner.DuplicateScanner(cfg, scan_table=timed_scan).scan_columns(ids, h.view(np.int64), sizes)
 table_wall = time.perf_counter() - t0
 table_lib = lib_s.pop()
 t0 = time.perf_counter()
@@ -95,7 +99,7 @@ members, offsets = ops.cluster_pairs_csr(ei.astype(np.int64), ej.astype(np.int64
 comp_ok = np.array_equal(members, scan["index"]) and np.array_equal(offsets, scan["offsets"])
 pairs = n * (n - 1) // 2
 report = {"n": n, "devices": len(group.devices),
-          "scan_columns": {"wall_s": round(table_wall, 3), "library_s": round(table_lib, 3),
+          "scan_columns": {"first_call_wall_s": round(first_wall, 3), "wall_s": round(table_wall, 3), "library_s": round(table_lib, 3),
                            "python_s": round(table_wall - table_lib, 3), "pairs_per_s": pairs / table_lib,
                            "clusters": len(table), "first_1000_clusters_materialised_s": round(page_s, 3)},
           "build_clusters_from_columns": {"wall_s": round(wall, 3), "library_s": round(lib_s[0], 3),
