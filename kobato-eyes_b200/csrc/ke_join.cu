@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) ke_join_kernel(const JoinArgs a) {
 // ~200 LOP3 per 32 pairs and lane = 6.3 ALU instructions per pair, no POPC at all.
 
 constexpr int kBThreads = 128;
-constexpr int kBTile = 2048;  // must equal the POPC kernel's tile (RPT = 8)
+constexpr int kBTile = 2048;  // the fused kernel's tile for large tables (= the POPC role's with RPT = 8); 1024 for mid sizes
 
 __global__ void __launch_bounds__(256) ke_bitslice_kernel(const uint64_t* __restrict__ hashes, long long n,
                                                           uint32_t* __restrict__ sliced) {
@@ -249,7 +249,7 @@ __device__ __noinline__ void emit_sliced_hits(const JoinArgs& a, uint64_t row, l
     }
 }
 
-template <int BAR>
+template <int BAR, int TILE>
 __device__ __forceinline__ void sliced_role(const JoinArgs& a, uint32_t* cols, long long* s_next_p, const int tid) {
     long long& s_next = *s_next_p;
     const long long nblk_total = (a.n + 31) / 32;
@@ -273,9 +273,9 @@ __device__ __forceinline__ void sliced_role(const JoinArgs& a, uint32_t* cols, l
         if (a.queue && tid == 0) atomicAdd(a.queue + 2, 1ull);
         long long tr, tc;
         tile_coords(t, a.tiles_per_dim, tr, tc);
-        const long long row0 = tr * kBTile, col0 = tc * kBTile;
+        const long long row0 = tr * TILE, col0 = tc * TILE;
         const long long blk0 = col0 / 32;
-        const int nblk = (int)min((long long)(kBTile / 32), nblk_total - blk0);
+        const int nblk = (int)min((long long)(TILE / 32), nblk_total - blk0);
         {
             const uint4* src = reinterpret_cast<const uint4*>(a.sliced + blk0 * 64);
             uint4* dst = reinterpret_cast<uint4*>(cols);
@@ -283,7 +283,7 @@ __device__ __forceinline__ void sliced_role(const JoinArgs& a, uint32_t* cols, l
         }
         role_sync<BAR, kBThreads>();
 
-        for (int pass = 0; pass < kBTile / kBThreads; ++pass) {
+        for (int pass = 0; pass < TILE / kBThreads; ++pass) {
             const long long i = row0 + (long long)pass * kBThreads + tid;
             if (row0 + (long long)pass * kBThreads >= a.n) break;
             const uint64_t row = i < a.n ? __ldg(a.hashes + i) : 0ull;
@@ -338,19 +338,24 @@ __device__ __forceinline__ void sliced_role(const JoinArgs& a, uint32_t* cols, l
 __global__ void __launch_bounds__(kBThreads) ke_join_sliced_kernel(const JoinArgs a) {
     __shared__ __align__(16) uint32_t cols[(kBTile / 32) * 64];  // 16 KB: 64 blocks x 64 words
     __shared__ long long s_next;
-    sliced_role<0>(a, cols, &s_next, threadIdx.x);
+    sliced_role<0, kBTile>(a, cols, &s_next, threadIdx.x);
 }
 
 // Fused hybrid: warps 0..7 run the POPC role, warps 8..11 the bit-sliced role, each with its own
 // column tile and named barrier, all pulling tiles from one queue.  Co-residency of the two
 // instruction mixes on every SM is then guaranteed by construction (two separate kernels on two
 // streams only co-run when the block scheduler happens to interleave them).
+// RPT = 8: tiles of 2048 hashes; RPT = 4: tiles of 1024 for mid-size tables, where 2048-hash tiles leave a CTA only a
+// handful of tiles and the roles' different tile times show as a tail (a rank's share of the 560 k table of the 8-GPU
+// step: 16 tiles per CTA; the 70 k table of the 1-GPU step: 2).
+template <int RPT>
 __global__ void __launch_bounds__(kThreads + kBThreads, 2) ke_join_fused_kernel(const JoinArgs a) {
-    __shared__ __align__(16) uint64_t cols_p[kBTile];
-    __shared__ __align__(16) uint32_t cols_b[(kBTile / 32) * 64];
+    constexpr int TILE = kThreads * RPT;
+    __shared__ __align__(16) uint64_t cols_p[TILE];
+    __shared__ __align__(16) uint32_t cols_b[(TILE / 32) * 64];
     __shared__ long long s_next[2];
-    if (threadIdx.x < kThreads) popc_role<8, 1>(a, cols_p, &s_next[0]);
-    else sliced_role<2>(a, cols_b, &s_next[1], threadIdx.x - kThreads);
+    if (threadIdx.x < kThreads) popc_role<RPT, 1>(a, cols_p, &s_next[0]);
+    else sliced_role<2, TILE>(a, cols_b, &s_next[1], threadIdx.x - kThreads);
 }
 
 template <int RPT>
@@ -375,8 +380,8 @@ int launch_join(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream) {
 
 // Hybrid launch: bit-slice the table, then the fused kernel (or the bit-sliced kernel alone) with a
 // dynamic tile queue.
-int launch_hybrid(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream, int mode) {
-    constexpr int TILE = kBTile;
+int launch_hybrid(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream, int mode, int tile) {
+    const int TILE = mode == 3 ? kBTile : tile;
     a.tiles_per_dim = (a.n + TILE - 1) / TILE;
     a.tile_total = a.tiles_per_dim * (a.tiles_per_dim + 1) / 2;
     const long long nblk = (a.n + 31) / 32;
@@ -401,7 +406,8 @@ int launch_hybrid(ke_ctx* ctx, JoinArgs& a, cudaStream_t stream, int mode) {
         ke_join_sliced_kernel<<<(unsigned)grid, kBThreads, 0, stream>>>(a);
     } else {
         long long grid = std::min<long long>((long long)ctx->sm_count * 2, mine);
-        ke_join_fused_kernel<<<(unsigned)grid, kThreads + kBThreads, 0, stream>>>(a);
+        if (TILE == kBTile) ke_join_fused_kernel<8><<<(unsigned)grid, kThreads + kBThreads, 0, stream>>>(a);
+        else ke_join_fused_kernel<4><<<(unsigned)grid, kThreads + kBThreads, 0, stream>>>(a);
     }
     ctx->launches++;
     KE_CUDA(cudaGetLastError());
@@ -485,7 +491,12 @@ extern "C" int ke_hamming_join(ke_ctx* ctx, const uint64_t* d_hashes, int64_t n,
     // predicate rejects — made this switch 8x slower at 70 k; `tools/probe_join70k.py` is the regression probe.)
     const long long bt = (n + kBTile - 1) / kBTile, btiles = bt * (bt + 1) / 2 / part_count;
     const bool hybrid_auto = rpt == 8 || btiles >= 2ll * ctx->sm_count;
-    if (threshold <= 15 && mode != 1 && (mode >= 2 || hybrid_auto)) return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode);
+    // fewer than 12 tiles of 2048 per CTA of the fused kernel: tiles of 1024 (four times as many) even out the tail
+    // (measured, tools/probe_join_sizes.py: 70 k hashes 1.16 -> 0.98 ms, a rank's share of 140 k / 280 k 2.05 -> 1.83 /
+    // 3.67 -> 3.53 ms; from 16 tiles per CTA on — a share of 560 k — the larger tile wins again)
+    const int tile = btiles >= 12ll * 2 * ctx->sm_count ? kBTile : kBTile / 2;
+    if (threshold <= 15 && mode != 1 && (mode >= 2 || hybrid_auto))
+        return launch_hybrid(ctx, a, s, mode == 0 ? 2 : mode, tile);
     switch (rpt) {
         case 8: return launch_join<8>(ctx, a, s);
         case 4: return launch_join<4>(ctx, a, s);
