@@ -13,6 +13,7 @@
 //   ke_tile_bits_kernel  per-tile sum, pixel*tile^2 > sum  (== pixel > mean), ballot-packed bits
 //   ke_bits_hamming_kernel / ke_plane_sad_kernel   pair (ia, ib) -> popcount(xor) / sum |a-b|
 // The intermediate [n,h,ow] plane costs ow/(w*c) of the input traffic (8 % at 512x512x3 -> 128).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -368,36 +369,38 @@ extern "C" int ke_plane_sad_pairs(ke_ctx* ctx, const uint8_t* d_planes, int64_t 
 // multi-GPU scan ships between ranks for its cross-shard SSIM pairs (a third of the RGB bytes).
 
 namespace {
+// grid = (blocks over one plane, images): 32-bit index arithmetic inside a plane (the first version divided 64-bit element
+// indices per thread and ran at a fifth of the HBM rate)
 template <int C>
 __global__ void __launch_bounds__(256) ke_luma_planes_kernel(const uint8_t* __restrict__ bank, int h, int w, long long img_stride,
                                                              long long row_stride, const long long* __restrict__ idx,
-                                                             long long n, uint8_t* __restrict__ out) {
-    const long long per = (long long)h * w, total = n * per;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long k = e / per, r = e - k * per;
-        const int y = (int)(r / w), x = (int)(r - (long long)y * w);
-        out[e] = (uint8_t)luma_at<C>(bank + idx[k] * img_stride + (long long)y * row_stride + (long long)x * C);
+                                                             uint8_t* __restrict__ out) {
+    const uint8_t* img = bank + idx[blockIdx.y] * img_stride;
+    uint8_t* dst = out + (long long)blockIdx.y * h * w;
+    const int per = h * w;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+        const int y = e / w, x = e - y * w;
+        dst[e] = (uint8_t)luma_at<C>(img + (long long)y * row_stride + (long long)x * C);
     }
 }
 
-// RGB rows on 4-byte boundaries, w % 4 == 0: a thread turns 12 bytes (3 coalesced words) into one word of 4 luma bytes
-__global__ void __launch_bounds__(256) ke_luma_planes_rgb4_kernel(const uint8_t* __restrict__ bank, int h, int w,
-                                                                  long long img_stride, long long row_stride,
-                                                                  const long long* __restrict__ idx, long long n,
-                                                                  uint32_t* __restrict__ out) {
-    const int wq = w >> 2;
-    const long long per = (long long)h * wq, total = n * per;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long k = e / per, r = e - k * per;
-        const int y = (int)(r / wq), q = (int)(r - (long long)y * wq);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(bank + idx[k] * img_stride + (long long)y * row_stride) + 3 * q;
-        const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-        auto lum = [](uint32_t r_, uint32_t g_, uint32_t b_) { return (r_ * 19595u + g_ * 38470u + b_ * 7471u + 0x8000u) >> 16; };
-        const uint32_t l0 = lum(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
-        const uint32_t l1 = lum(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
-        const uint32_t l2 = lum((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
-        const uint32_t l3 = lum((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
-        out[e] = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+// RGB rows on 16-byte boundaries, w % 16 == 0: a thread turns 48 bytes (three coalesced 16-byte loads) into 16 luma bytes
+__global__ void __launch_bounds__(256) ke_luma_planes_rgb16_kernel(const uint8_t* __restrict__ bank, int h, int w,
+                                                                   long long img_stride, long long row_stride,
+                                                                   const long long* __restrict__ idx, uint4* __restrict__ out) {
+    const uint8_t* img = bank + idx[blockIdx.y] * img_stride;
+    const int wg = w >> 4, per = h * wg;
+    uint4* dst = out + (long long)blockIdx.y * per;
+    auto lum = [](uint32_t r_, uint32_t g_, uint32_t b_) { return (r_ * 19595u + g_ * 38470u + b_ * 7471u + 0x8000u) >> 16; };
+    auto four = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
+        return lum(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u) | (lum(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u) << 8) |
+               (lum((w1 >> 16) & 255u, w1 >> 24, w2 & 255u) << 16) | (lum((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24) << 24);
+    };
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+        const int y = e / wg, g = e - y * wg;
+        const uint4* src = reinterpret_cast<const uint4*>(img + (long long)y * row_stride) + 3 * g;
+        const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        dst[e] = make_uint4(four(a.x, a.y, a.z), four(a.w, b.x, b.y), four(b.z, b.w, c.x), four(c.y, c.z, c.w));
     }
 }
 }  // namespace
@@ -410,21 +413,27 @@ extern "C" int ke_luma_planes(ke_ctx* ctx, const uint8_t* d_bank, int h, int w, 
     KE_REQUIRE(d_bank && d_idx && d_out, "ke_luma_planes: NULL buffer");
     KeDeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (c == 3 && (w & 3) == 0 && (row_stride & 3) == 0 && (img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(d_bank) & 3) == 0 &&
-        (reinterpret_cast<uintptr_t>(d_out) & 3) == 0) {
-        ke_luma_planes_rgb4_kernel<<<grid_for(n * h * (w >> 2), 256, ctx), 256, 0, s>>>(d_bank, h, w, img_stride, row_stride,
-                                                                                    (const long long*)d_idx, n, (uint32_t*)d_out);
-        KE_CUDA(cudaGetLastError());
+    KE_REQUIRE(n <= 65535 * 1024ll, "ke_luma_planes: too many planes in one call");
+    const long long per = (long long)h * w;
+    KE_REQUIRE(per < (1ll << 31), "ke_luma_planes: plane too large");
+    for (int64_t k0 = 0; k0 < n; k0 += 65535) {  // gridDim.y limit
+        const unsigned ny = (unsigned)std::min<int64_t>(65535, n - k0);
+        const long long* idx = (const long long*)d_idx + k0;
+        uint8_t* out = d_out + k0 * per;
+        if (c == 3 && (w & 15) == 0 && (row_stride & 15) == 0 && (img_stride & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(d_bank) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+            const unsigned nx = (unsigned)std::min<long long>((per / 16 + 255) / 256, 64);
+            ke_luma_planes_rgb16_kernel<<<dim3(nx, ny), 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, idx, (uint4*)out);
+        } else {
+            const unsigned nx = (unsigned)std::min<long long>((per + 255) / 256, 256);
+            switch (c) {
+                case 1: ke_luma_planes_kernel<1><<<dim3(nx, ny), 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, idx, out); break;
+                case 3: ke_luma_planes_kernel<3><<<dim3(nx, ny), 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, idx, out); break;
+                default: ke_luma_planes_kernel<4><<<dim3(nx, ny), 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, idx, out);
+            }
+        }
         ctx->launches++;
-        return KE_OK;
-    }
-    const unsigned grid = grid_for(n * h * w, 256, ctx);
-    switch (c) {
-        case 1: ke_luma_planes_kernel<1><<<grid, 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, (const long long*)d_idx, n, d_out); break;
-        case 3: ke_luma_planes_kernel<3><<<grid, 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, (const long long*)d_idx, n, d_out); break;
-        default: ke_luma_planes_kernel<4><<<grid, 256, 0, s>>>(d_bank, h, w, img_stride, row_stride, (const long long*)d_idx, n, d_out);
     }
     KE_CUDA(cudaGetLastError());
-    ctx->launches++;
     return KE_OK;
 }

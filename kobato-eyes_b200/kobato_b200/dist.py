@@ -135,15 +135,17 @@ def plan_cross_pairs(ci: np.ndarray, cj: np.ndarray, offsets: np.ndarray, rank: 
             "send": send, "recv": recv, "own_i": own_i, "own_j": own_j, "scorer": scorer}
 
 
-def exchange_rows(rows, send_counts, recv_counts, async_op: bool = False):
+def exchange_rows(rows, send_counts, recv_counts, async_op: bool = False, out=None):
     """ONE ``all_to_all_single``: ``rows`` = [sum(send_counts), k] with the rows for rank 0 first, then rank 1, ...;
-    returns [sum(recv_counts), k] ordered by source rank — or ``(buffer, work)`` with ``async_op`` (``work.wait()`` before
-    the buffer is read; ``work`` is None when nothing was launched)."""
+    returns [sum(recv_counts), k] ordered by source rank (received straight into ``out`` when given) — or
+    ``(buffer, work)`` with ``async_op`` (``work.wait()`` before the buffer is read; ``work`` is None when nothing was
+    launched)."""
     import torch
 
     dist = _dist()
     rank, size = world()
-    out = torch.empty((int(sum(recv_counts)),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    if out is None:
+        out = torch.empty((int(sum(recv_counts)),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
     work = None
     if size > 1:
         work = dist.all_to_all_single(out, rows.contiguous(), output_split_sizes=[int(c) for c in recv_counts],

@@ -219,13 +219,7 @@ def ssim_batch(bank, ia, ib, *, gaussian: bool = False):
     if x.stride(3) != 1 or x.stride(2) != c:
         x = x.contiguous()
     dev = x.device.index
-    ia_t = torch.as_tensor(ia, dtype=torch.int64).to(x.device).contiguous()
-    ib_t = torch.as_tensor(ib, dtype=torch.int64).to(x.device).contiguous()
-    if ia_t.shape != ib_t.shape or ia_t.dim() != 1:
-        raise ValueError("ia and ib must be 1-D and of equal length")
-    n = ia_t.numel()
-    if n and (int(torch.max(torch.maximum(ia_t, ib_t))) >= m or int(torch.min(torch.minimum(ia_t, ib_t))) < 0):
-        raise ValueError("pair index out of range")
+    ia_t, ib_t, n = _pair_index(ia, ib, m, x.device)
     out = torch.empty(n, dtype=torch.float64, device=x.device)
     if n:
         ctx = nat.context(dev)
@@ -341,7 +335,18 @@ def bits_to_ints(bits) -> list[int]:
 
 
 def _pair_index(ia, ib, m: int, device):
+    """Pair index sequences -> int64 device tensors, range-checked.  Host sequences (lists, numpy arrays) are checked on
+    the host before they are uploaded; only device tensors cost a device reduction and a synchronisation."""
     torch = _torch()
+    if not (_is_tensor(ia) and ia.is_cuda) and not (_is_tensor(ib) and ib.is_cuda):
+        a = np.ascontiguousarray(ia.cpu().numpy() if _is_tensor(ia) else ia, np.int64)
+        b = np.ascontiguousarray(ib.cpu().numpy() if _is_tensor(ib) else ib, np.int64)
+        if a.shape != b.shape or a.ndim != 1:
+            raise ValueError("ia and ib must be 1-D and of equal length")
+        if a.size and (max(int(a.max()), int(b.max())) >= m or min(int(a.min()), int(b.min())) < 0):
+            raise ValueError("pair index out of range")
+        both = torch.from_numpy(np.stack([a, b])).to(device)  # one upload
+        return both[0], both[1], int(a.size)
     ia_t = torch.as_tensor(ia, dtype=torch.int64).to(device).contiguous()
     ib_t = torch.as_tensor(ib, dtype=torch.int64).to(device).contiguous()
     if ia_t.shape != ib_t.shape or ia_t.dim() != 1:
@@ -493,9 +498,9 @@ def orb_match_pairs(desc_a: list, desc_b: list, *, want_matches: bool = False):
     return counts
 
 
-def luma_planes(bank, idx):
+def luma_planes(bank, idx, out=None):
     """``convert("L")`` planes of ``bank[idx]`` (Pillow rgb2l; reference src/dup/refine.py:48-49) -> uint8 CUDA tensor
-    ``[len(idx), h, w]``."""
+    ``[len(idx), h, w]`` (written into ``out`` — contiguous, ``len(idx) * h * w`` bytes — when given)."""
     torch = _torch()
     lib = nat.load()
     x = _as_cuda_u8(bank)
@@ -504,7 +509,10 @@ def luma_planes(bank, idx):
     n = idx_t.numel()
     if n and (int(idx_t.max()) >= m or int(idx_t.min()) < 0):
         raise ValueError("image index out of range")
-    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    elif not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == n * h * w):
+        raise ValueError("out must be a contiguous CUDA uint8 tensor of len(idx) * h * w bytes")
     if n:
         dev = x.device.index
         ctx = nat.context(dev)

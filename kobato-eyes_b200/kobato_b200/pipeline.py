@@ -113,35 +113,42 @@ def verify_pairs(bank, ci, cj, offsets, *, ssim_batch=None, luma_planes=None, on
     mine, cross = plan["local"], plan["cross"]
     scores = torch.zeros(len(ci), dtype=torch.float64, device=dev)
     n_sent = n_recv = 0
-    pending = got = recv_rows = None
+    pending = tmp = None
     if size > 1:
-        # the travelling planes leave FIRST (asynchronous all_to_all), the same-shard pairs are scored while they fly
+        # One buffer of 'L' planes for the cross-shard pairs: [planes received | planes of my own images].  The travelling
+        # planes leave FIRST (asynchronous all_to_all straight into the buffer's head); my own ends are converted and the
+        # same-shard pairs scored while they fly.
         send_rows = np.concatenate(plan["send"])
         recv_rows = np.concatenate(plan["recv"])  # per-source sorted runs in source order = globally sorted
         n_sent, n_recv = len(send_rows), len(recv_rows)
-        planes = luma_planes(bank, send_rows - my_lo).reshape(len(send_rows), h * w)
-        got, pending = kdist.exchange_rows(planes, [len(x) for x in plan["send"]], [len(x) for x in plan["recv"]], async_op=True)
-    if len(mine):
-        scores[torch.from_numpy(mine).to(dev)] = ssim_batch(bank, ci[mine] - my_lo, cj[mine] - my_lo)
-    if on_local_done:
-        on_local_done()
-    if size > 1:
-        own_planes = None
         if len(cross):
-            # my end of each cross pair: luma planes of my own images, appended behind the received ones
             i_mine = plan["own_i"][cross] == rank
             own_rows = np.where(i_mine, ci[cross], cj[cross])
             far_rows = np.where(i_mine, cj[cross], ci[cross])
             own_uni, own_pos = np.unique(own_rows, return_inverse=True)
             far_pos = np.searchsorted(recv_rows, far_rows)
-            own_planes = luma_planes(bank, own_uni - my_lo).reshape(len(own_uni), h * w)
+        else:
+            own_uni = np.zeros(0, np.int64)
+        tmp = torch.empty((n_recv + len(own_uni), h * w), dtype=torch.uint8, device=dev)
+        planes = luma_planes(bank, send_rows - my_lo).reshape(n_sent, h * w)
+        _, pending = kdist.exchange_rows(planes, [len(x) for x in plan["send"]], [len(x) for x in plan["recv"]], async_op=True,
+                                         out=tmp[:n_recv])
+        if len(own_uni):
+            if luma_planes is ops.luma_planes:
+                luma_planes(bank, own_uni - my_lo, out=tmp[n_recv:])
+            else:  # injected stand-in (tests) without an `out` parameter
+                tmp[n_recv:] = luma_planes(bank, own_uni - my_lo).reshape(len(own_uni), h * w)
+    if len(mine):
+        scores[torch.from_numpy(mine).to(dev)] = ssim_batch(bank, ci[mine] - my_lo, cj[mine] - my_lo)
+    if on_local_done:
+        on_local_done()
+    if size > 1:
         if pending is not None:
             pending.wait()
         if len(cross):
-            tmp = torch.cat([got, own_planes]).view(-1, h, w)
-            a_idx = np.where(i_mine, len(recv_rows) + own_pos, far_pos)
-            b_idx = np.where(i_mine, far_pos, len(recv_rows) + own_pos)
-            scores[torch.from_numpy(cross).to(dev)] = ssim_batch(tmp, a_idx, b_idx)
+            a_idx = np.where(i_mine, n_recv + own_pos, far_pos)
+            b_idx = np.where(i_mine, far_pos, n_recv + own_pos)
+            scores[torch.from_numpy(cross).to(dev)] = ssim_batch(tmp.view(-1, h, w), a_idx, b_idx)
         kdist._dist().all_reduce(scores)  # every pair was scored by exactly one rank: SUM merges
     return scores, {"ssim_pairs_local": int(len(mine)), "ssim_pairs_cross": int(len(cross)), "planes_sent": int(n_sent),
                     "planes_received": int(n_recv), "plane_bytes_sent": int(n_sent) * h * w}
