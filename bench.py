@@ -248,6 +248,9 @@ def run_cuda(args) -> dict:
     # tens of milliseconds, which showed up as a one-off stall inside the first timed step when it was started there
     clocks = ClockSampler(local)
     clocks.__enter__()
+    t_wait = time.perf_counter()
+    while len(clocks.rows) < 3 and time.perf_counter() - t_wait < 2.0:  # the first polls are the slow ones: let them pass
+        time.sleep(0.05)
     for _ in range(args.warmup):
         pipeline.scan(bank, threshold=8, ssim_threshold=0.9)
     barrier()

@@ -97,7 +97,8 @@ int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int h, int w, i
 /* Same, host buffers in and out (densely packed n*h*w*c).  Images are split into contiguous ranges over the context's
  * devices; per device, chunks of <= 256 MB go host -> device on two alternating streams with each chunk's kernel behind
  * its copy.  Page-locked sources (cudaHostAlloc / cudaHostRegister, torch pinned tensors) are DMA'd in place; pageable
- * ones pass through the context's pinned staging buffers (2 x 32 MB, filled by KE_STAGE_THREADS=4 host threads).
+ * ones pass through the context's pinned staging buffers (2 x 32 MB, filled by KE_STAGE_THREADS host threads, default
+ * min(8, cores / 2): 35 GB/s against 55 GB/s from page-locked memory on the test box).
  * This is the call behind the drop-in core.fastsig.compute_signatures_mp (src/core/fastsig.py:65-99). */
 int ke_phash_batch_host(ke_ctx* ctx, const uint8_t* h_img, int64_t n, int h, int w, int c, uint64_t* h_phash,
                         uint64_t* h_dhash, float* h_min_margin);
