@@ -104,6 +104,14 @@ def all_gather_hashes(local, return_counts: bool = False):
     return (table, counts) if return_counts else table
 
 
+def sorted_unique(x: np.ndarray) -> np.ndarray:
+    """Sorted distinct values by sort + neighbour compare (np.unique costs 5 ms on 25 k int64 here, a sort 0.3 ms)."""
+    if x.size == 0:
+        return x
+    y = np.sort(x)
+    return y[np.concatenate([[True], y[1:] != y[:-1]])]
+
+
 def plan_cross_pairs(ci: np.ndarray, cj: np.ndarray, offsets: np.ndarray, rank: int, size: int) -> dict:
     """Who verifies which candidate pair, and which images travel for it.  Pure arithmetic on the (global) candidate
     list every rank holds, so all ranks derive the same plan without exchanging anything.
@@ -120,18 +128,25 @@ def plan_cross_pairs(ci: np.ndarray, cj: np.ndarray, offsets: np.ndarray, rank: 
     offsets = np.asarray(offsets, np.int64)
     own_i = np.searchsorted(offsets, ci, side="right") - 1
     own_j = np.searchsorted(offsets, cj, side="right") - 1
-    scorer = np.where(own_i == own_j, own_i, np.where(((ci + cj) & 1) == 0, own_i, own_j))
     is_cross = own_i != own_j
+    scorer = np.where(is_cross & (((ci + cj) & 1) == 1), own_j, own_i)
+    cross_all = np.flatnonzero(is_cross)
+    sc = scorer[cross_all]
     # the image that has to travel: the one NOT owned by the scorer
-    trav = np.where(scorer == own_i, cj, ci)
-    trav_owner = np.where(scorer == own_i, own_j, own_i)
-    send, recv = [], []
-    for peer in range(size):
-        out_sel = is_cross & (trav_owner == rank) & (scorer == peer)
-        in_sel = is_cross & (trav_owner == peer) & (scorer == rank)
-        send.append(np.unique(trav[out_sel]) if peer != rank else np.zeros(0, np.int64))
-        recv.append(np.unique(trav[in_sel]) if peer != rank else np.zeros(0, np.int64))
-    return {"local": np.flatnonzero(~is_cross & (scorer == rank)), "cross": np.flatnonzero(is_cross & (scorer == rank)),
+    i_scores = sc == own_i[cross_all]
+    trav = np.where(i_scores, cj[cross_all], ci[cross_all])
+    trav_owner = np.where(i_scores, own_j[cross_all], own_i[cross_all])
+    # what I send, grouped by destination (one sort of a combined key instead of a mask per peer), and what I receive,
+    # grouped by source — rows of one owner are contiguous in the table, so the sorted distinct rows ARE grouped by source
+    mine_out = trav_owner == rank
+    key = sorted_unique(sc[mine_out] * (int(offsets[-1]) + 1) + trav[mine_out])
+    dest, rows_out = np.divmod(key, int(offsets[-1]) + 1)
+    cuts = np.searchsorted(dest, np.arange(size + 1))
+    send = [rows_out[cuts[p]:cuts[p + 1]] for p in range(size)]
+    rows_in = sorted_unique(trav[sc == rank])
+    cuts = np.searchsorted(rows_in, offsets)
+    recv = [rows_in[cuts[p]:cuts[p + 1]] for p in range(size)]
+    return {"local": np.flatnonzero(~is_cross & (own_i == rank)), "cross": cross_all[sc == rank],
             "send": send, "recv": recv, "own_i": own_i, "own_j": own_j, "scorer": scorer}
 
 

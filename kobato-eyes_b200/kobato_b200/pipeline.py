@@ -125,7 +125,8 @@ def verify_pairs(bank, ci, cj, offsets, *, ssim_batch=None, luma_planes=None, on
             i_mine = plan["own_i"][cross] == rank
             own_rows = np.where(i_mine, ci[cross], cj[cross])
             far_rows = np.where(i_mine, cj[cross], ci[cross])
-            own_uni, own_pos = np.unique(own_rows, return_inverse=True)
+            own_uni = kdist.sorted_unique(own_rows)
+            own_pos = np.searchsorted(own_uni, own_rows)
             far_pos = np.searchsorted(recv_rows, far_rows)
         else:
             own_uni = np.zeros(0, np.int64)
