@@ -60,7 +60,7 @@ ke_ctx* ke_ctx_child(ke_ctx* ctx, int k); /* k in [0, device_count): child 0 is 
  * 2 hybrid (POPC role + bit-sliced LOP3 role in one kernel), 3 bit-sliced kernel only. */
 #define KE_OPT_JOIN_MODE 2
 /* KE_OPT_PHASH_CFG: pin the streaming K1 kernel's staging (0 = automatic): sub_rows | slot_shift << 8 | luma_buffers << 12
- * | placement << 16 (0 resample fragments on chip, 1 wide-target fragments in L2, 2 both in L2). */
+ * | placement << 16 (0 resample fragments on chip, 1 wide-target fragments in L2, 2 both in L2) | 16-row ring buffers << 20. */
 #define KE_OPT_PHASH_CFG 5
 /* KE_OPT_SSIM_V1=1: K3 on the one-column-per-thread kernel (the one that takes unaligned banks). */
 #define KE_OPT_SSIM_V1 3

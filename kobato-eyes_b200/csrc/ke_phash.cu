@@ -901,7 +901,7 @@ struct V5Layout {
 };
 
 __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, int n_slots, int mma_words /* in shared memory */,
-                                                  int nlb /* luma chunk buffers */) {
+                                                  int nlb /* luma chunk buffers */, int chunk_rows = 32) {
     V5Layout L;
     int off = 0;
     auto take = [&](int bytes, int align) {
@@ -910,7 +910,7 @@ __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, i
         off += bytes;
         return at;
     };
-    L.luma_bytes = (32 * pitch_bytes + 127) / 128 * 128;
+    L.luma_bytes = (chunk_rows * pitch_bytes + 127) / 128 * 128;
     L.raw = take(n_slots * slot_bytes, 128);
     L.luma = take(nlb * L.luma_bytes, 128);
     L.bfrag = take(mma_words * 8, 16);
@@ -947,12 +947,12 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int32_t hi, int32_t lo) {  // sa
 
 // One 32-row luma chunk -> this warp's columns of the row plane.  NT tiles share the k range.
 // WIDE: tiles are the three digits of outputs out0..out0+7; else tile tl is the output pair (out0 + 2 tl, +1).
-template <int NT, bool WIDE>
+template <int NT, bool WIDE, int NRB = 2>
 __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict__ bw, int nk, int pitch_bytes,
-                                        uint8_t* __restrict__ hrow, int out0, int lane) {
-    int32_t c[2][NT][4];
+                                        uint8_t* __restrict__ hrow, int out0, int lane, int row_off = 0) {
+    int32_t c[NRB][NT][4];
 #pragma unroll
-    for (int rb = 0; rb < 2; ++rb)
+    for (int rb = 0; rb < NRB; ++rb)
 #pragma unroll
         for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
@@ -962,19 +962,19 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
     for (int k = 0; k < nk; ++k) {
         uint32_t a0[4], a1[4];
         ldmatrix_x4(a0, a_addr + k * 32);
-        ldmatrix_x4(a1, a_addr + k * 32 + 16 * pitch_bytes);
+        if (NRB == 2) ldmatrix_x4(a1, a_addr + k * 32 + 16 * pitch_bytes);
 #pragma unroll
         for (int tl = 0; tl < NT; ++tl) {
             const uint2 b = bw[(k * NT + tl) * 32];
             mma_u8s8(c[0][tl], a0, b);
-            mma_u8s8(c[1][tl], a1, b);
+            if (NRB == 2) mma_u8s8(c[NRB - 1][tl], a1, b);
         }
     }
     const int g = lane >> 2, t = lane & 3;
     {
         const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
 #pragma unroll
-        for (int rb = 0; rb < 2; ++rb)
+        for (int rb = 0; rb < NRB; ++rb)
 #pragma unroll
             for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
@@ -983,7 +983,7 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
                     const int32_t xb = __shfl_sync(0xffffffffu, c[rb][tl][2 * hf + 1], src);
                     const int32_t d2 = t == 0 ? xa : xb;
                     const int32_t v = c[rb][tl][2 * hf] + (c[rb][tl][2 * hf + 1] << 8) + (d2 << 16);
-                    if (t < 2) hrow[(out0 + 2 * tl + t) * kHP + rb * 16 + hf * 8 + g] = (uint8_t)pack_sat_u8(0, v >> kPrec);
+                    if (t < 2) hrow[(out0 + 2 * tl + t) * kHP + row_off + rb * 16 + hf * 8 + g] = (uint8_t)pack_sat_u8(0, v >> kPrec);
                 }
     }
 }
@@ -1028,6 +1028,7 @@ enum { kBReg = 0, kBSmem = 1, kBGmem = 2 };
 
 struct V5Config {
     int sub_rows, slot_shift, pitch_bytes, nlb;
+    int cr;          // rows per luma ring buffer: 32, or 16 (pointer-fed tap loops only)
     int slot_bytes;  // stride of a raw slot: sub_rows * row_bytes, + slack for the aligned superset when !aligned
     int aligned;     // base, images and rows on 16-byte boundaries and w % 16 == 0: exact copies, vector luma path
     int wide_b, narrow_b;  // kBReg / kBSmem / kBGmem
@@ -1037,11 +1038,12 @@ struct V5Config {
 };
 
 // Wide-target taps with the B fragments behind a pointer (shared or global memory): bands of more than kNKP k-steps.
+template <int NRB>
 __device__ __forceinline__ void v5_taps_wide_mem(uint32_t a_addr, const uint2* __restrict__ bw, int nk, int pitch_bytes,
-                                                 uint8_t* __restrict__ hrow, int out0, int lane) {
+                                                 uint8_t* __restrict__ hrow, int out0, int lane, int row_off) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int rb = 0; rb < 2; ++rb) {
+    for (int rb = 0; rb < NRB; ++rb) {
         int32_t c[3][4];
 #pragma unroll
         for (int tl = 0; tl < 3; ++tl)
@@ -1058,7 +1060,7 @@ __device__ __forceinline__ void v5_taps_wide_mem(uint32_t a_addr, const uint2* _
         for (int hf = 0; hf < 2; ++hf) {
             const int32_t v0 = c[0][2 * hf] + (c[1][2 * hf] << 8) + (c[2][2 * hf] << 16);
             const int32_t v1 = c[0][2 * hf + 1] + (c[1][2 * hf + 1] << 8) + (c[2][2 * hf + 1] << 16);
-            const int row = rb * 16 + hf * 8 + g;
+            const int row = row_off + rb * 16 + hf * 8 + g;
             hrow[(out0 + 2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
             hrow[(out0 + 2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
         }
@@ -1104,11 +1106,14 @@ __device__ __noinline__ void luma_rows_any(const uint8_t* __restrict__ slot, int
 // The staging geometry comes as SCALAR kernel parameters and the shared-memory layout is recomputed in the kernel: with
 // the same values read from a parameter struct the compiler kept them off the uniform datapath and the 512x512 RGB case
 // lost 15 % (measured: 10.7 ms against 9.2 ms per 70 000 images).
-template <int C, bool BMEM, bool ALIGNED>
+// CR = rows per luma ring buffer: 32 (one vertical k-step per buffer), or 16 for long rows — half the ring, so that two
+// CTAs fit an SM again; the tap warps then run the vertical pass after every second buffer.
+template <int C, bool BMEM, bool ALIGNED, int CR = 32>
 __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift,
                                                                    const int pitch_bytes, const int nlb, const int dbg,
                                                                    const V5Config cfg) {
-    constexpr int CR = 32, NW = kV5Tap;
+    constexpr int NW = kV5Tap, NRB = CR / 16;
+    static_assert(CR == 32 || (CR == 16 && BMEM), "16-row buffers come with the pointer-fed tap loops only");
     extern __shared__ __align__(128) uint8_t smem[];
     const int row_bytes = a.w * C;
     const int sub_bytes = sub_rows * row_bytes;
@@ -1119,7 +1124,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     // cfg.narrow_b == kBSmem], in table order
     const int b_first = (BMEM && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
     const int b_last = (BMEM && cfg.narrow_b != kBSmem) ? a.mma_boff[4] : a.mma_words;
-    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb);
+    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR);
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
@@ -1312,17 +1317,22 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                 for (int d = 0; d < 3; ++d)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) vc[u][d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
-            int ci = 0;
-            for (int r0 = 0; r0 < a.h; r0 += CR, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
+            int hc = 0;  // ring buffers consumed of this image; vertical k-step ci = rows / 32
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++hc, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
                 mbar_wait_sleep(&l_full[lb], lph, poll_ns);
+                const int row_off = CR == 32 ? 0 : (hc & 1) * 16;
                 {
                     const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
                     if constexpr (!BMEM) v5_taps_wide_reg(a_addr, breg, nk, pitch_bytes, hrow, 8 * warp, lane);
-                    else v5_taps_wide_mem(a_addr, bmem, nk, pitch_bytes, hrow, 8 * warp, lane);
+                    else v5_taps_wide_mem<NRB>(a_addr, bmem, nk, pitch_bytes, hrow, 8 * warp, lane, row_off);
                 }
                 __syncwarp();  // the eight columns are written
                 if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
-                if (!(dbg & 4)) {
+                // 16-row buffers: the vertical k-step needs both halves of its 32 rows (or the image's last rows; whatever
+                // an earlier chunk left in the other half meets zero taps there)
+                const bool vstep = CR == 32 || (hc & 1) || r0 + CR >= a.h;
+                const int ci = CR == 32 ? hc : hc >> 1;
+                if (vstep && !(dbg & 4)) {
                     const uint32_t b0 = col[t], b1 = col[4 + t];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -1367,15 +1377,18 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         for (int d = 0; d < 3; ++d)
 #pragma unroll
             for (int i = 0; i < 4; ++i) vc[d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
-        int ci = 0;
-        for (int r0 = 0; r0 < a.h; r0 += CR, ++ci, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
+        int hc = 0;
+        for (int r0 = 0; r0 < a.h; r0 += CR, ++hc, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1) {
             mbar_wait_sleep(&l_full[lb], lph, poll_ns);
             const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
-            if (warp < 7) v5_taps<1, false>(a_addr, bw, nk, pitch_bytes, scr, scr_col, lane);
-            else v5_taps<2, false>(a_addr, bw, nk, pitch_bytes, scr, scr_col, lane);
+            const int row_off = CR == 32 ? 0 : (hc & 1) * 16;
+            if (warp < 7) v5_taps<1, false, NRB>(a_addr, bw, nk, pitch_bytes, scr, scr_col, lane, row_off);
+            else v5_taps<2, false, NRB>(a_addr, bw, nk, pitch_bytes, scr, scr_col, lane, row_off);
             __syncwarp();  // the pair's columns are written
             if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
-            if (!(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
+            const bool vstep = CR == 32 || (hc & 1) || r0 + CR >= a.h;
+            const int ci = CR == 32 ? hc : hc >> 1;
+            if (vstep && !(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
                 const uint32_t b0 = col[t], b1 = col[4 + t];
                 const uint4* af = a.vmma + ((size_t)(ci * 3 + 2) * 3) * 32 + lane;
 #pragma unroll
@@ -1412,25 +1425,28 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     cfg.dbg = 0;
     const int wide_words = a.mma_boff[4], narrow_words = a.mma_words - a.mma_boff[4];
     const int wide_chip = nk_wide <= kNKP ? kBReg : kBSmem;
-    auto fits = [&](int budget, int wide, int narrow, int bufs, int sub, int shift) -> bool {
-        if (sub < 1 || sub > 32 || (32 % sub) || sub * row_bytes > (1 << 20) || shift < 1 || shift > 3 || bufs < 1 ||
+    auto fits = [&](int budget, int wide, int narrow, int bufs, int sub, int shift, int cr) -> bool {
+        if (sub < 1 || sub > cr || (cr % sub) || sub * row_bytes > (1 << 20) || shift < 1 || shift > 3 || bufs < 1 ||
             bufs > kMaxLumaBufs)
             return false;
+        if (cr == 16 && wide == kBReg) return false;  // 16-row buffers exist for the pointer-fed tap loops only
         if (a.n * ((a.h + sub - 1) / sub) >= (1ll << 31)) return false;
         // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the luma loads that
         // run a few words past the last pixel
         const int slot = cfg.aligned ? (int)(sub * row_bytes) : (int)((sub * row_bytes + 64 + 127) / 128 * 128);
         const int words = (wide == kBSmem ? wide_words : 0) + (narrow == kBSmem ? narrow_words : 0);
-        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs);
+        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs, cr);
         if (L.total > budget) return false;
-        cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot;
+        cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot, cfg.cr = cr;
         cfg.wide_b = wide, cfg.narrow_b = narrow, cfg.smem_words = words, cfg.L = L;
         return true;
     };
-    if (forced) {  // KE_OPT_PHASH_CFG (tests / tuning): sub_rows | slot_shift << 8 | luma buffers << 12 | placement << 16
+    if (forced) {  // KE_OPT_PHASH_CFG (tests / tuning): sub_rows | slot_shift << 8 | luma buffers << 12 | placement << 16 | cr16 << 20
         const int place = (forced >> 16) & 3;  // 0: on chip, 1: wide fragments in L2, 2: both in L2
-        return fits(227 * 1024, place == 0 ? wide_chip : (nk_wide <= kNKP ? kBReg : kBGmem), place == 2 ? kBGmem : kBSmem,
-                    (forced >> 12) & 15, forced & 255, (forced >> 8) & 15);
+        const int cr = ((forced >> 20) & 1) ? 16 : 32;
+        const int chip = cr == 16 ? kBSmem : wide_chip;
+        return fits(227 * 1024, place == 0 ? chip : (cr == 32 && nk_wide <= kNKP ? kBReg : kBGmem), place == 2 ? kBGmem : kBSmem,
+                    (forced >> 12) & 15, forced & 255, (forced >> 8) & 15, cr);
     }
     // What matters (measured, tools/probe_phash_large.py: 512 / 1024 / 2048 / 4000-pixel rows): a double-buffered luma
     // ring, raw sub-chunks of >= 12 KB (small bulk copies are latency bound: 2-row copies cost half the bandwidth at 2048
@@ -1442,21 +1458,32 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     // two CTAs per SM with everything on chip, as long as a sub-chunk of >= 12 KB (or 16 rows) still fits beside them
     const long long min_slot = std::min<long long>(12 * 1024, 16 * row_bytes);
     for (int sub : {16, 8, 4, 2, 1})
-        if (sub * row_bytes >= min_slot && fits(113 * 1024, wide_chip, kBSmem, 2, sub, 1)) return true;
-    // else one CTA per SM: the largest sub-chunk that fits, fragments moved out to L2 where that is what it takes
+        if (sub * row_bytes >= min_slot && fits(113 * 1024, wide_chip, kBSmem, 2, sub, 1, 32)) return true;
+    // Long rows (resample bands beyond the register budget): one CTA per SM with 16-row luma buffers — the finer hand-off
+    // between luma and tap warps is worth 0.61 -> 0.70 of HBM at 1024 pixels and 0.59 -> 0.71 at 2048 — the largest
+    // sub-chunk that fits, fragments moved out to L2 where that is what it takes.
     const Place places[] = {{227 * 1024, wide_chip, kBSmem}, {227 * 1024, wide_l2, kBSmem}, {227 * 1024, wide_l2, kBGmem}};
+    if (nk_wide > kNKP)
+        for (int sub : {16, 8, 4, 2, 1})
+            for (const Place& pl : places)
+                if (fits(pl.budget, pl.wide, pl.narrow, 2, sub, 1, 16)) return true;
     for (int bufs : {2, 1})
         for (int sub : {16, 8, 4, 2, 1})
             for (const Place& pl : places)
-                if (fits(pl.budget, pl.wide, pl.narrow, bufs, sub, 1)) return true;
+                if (fits(pl.budget, pl.wide, pl.narrow, bufs, sub, 1, 32)) return true;
+    if (nk_wide > kNKP)
+        for (int sub : {16, 8, 4, 2, 1})
+            for (const Place& pl : places)
+                if (fits(pl.budget, pl.wide, pl.narrow, 1, sub, 1, 16)) return true;
     return false;
 }
 
 template <int C>
 int launch_v5(ke_ctx* ctx, const PhashArgs& a, V5Config& cfg, cudaStream_t s) {
     const bool bmem = !(cfg.wide_b == kBReg && cfg.narrow_b == kBSmem);
-    auto kernel = cfg.aligned ? (bmem ? ke_phash_v5_kernel<C, true, true> : ke_phash_v5_kernel<C, false, true>)
-                              : (bmem ? ke_phash_v5_kernel<C, true, false> : ke_phash_v5_kernel<C, false, false>);
+    auto kernel = cfg.aligned ? (bmem ? ke_phash_v5_kernel<C, true, true, 32> : ke_phash_v5_kernel<C, false, true, 32>)
+                              : (bmem ? ke_phash_v5_kernel<C, true, false, 32> : ke_phash_v5_kernel<C, false, false, 32>);
+    if (cfg.cr == 16) kernel = cfg.aligned ? ke_phash_v5_kernel<C, true, true, 16> : ke_phash_v5_kernel<C, true, false, 16>;
     KE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.L.total));
     int per_sm = 0;
     KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kV5Threads, cfg.L.total));

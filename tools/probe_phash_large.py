@@ -41,11 +41,13 @@ for (h, w, c) in ((512, 512, 3), (1024, 1024, 3), (1536, 2048, 3), (3000, 4000, 
         ops.synth_images_device(lo, k, h, w, c, n_set=n, out=bank[lo:lo + k])
     res = {}
     cfgs = [("auto", 0)]
-    for place in (0, 1, 2):
-        for bufs in (4, 3, 2, 1):
-            for sub in (16, 8, 4, 2, 1):
-                for shift in (1, 2):
-                    cfgs.append((f"p{place} b{bufs} sub{sub} s{shift}", sub | shift << 8 | bufs << 12 | place << 16))
+    for cr16 in (0, 1):
+        for place in (0, 1, 2):
+            for bufs in (4, 3, 2, 1):
+                for sub in (16, 8, 4, 2, 1):
+                    for shift in (1, 2):
+                        cfgs.append((f"{'cr16 ' if cr16 else ''}p{place} b{bufs} sub{sub} s{shift}",
+                                     sub | shift << 8 | bufs << 12 | place << 16 | cr16 << 20))
     for name, value in cfgs:
         ctx.set_option(nat.KE_OPT_PHASH_CFG, value)
         try:
