@@ -353,7 +353,8 @@ def run_cuda(args) -> dict:
     # kernel with its resample fragments in shared memory (1024 px) / L2 (2048 px); banks of 6 GB >> L2
     roof_k1_large = {}
     for (hh, ww) in ((1024, 1024), (1536, 2048)):
-        cnt_l = max(64, int(6e9) // (hh * ww * C))
+        # ~6 GB banks, a whole number of images per persistent CTA (296 = 2 x 148 covers one and two CTAs per SM)
+        cnt_l = max(296, int(6e9) // (hh * ww * C) // 296 * 296)
         big = torch.empty((cnt_l, hh, ww, C), dtype=torch.uint8, device=dev)
         for lo in range(0, cnt_l, 256):
             c_ = min(256, cnt_l - lo)

@@ -404,6 +404,36 @@ def test_phash_streaming_and_generic_kernels_agree():
                 assert torch.equal(off[2][0], gen[3][0]) and torch.equal(off[2][1], gen[3][1]), (h, w, c, shift)
 
 
+def test_phash_every_staging_configuration_gives_the_same_hashes():
+    """The streaming K1 kernel under pinned staging configurations (KE_OPT_PHASH_CFG: sub-chunk rows, raw slots, luma
+    ring buffers of 32 or 16 rows, resample fragments on chip / in L2): every configuration that fits a geometry must give
+    the automatic choice's planes and hashes, on short and long rows, aligned or not."""
+    torch = _torch()
+    from kobato_b200 import _native as nat
+
+    ctx = nat.context(torch.cuda.current_device())
+    for (h, w, c, n) in ((200, 512, 3, 40), (150, 1024, 3, 12), (97, 2048, 3, 6), (130, 1000, 1, 9), (77, 1201, 3, 5), (64, 640, 4, 7)):
+        imgs = ops.synth_images_device(0, n, h, w, c, n_set=n)
+        want = ops.phash_dhash_batch(imgs, want_planes=True)
+        tried = 0
+        for cr16 in (0, 1):
+            for place in (0, 1, 2):
+                for bufs in (1, 2, 3):
+                    for sub in (16, 4, 1):
+                        value = sub | 1 << 8 | bufs << 12 | place << 16 | cr16 << 20
+                        ctx.set_option(nat.KE_OPT_PHASH_CFG, value)
+                        try:
+                            got = ops.phash_dhash_batch(imgs, want_planes=True)
+                        except nat.KobatoNativeError:
+                            continue  # this configuration does not fit the geometry
+                        finally:
+                            ctx.set_option(nat.KE_OPT_PHASH_CFG, 0)
+                        tried += 1
+                        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), (h, w, c, hex(value))
+                        assert torch.equal(got[2][0], want[2][0]) and torch.equal(got[2][1], want[2][1]), (h, w, c, hex(value))
+        assert tried >= 12, (h, w, c, tried)
+
+
 @pytest.mark.parametrize("mode", [2, 3])
 def test_join_hybrid_and_bit_sliced_kernels_match_oracle(mode):
     """K2 has a second, LOP3-only (bit-sliced carry-save) kernel that runs concurrently with the POPC
