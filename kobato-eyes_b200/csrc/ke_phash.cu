@@ -889,6 +889,9 @@ constexpr int kV5Tap = 8, kV5Luma = 4;
 // Registers per role (setmaxnreg per 4-warp group; the CTA launches with 80 per thread): the wide-target warps hold their
 // B fragments and the vertical accumulators in registers and take what the other two groups hand back.
 constexpr int kV5WideRegs = 104, kV5NarrowRegs = 72, kV5LumaRegs = 64;
+// one CTA per SM (168 per thread at launch): wide warps holding 16 / 32 k-steps of fragments (96 / 192 registers)
+constexpr int kV5WideRegs16 = 200, kV5WideRegs32 = 232, kV5NarrowRegsOne = 104;
+static_assert(kV5WideRegs32 + kV5NarrowRegsOne + kV5LumaRegs <= 3 * 168, "register pool of the 3 warp groups, one CTA per SM");
 static_assert(kV5WideRegs + kV5NarrowRegs + kV5LumaRegs == 3 * 80, "register pool of the 3 warp groups");
 constexpr int kV5Threads = (kV5Tap + kV5Luma) * 32;
 constexpr int kHP = 48;   // horizontal-pass output plane, stored TRANSPOSED: [column 0..47][row 0..31], column pitch 48 B
@@ -992,18 +995,19 @@ __device__ __forceinline__ void v5_taps(uint32_t a_addr, const uint2* __restrict
 // Wide-target warps keep their B fragments (3 digits x <= kNKP k-steps) in REGISTERS for the whole kernel: no
 // shared-memory table, no LDS per MMA.  One 16-row block at a time keeps the accumulators at 12 registers.
 constexpr int kNKP = 8;
-__device__ __forceinline__ void v5_taps_wide_reg(uint32_t a_addr, const uint2 (&breg)[kNKP][3], int nk, int pitch_bytes,
-                                                 uint8_t* __restrict__ hrow, int out0, int lane) {
+template <int NKW, int NRB>
+__device__ __forceinline__ void v5_taps_wide_reg(uint32_t a_addr, const uint2 (&breg)[NKW][3], int nk, int pitch_bytes,
+                                                 uint8_t* __restrict__ hrow, int out0, int lane, int row_off) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int rb = 0; rb < 2; ++rb) {
+    for (int rb = 0; rb < NRB; ++rb) {
         int32_t c[3][4];
 #pragma unroll
         for (int tl = 0; tl < 3; ++tl)
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[tl][i] = tl == 0 ? (1 << (kPrec - 1)) : 0;
 #pragma unroll
-        for (int k = 0; k < kNKP; ++k) {
+        for (int k = 0; k < NKW; ++k) {
             if (k < nk) {
                 uint32_t a0[4];
                 ldmatrix_x4(a0, a_addr + k * 32 + rb * 16 * pitch_bytes);
@@ -1015,7 +1019,7 @@ __device__ __forceinline__ void v5_taps_wide_reg(uint32_t a_addr, const uint2 (&
         for (int hf = 0; hf < 2; ++hf) {
             const int32_t v0 = c[0][2 * hf] + (c[1][2 * hf] << 8) + (c[2][2 * hf] << 16);
             const int32_t v1 = c[0][2 * hf + 1] + (c[1][2 * hf + 1] << 8) + (c[2][2 * hf + 1] << 16);
-            const int row = rb * 16 + hf * 8 + g;
+            const int row = row_off + rb * 16 + hf * 8 + g;
             hrow[(out0 + 2 * t) * kHP + row] = (uint8_t)pack_sat_u8(0, v0 >> kPrec);
             hrow[(out0 + 2 * t + 1) * kHP + row] = (uint8_t)pack_sat_u8(0, v1 >> kPrec);
         }
@@ -1032,6 +1036,7 @@ struct V5Config {
     int slot_bytes;  // stride of a raw slot: sub_rows * row_bytes, + slack for the aligned superset when !aligned
     int aligned;     // base, images and rows on 16-byte boundaries and w % 16 == 0: exact copies, vector luma path
     int wide_b, narrow_b;  // kBReg / kBSmem / kBGmem
+    int nkw;         // k-steps of wide-target fragments a warp keeps in registers: 8 (two CTAs per SM), 16 / 32 (one), 0: none
     int smem_words;  // uint2 words of B fragments kept in shared memory
     int dbg;
     V5Layout L;
@@ -1100,20 +1105,29 @@ __device__ __noinline__ void luma_rows_any(const uint8_t* __restrict__ slot, int
     }
 }
 
-// BMEM = false: wide-target fragments in registers, narrow-target ones in shared memory (widths up to ~512: the
-// benchmark geometry; identical to the round-1 kernel).  BMEM = true: both behind pointers into shared or global memory.
+// NKW = k-steps of wide-target resample fragments each wide warp keeps in REGISTERS:
+//   8   bands of <= 8 k-steps (widths up to ~512: the benchmark geometry); narrow-target fragments in shared memory;
+//       80 registers per thread, two CTAs per SM.
+//   16 / 32   longer rows (up to ~1100 / ~2200 pixels): ONE CTA per SM with 168 registers per thread at launch, which
+//       setmaxnreg redistributes — the wide warps take 200 / 232 and hold their whole band.  Shared memory was the
+//       bound there (ncu: the LSU data pipe at 60 % + the bulk-copy writes at 0.70 of HBM, a third of it fragment
+//       reads); narrow-target fragments behind a pointer (shared memory or L2).
+//   0   bands beyond that: every fragment behind a pointer into shared or global memory (L2).
 // ALIGNED = true: base, images and rows on 16-byte boundaries and w % 16 == 0 (exact copies, vector luma path).
 // The staging geometry comes as SCALAR kernel parameters and the shared-memory layout is recomputed in the kernel: with
 // the same values read from a parameter struct the compiler kept them off the uniform datapath and the 512x512 RGB case
 // lost 15 % (measured: 10.7 ms against 9.2 ms per 70 000 images).
-// CR = rows per luma ring buffer: 32 (one vertical k-step per buffer), or 16 for long rows — half the ring, so that two
-// CTAs fit an SM again; the tap warps then run the vertical pass after every second buffer.
-template <int C, bool BMEM, bool ALIGNED, int CR = 32>
-__global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift,
-                                                                   const int pitch_bytes, const int nlb, const int dbg,
-                                                                   const V5Config cfg) {
+// CR = rows per luma ring buffer: 32 (one vertical k-step per buffer), or 16 for long rows — half the ring and a finer
+// hand-off between luma and tap warps; the tap warps then run the vertical pass after every second buffer.
+template <int C, int NKW, bool ALIGNED, int CR = 32>
+__global__ void __launch_bounds__(kV5Threads, NKW > kNKP ? 1 : 2)
+ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, const int pitch_bytes, const int nlb,
+                   const int dbg, const V5Config cfg) {
     constexpr int NW = kV5Tap, NRB = CR / 16;
-    static_assert(CR == 32 || (CR == 16 && BMEM), "16-row buffers come with the pointer-fed tap loops only");
+    constexpr bool BMEM = NKW != kNKP;  // narrow-target (and, NKW == 0, wide-target) fragments behind a pointer
+    constexpr bool ONE = NKW > kNKP;    // one CTA per SM
+    static_assert(NKW == 0 || NKW == kNKP || NKW == 16 || NKW == 32, "register-resident bands of 8, 16 or 32 k-steps");
+    static_assert(CR == 32 || (CR == 16 && BMEM), "16-row buffers come with the pointer-fed narrow tap loops only");
     extern __shared__ __align__(128) uint8_t smem[];
     const int row_bytes = a.w * C;
     const int sub_bytes = sub_rows * row_bytes;
@@ -1122,7 +1136,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     const uint32_t slot_mask = (uint32_t)n_slots - 1u;
     // B fragments in shared memory: [wide-target warps 0..3 when cfg.wide_b == kBSmem][narrow-target warps 4..7 when
     // cfg.narrow_b == kBSmem], in table order
-    const int b_first = (BMEM && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
+    const int b_first = (NKW == 0 && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
     const int b_last = (BMEM && cfg.narrow_b != kBSmem) ? a.mma_boff[4] : a.mma_words;
     const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR);
     uint8_t* s_raw = smem + L.raw;
@@ -1161,7 +1175,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     __syncthreads();
 
     if (warp >= kV5Tap) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5LumaRegs));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5LumaRegs));  // (from 80, or 168 with one CTA per SM)
         // ===== luma warps: raw rows -> (TMA) raw ring -> luma chunk ring =====
         // A raw slot is refilled by whichever luma warp finishes reading it LAST (a shared-memory counter
         // per slot tells): no issuer warp, no "slot empty" barrier to wait on, the copy of sub-chunk
@@ -1282,7 +1296,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     }
 
     // ===== tap warps =====
-    const int nk = (dbg & 2) ? 0 : a.mma_nk[warp];
+    const int nk = ((dbg & 2) || ((dbg & 32) && warp < 4) || ((dbg & 64) && warp >= 4)) ? 0 : a.mma_nk[warp];  // probes
     const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mma_k0[warp] * 32);
     const uint32_t poll_ns = (uint32_t)dbg >> 8;
     const int g = lane >> 2, t = lane & 3;
@@ -1293,17 +1307,17 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
         // ---- wide target: warp q owns outputs 8q..8q+7 END TO END — horizontal taps (B fragments in registers), then
         // the vertical pass of exactly those eight columns (both 16-row halves of the 32x32 plane).  It reads back only
         // what it wrote itself, so it never meets another tap warp before the image is finished.
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kV5WideRegs));
-        uint2 breg[BMEM ? 1 : kNKP][3];
-        if (!BMEM) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NKW == 32 ? kV5WideRegs32 : NKW == 16 ? kV5WideRegs16 : kV5WideRegs));
+        uint2 breg[NKW ? NKW : 1][3];
+        if constexpr (NKW > 0) {
 #pragma unroll
-            for (int k = 0; k < (BMEM ? 1 : kNKP); ++k)
+            for (int k = 0; k < NKW; ++k)
 #pragma unroll
                 for (int tl = 0; tl < 3; ++tl)
                     breg[k][tl] = k < a.mma_nk[warp] ? __ldg(a.mma_b + a.mma_boff[warp] + (k * 3 + tl) * 32 + lane) : make_uint2(0u, 0u);
         }
-        // BMEM: bands of more than kNKP k-steps (widths above ~512) — fragments from shared memory, or from global memory
-        // (L2) when they do not fit next to the luma ring
+        // NKW == 0: bands of more than 32 k-steps — fragments from shared memory, or from global memory (L2) when they do
+        // not fit next to the luma ring
         const uint2* bmem = (cfg.wide_b == kBSmem ? s_b + (a.mma_boff[warp] - b_first) : a.mma_b + a.mma_boff[warp]) + lane;
         uint8_t* hrow = s_hrow;  // columns 8q..8q+7 of plane 0 are this warp's private scratch
         const uint32_t* col = reinterpret_cast<const uint32_t*>(hrow + (8 * warp + g) * kHP);
@@ -1323,7 +1337,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
                 const int row_off = CR == 32 ? 0 : (hc & 1) * 16;
                 {
                     const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + a_off;
-                    if constexpr (!BMEM) v5_taps_wide_reg(a_addr, breg, nk, pitch_bytes, hrow, 8 * warp, lane);
+                    if constexpr (NKW > 0) v5_taps_wide_reg<NKW, NRB>(a_addr, breg, nk, pitch_bytes, hrow, 8 * warp, lane, row_off);
                     else v5_taps_wide_mem<NRB>(a_addr, bmem, nk, pitch_bytes, hrow, 8 * warp, lane, row_off);
                 }
                 __syncwarp();  // the eight columns are written
@@ -1363,7 +1377,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) ke_phash_v5_kernel(const PhashA
     // the pair's columns go into a private 8-column scratch (plane 1 of the row plane) and come straight back as the B
     // fragment of the 8x9 plane's vertical pass — six of the tile's eight columns are padding, three MMAs per chunk
     // are cheap, and no tap warp waits for another before the image is finished.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kV5NarrowRegs));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ONE ? kV5NarrowRegsOne : kV5NarrowRegs));
     const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
     if (BMEM && cfg.narrow_b == kBGmem) bw = a.mma_b + a.mma_boff[warp] + lane;
     uint8_t* scr = s_hrow + kHCols * kHP;                 // plane 1
@@ -1424,12 +1438,16 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     cfg.pitch_bytes = (a.w + 31) / 32 * 32 + 16;  // rows of 16-byte units, odd count: ldmatrix reads are conflict free
     cfg.dbg = 0;
     const int wide_words = a.mma_boff[4], narrow_words = a.mma_words - a.mma_boff[4];
-    const int wide_chip = nk_wide <= kNKP ? kBReg : kBSmem;
+    // wide-target bands of <= 8 k-steps stay in registers at two CTAs per SM, of <= 32 at one CTA per SM
+    const int nkw_reg = nk_wide <= kNKP ? kNKP : nk_wide <= 16 ? 16 : nk_wide <= 32 ? 32 : 0;
     auto fits = [&](int budget, int wide, int narrow, int bufs, int sub, int shift, int cr) -> bool {
         if (sub < 1 || sub > cr || (cr % sub) || sub * row_bytes > (1 << 20) || shift < 1 || shift > 3 || bufs < 1 ||
             bufs > kMaxLumaBufs)
             return false;
-        if (cr == 16 && wide == kBReg) return false;  // 16-row buffers exist for the pointer-fed tap loops only
+        if (wide == kBReg && nkw_reg == 0) return false;
+        const int nkw = wide == kBReg ? nkw_reg : 0;
+        if (nkw == kNKP && (cr == 16 || narrow != kBSmem)) return false;  // the two-CTA kernel: 32-row buffers, fragments on chip
+        if (nkw > kNKP && budget < 227 * 1024) return false;                // 168 registers per thread: one CTA per SM
         if (a.n * ((a.h + sub - 1) / sub) >= (1ll << 31)) return false;
         // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the luma loads that
         // run a few words past the last pixel
@@ -1438,31 +1456,40 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
         const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs, cr);
         if (L.total > budget) return false;
         cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot, cfg.cr = cr;
-        cfg.wide_b = wide, cfg.narrow_b = narrow, cfg.smem_words = words, cfg.L = L;
+        cfg.wide_b = wide, cfg.narrow_b = narrow, cfg.smem_words = words, cfg.L = L, cfg.nkw = nkw;
         return true;
     };
     if (forced) {  // KE_OPT_PHASH_CFG (tests / tuning): sub_rows | slot_shift << 8 | luma buffers << 12 | placement << 16 | cr16 << 20
-        const int place = (forced >> 16) & 3;  // 0: on chip, 1: wide fragments in L2, 2: both in L2
+        // placement 0: wide fragments in registers where the band allows (else shared memory), narrow in shared memory;
+        // 1: wide in L2 (registers where the band fits the two-CTA kernel), narrow in shared memory; 2: wide as 1, narrow in
+        // L2; 3: both in shared memory (the pointer-fed loops)
+        const int place = (forced >> 16) & 3;
         const int cr = ((forced >> 20) & 1) ? 16 : 32;
-        const int chip = cr == 16 ? kBSmem : wide_chip;
-        return fits(227 * 1024, place == 0 ? chip : (cr == 32 && nk_wide <= kNKP ? kBReg : kBGmem), place == 2 ? kBGmem : kBSmem,
-                    (forced >> 12) & 15, forced & 255, (forced >> 8) & 15, cr);
+        const int chip = nkw_reg && !(nkw_reg == kNKP && cr == 16) ? kBReg : kBSmem;
+        const int l2 = nkw_reg == kNKP && cr == 32 ? kBReg : kBGmem;
+        const int wide = place == 0 ? chip : place == 3 ? kBSmem : l2;
+        return fits(227 * 1024, wide, place == 2 ? kBGmem : kBSmem, (forced >> 12) & 15, forced & 255, (forced >> 8) & 15, cr);
     }
-    // What matters (measured, tools/probe_phash_large.py: 512 / 1024 / 2048 / 4000-pixel rows): a double-buffered luma
-    // ring, raw sub-chunks of >= 12 KB (small bulk copies are latency bound: 2-row copies cost half the bandwidth at 2048
-    // pixels) and, where both still fit, two CTAs per SM (RGBA at 512: 13.9 ms with two CTAs and 8-row sub-chunks, 17.6 ms
-    // with one CTA and 16-row ones); where the resample fragments sit hardly matters (they are L2-resident and read with
-    // the same pattern by every CTA), so they move out of shared memory whenever that buys a larger sub-chunk.
+    // What matters (measured, tools/probe_phash_large.py and probe_phash_roles.py: 512 / 1024 / 2048 / 4000-pixel rows):
+    // a double-buffered luma ring, raw sub-chunks of >= 12 KB (small bulk copies are latency bound: 2-row copies cost
+    // half the bandwidth at 2048 pixels), two CTAs per SM where everything still fits — and, on longer rows, as little
+    // shared-memory traffic per pixel as possible: the wide-target fragments in registers (one CTA per SM).
     struct Place { int budget, wide, narrow; };
-    const int wide_l2 = nk_wide <= kNKP ? kBReg : kBGmem;
     // two CTAs per SM with everything on chip, as long as a sub-chunk of >= 12 KB (or 16 rows) still fits beside them
     const long long min_slot = std::min<long long>(12 * 1024, 16 * row_bytes);
-    for (int sub : {16, 8, 4, 2, 1})
-        if (sub * row_bytes >= min_slot && fits(113 * 1024, wide_chip, kBSmem, 2, sub, 1, 32)) return true;
-    // Long rows (resample bands beyond the register budget): one CTA per SM with 16-row luma buffers — the finer hand-off
-    // between luma and tap warps is worth 0.61 -> 0.70 of HBM at 1024 pixels and 0.59 -> 0.71 at 2048 — the largest
-    // sub-chunk that fits, fragments moved out to L2 where that is what it takes.
+    if (nkw_reg == kNKP)
+        for (int sub : {16, 8, 4, 2, 1})
+            if (sub * row_bytes >= min_slot && fits(113 * 1024, kBReg, kBSmem, 2, sub, 1, 32)) return true;
+    // Long rows: one CTA per SM.  With pointer-fed fragments 16-row luma buffers — a finer hand-off between luma and tap
+    // warps — were worth 0.61 -> 0.70 of HBM at 1024 pixels and 0.59 -> 0.71 at 2048; the largest sub-chunk that fits, the
+    // narrow-target fragments moved out to L2 where that is what it takes.
+    const int wide_chip = nkw_reg ? kBReg : kBSmem, wide_l2 = nkw_reg ? kBReg : kBGmem;
     const Place places[] = {{227 * 1024, wide_chip, kBSmem}, {227 * 1024, wide_l2, kBSmem}, {227 * 1024, wide_l2, kBGmem}};
+    // register-resident bands: 32-row buffers while two of them fit beside >= 12 KB sub-chunks (1024 pixels: 0.855 of HBM
+    // against 0.787 with 16-row buffers), else 16-row buffers (2048 pixels: 0.862)
+    if (nkw_reg > kNKP)
+        for (int sub : {16, 8, 4, 2, 1})
+            if (sub * row_bytes >= min_slot && fits(227 * 1024, kBReg, kBSmem, 2, sub, 1, 32)) return true;
     if (nk_wide > kNKP)
         for (int sub : {16, 8, 4, 2, 1})
             for (const Place& pl : places)
@@ -1480,10 +1507,23 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
 
 template <int C>
 int launch_v5(ke_ctx* ctx, const PhashArgs& a, V5Config& cfg, cudaStream_t s) {
-    const bool bmem = !(cfg.wide_b == kBReg && cfg.narrow_b == kBSmem);
-    auto kernel = cfg.aligned ? (bmem ? ke_phash_v5_kernel<C, true, true, 32> : ke_phash_v5_kernel<C, false, true, 32>)
-                              : (bmem ? ke_phash_v5_kernel<C, true, false, 32> : ke_phash_v5_kernel<C, false, false, 32>);
-    if (cfg.cr == 16) kernel = cfg.aligned ? ke_phash_v5_kernel<C, true, true, 16> : ke_phash_v5_kernel<C, true, false, 16>;
+    using Kernel = void (*)(const PhashArgs, const int, const int, const int, const int, const int, const V5Config);
+    Kernel kernel = nullptr;
+    const bool al = cfg.aligned != 0, c16 = cfg.cr == 16;
+    switch (cfg.nkw) {
+        case kNKP: kernel = al ? ke_phash_v5_kernel<C, kNKP, true, 32> : ke_phash_v5_kernel<C, kNKP, false, 32>; break;
+        case 16:
+            kernel = c16 ? (al ? ke_phash_v5_kernel<C, 16, true, 16> : ke_phash_v5_kernel<C, 16, false, 16>)
+                         : (al ? ke_phash_v5_kernel<C, 16, true, 32> : ke_phash_v5_kernel<C, 16, false, 32>);
+            break;
+        case 32:
+            kernel = c16 ? (al ? ke_phash_v5_kernel<C, 32, true, 16> : ke_phash_v5_kernel<C, 32, false, 16>)
+                         : (al ? ke_phash_v5_kernel<C, 32, true, 32> : ke_phash_v5_kernel<C, 32, false, 32>);
+            break;
+        default:
+            kernel = c16 ? (al ? ke_phash_v5_kernel<C, 0, true, 16> : ke_phash_v5_kernel<C, 0, false, 16>)
+                         : (al ? ke_phash_v5_kernel<C, 0, true, 32> : ke_phash_v5_kernel<C, 0, false, 32>);
+    }
     KE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.L.total));
     int per_sm = 0;
     KE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kV5Threads, cfg.L.total));

@@ -406,7 +406,7 @@ def test_phash_streaming_and_generic_kernels_agree():
 
 def test_phash_every_staging_configuration_gives_the_same_hashes():
     """The streaming K1 kernel under pinned staging configurations (KE_OPT_PHASH_CFG: sub-chunk rows, raw slots, luma
-    ring buffers of 32 or 16 rows, resample fragments on chip / in L2): every configuration that fits a geometry must give
+    ring buffers of 32 or 16 rows, resample fragments in registers / shared memory / L2): every configuration that fits a geometry must give
     the automatic choice's planes and hashes, on short and long rows, aligned or not."""
     torch = _torch()
     from kobato_b200 import _native as nat
@@ -417,7 +417,7 @@ def test_phash_every_staging_configuration_gives_the_same_hashes():
         want = ops.phash_dhash_batch(imgs, want_planes=True)
         tried = 0
         for cr16 in (0, 1):
-            for place in (0, 1, 2):
+            for place in (0, 1, 2, 3):
                 for bufs in (1, 2, 3):
                     for sub in (16, 4, 1):
                         value = sub | 1 << 8 | bufs << 12 | place << 16 | cr16 << 20

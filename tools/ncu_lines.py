@@ -23,7 +23,9 @@ data = [r for r in rows[s + 2:e] if len(r) > ii]
 base = int(data[0][ia], 16)
 # map function offsets -> source line from nvdisasm -g output
 fn = re.search(r"ke_\w+_kernel\w*", kname).group(0)
-tmpl = re.findall(r"\(int\)(\d+)", kname)
+tmpl = re.findall(r"\((?:int|bool)\)(\d+)", kname)
+if not tmpl and "<" in kname:  # newer ncu prints "kernel<3, 1, 1, 16>(...)": ints and bools alike
+    tmpl = re.findall(r"\d+", kname[kname.index(fn) + len(fn):].split(">")[0])
 line_of = {}
 cur = None
 infn = False
@@ -32,7 +34,7 @@ for ln in open(sass):
     m = re.match(r"\s*\.section\s+\.text\.(\S+)", ln)
     if m:
         name = m.group(1)
-        infn = (fn + "I" in name or fn + "E" in name) and "".join(f"Li{t}E" for t in tmpl) in name
+        infn = (fn + "I" in name or fn + "E" in name) and re.search("".join(f"L[ib]{t}E" for t in tmpl) + "E", name) is not None
         continue
     if not infn:
         continue

@@ -42,7 +42,7 @@ for (h, w, c) in ((512, 512, 3), (1024, 1024, 3), (1536, 2048, 3), (3000, 4000, 
     res = {}
     cfgs = [("auto", 0)]
     for cr16 in (0, 1):
-        for place in (0, 1, 2):
+        for place in (0, 1, 2, 3):
             for bufs in (4, 3, 2, 1):
                 for sub in (16, 8, 4, 2, 1):
                     for shift in (1, 2):
