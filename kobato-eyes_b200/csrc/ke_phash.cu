@@ -64,6 +64,8 @@ struct HTable {           // horizontal pass, one per input width
     uint2* d_mma_b = nullptr;
     int mma_words = 0;           // uint2 words in d_mma_b (0: this width is not served by v5)
     int mma_k0[8] = {}, mma_nk[8] = {}, mma_boff[8] = {};
+    // narrow target split by k range: warp 4 + j owns k-steps [mmaq_k0[j], + mmaq_nk[j]) of ALL nine outputs (four tiles)
+    int mmaq_k0[4] = {}, mmaq_nk[4] = {}, mmaq_boff[4] = {}, mmaq_kq = 0;
 };
 struct VTable {           // vertical pass, one per input height
     int* d_kk32 = nullptr;
@@ -179,6 +181,8 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
     // {a.d0, a.d1, b.d0, b.d1, a.d2, b.d2, 0, 0}; warp 7 carries the pairs (6,7) and (8,-).
     std::vector<uint2> mma_b;
     int mma_k0[8], mma_nk[8], mma_boff[8];
+    int mmaq_k0[4] = {}, mmaq_nk[4] = {}, mmaq_boff[4] = {}, mmaq_kq = 0;
+    int mma_words_ptr = 0;  // words of the per-output-band tables above (what the pointer-fed kernel may copy to shared memory)
     bool mma_ok = true;  // any width: taps are zero outside an output's support, so the padding of the last k-step adds nothing
     if (mma_ok) {
         std::vector<int32_t> kkP, bdP, kkD, bdD;
@@ -243,6 +247,39 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
                         mma_b.push_back(make_uint2(wd[0], wd[1]));
                     }
         }
+    // The same nine outputs split by K instead: narrow warp j takes a quarter of the row's k-steps for every output, so
+    // each luma byte is read by ONE narrow warp (not by all four, whose output bands nearly cover the row) and the
+    // quarter-band fits registers.  Four tiles per k-step: tile T = {a.d0, a.d1, b.d0, b.d1, a.d2, b.d2, e0, e1} with
+    // (a, b) = outputs (2T, 2T + 1); the ninth output rides in the spare columns: e = (8.d0, 8.d1) in tile 0, (8.d2, -) in
+    // tile 1.  The warps exchange their partial sums through shared memory (see the kernel).
+    if (mma_ok) {
+        mma_words_ptr = (int)mma_b.size();
+        const int KT = (w + 31) / 32;
+        mmaq_kq = (KT + 3) / 4;
+        for (int j = 0; j < 4; ++j) {
+            mmaq_k0[j] = j * mmaq_kq;
+            mmaq_nk[j] = std::max(0, std::min(mmaq_kq, KT - j * mmaq_kq));
+            mmaq_boff[j] = (int)mma_b.size();
+            for (int k = 0; k < mmaq_nk[j]; ++k)
+                for (int T = 0; T < 4; ++T)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int n = lane >> 2, t4 = lane & 3;
+                        static const int sel_out[6] = {0, 0, 1, 1, 0, 1}, sel_d[6] = {0, 1, 0, 1, 2, 2};
+                        int out = -1, dg = 0;
+                        if (n < 6) out = kOutW + 2 * T + sel_out[n], dg = sel_d[n];
+                        else if (T == 0) out = kOutW + 8, dg = n - 6;
+                        else if (T == 1 && n == 6) out = kOutW + 8, dg = 2;
+                        uint32_t wd[2] = {0, 0};
+                        for (int half = 0; half < 2; ++half)
+                            for (int i = 0; i < 4; ++i) {
+                                const int x = (mmaq_k0[j] + k) * 32 + half * 16 + 4 * t4 + i;
+                                const int dv = out < 0 ? 0 : digit(tap(out, x), dg);
+                                wd[half] |= ((uint32_t)dv & 0xFFu) << (8 * i);
+                            }
+                        mma_b.push_back(make_uint2(wd[0], wd[1]));
+                    }
+            }
+        }
     }
     HTable t;
     t.n_items = (int)items.size();
@@ -253,8 +290,10 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
     if ((rc = upload(meta, &t.d_meta))) return rc;
     if (mma_ok) {
         if ((rc = upload(mma_b, &t.d_mma_b))) return rc;
-        t.mma_words = (int)mma_b.size();
+        t.mma_words = mma_words_ptr;
         for (int i = 0; i < 8; ++i) t.mma_k0[i] = mma_k0[i], t.mma_nk[i] = mma_nk[i], t.mma_boff[i] = mma_boff[i];
+        for (int i = 0; i < 4; ++i) t.mmaq_k0[i] = mmaq_k0[i], t.mmaq_nk[i] = mmaq_nk[i], t.mmaq_boff[i] = mmaq_boff[i];
+        t.mmaq_kq = mmaq_kq;
     }
     auto ins = ctx->tables->h.emplace(w, t);
     *out = &ins.first->second;
@@ -403,6 +442,7 @@ struct PhashArgs {
     const uint2* mma_b;
     int mma_words;
     int mma_k0[8], mma_nk[8], mma_boff[8];
+    int mmaq_k0[4], mmaq_nk[4], mmaq_boff[4], mmaq_kq;
     const uint4* vmma;
     int v_lo[3], v_hi[3];
     const int* kk32;
@@ -890,21 +930,26 @@ constexpr int kV5Tap = 8, kV5Luma = 4;
 // B fragments and the vertical accumulators in registers and take what the other two groups hand back.
 constexpr int kV5WideRegs = 104, kV5NarrowRegs = 72, kV5LumaRegs = 64;
 // one CTA per SM (168 per thread at launch): wide warps holding 16 / 32 k-steps of fragments (96 / 192 registers)
-constexpr int kV5WideRegs16 = 200, kV5WideRegs32 = 232, kV5NarrowRegsOne = 104;
-static_assert(kV5WideRegs32 + kV5NarrowRegsOne + kV5LumaRegs <= 3 * 168, "register pool of the 3 warp groups, one CTA per SM");
+// and narrow warps holding their quarter of the row: 9 / 18 k-steps x 4 tiles (72 / 144 registers)
+constexpr int kV5WideRegs16 = 200, kV5WideRegs32 = 232, kV5NarrowRegs16 = 144, kV5NarrowRegs32 = 200;
+static_assert(kV5WideRegs32 + kV5NarrowRegs32 + kV5LumaRegs <= 3 * 168 && kV5WideRegs16 + kV5NarrowRegs16 + kV5LumaRegs <= 3 * 168,
+              "register pool of the 3 warp groups, one CTA per SM");
 static_assert(kV5WideRegs + kV5NarrowRegs + kV5LumaRegs == 3 * 80, "register pool of the 3 warp groups");
 constexpr int kV5Threads = (kV5Tap + kV5Luma) * 32;
 constexpr int kHP = 48;   // horizontal-pass output plane, stored TRANSPOSED: [column 0..47][row 0..31], column pitch 48 B
 constexpr int kHCols = 48;
 
 constexpr int kMaxLumaBufs = 4;
+// narrow-target partial sums: [2 buffers][4 source warps][9 outputs][32 rows (stride 40: outputs 8 banks apart)] int32
+constexpr int kPartOut = 40, kPartWords = 2 * 4 * kDW * kPartOut;
 
 struct V5Layout {
-    int raw, luma, bfrag, hrow, x32, x98, tmat, ymat, bar, luma_bytes, total;
+    int raw, luma, bfrag, hrow, part, x32, x98, tmat, ymat, bar, luma_bytes, total;
 };
 
 __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, int n_slots, int mma_words /* in shared memory */,
-                                                  int nlb /* luma chunk buffers */, int chunk_rows = 32) {
+                                                  int nlb /* luma chunk buffers */, int chunk_rows = 32,
+                                                  bool ksplit = false /* narrow-target partial sums */) {
     V5Layout L;
     int off = 0;
     auto take = [&](int bytes, int align) {
@@ -918,6 +963,7 @@ __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, i
     L.luma = take(nlb * L.luma_bytes, 128);
     L.bfrag = take(mma_words * 8, 16);
     L.hrow = take(2 * kHCols * kHP, 16);
+    L.part = take(ksplit ? kPartWords * 4 : 0, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
@@ -1137,12 +1183,13 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
     // B fragments in shared memory: [wide-target warps 0..3 when cfg.wide_b == kBSmem][narrow-target warps 4..7 when
     // cfg.narrow_b == kBSmem], in table order
     const int b_first = (NKW == 0 && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
-    const int b_last = (BMEM && cfg.narrow_b != kBSmem) ? a.mma_boff[4] : a.mma_words;
-    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR);
+    const int b_last = NKW > kNKP ? b_first : (cfg.narrow_b != kBSmem ? a.mma_boff[4] : a.mma_words);
+    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR, NKW > kNKP);
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
     uint8_t* s_hrow = smem + L.hrow;
+    int32_t* s_part = reinterpret_cast<int32_t*>(smem + L.part);
     uint8_t* s_x32 = smem + L.x32;
     uint8_t* s_x98 = smem + L.x98;
     double* s_t = reinterpret_cast<double*>(smem + L.tmat);
@@ -1373,19 +1420,126 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
         return;
     }
 
-    // ---- narrow target: warps 4..7 own output pairs of the 9-wide target (warp 7: outputs 6, 7 and 8), also END TO END:
-    // the pair's columns go into a private 8-column scratch (plane 1 of the row plane) and come straight back as the B
-    // fragment of the 8x9 plane's vertical pass — six of the tile's eight columns are padding, three MMAs per chunk
-    // are cheap, and no tap warp waits for another before the image is finished.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ONE ? kV5NarrowRegsOne : kV5NarrowRegs));
-    const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
-    if (BMEM && cfg.narrow_b == kBGmem) bw = a.mma_b + a.mma_boff[warp] + lane;
+    // ---- narrow target (9 x 8 plane), warps 4..7.
+    if constexpr (NKW == 32) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kV5NarrowRegs32));  // above the 168 of the launch
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NKW == 16 ? kV5NarrowRegs16 : kV5NarrowRegs));
     uint8_t* scr = s_hrow + kHCols * kHP;                 // plane 1
     const int scr_col = 8 * (warp - 4);                   // this warp's private columns scr_col .. scr_col + 7
     const uint32_t* col = reinterpret_cast<const uint32_t*>(scr + (scr_col + g) * kHP);
     int32_t vc[3][4];
     uint32_t lph = 0;
     int lb = 0;
+    if constexpr (NKW > kNKP) {
+        // Horizontal pass split by K (one CTA per SM, where the registers for it exist): warp 4 + j multiplies ITS quarter of the row's k-steps (fragments in registers) into
+        // all nine outputs — every luma byte is read by one narrow warp instead of four, and no fragment is re-read per
+        // chunk (measured before: the narrow warps cost 0.09 of HBM at 512 pixels, 0.10 at 1024).  The quarter sums meet in
+        // shared memory (double-buffered: one 128-thread barrier per chunk), warp 4 + j finishes the output pair
+        // (2j, 2j + 1) (warp 7: 6, 7 and 8) — sum of four, round, clip — into its private columns and runs the
+        // vertical pass of exactly those columns, as before.
+        constexpr int NKN = NKW == 32 ? 18 : 9;
+        const int j = warp - 4;
+        const int nkq = ((dbg & 2) || (dbg & 64)) ? 0 : a.mmaq_nk[j];
+        uint2 nreg[NKN][4];
+#pragma unroll
+        for (int k = 0; k < NKN; ++k)
+#pragma unroll
+            for (int T = 0; T < 4; ++T)
+                nreg[k][T] = k < a.mmaq_nk[j] ? __ldg(a.mma_b + a.mmaq_boff[j] + (k * 4 + T) * 32 + lane) : make_uint2(0u, 0u);
+        const uint32_t aq_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mmaq_k0[j] * 32);
+        const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
+        const int n_own = j == 3 ? 3 : 2;
+        int pb = 0;
+        for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vc[d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+            int hc = 0;
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++hc, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1, pb ^= 1) {
+                mbar_wait_sleep(&l_full[lb], lph, poll_ns);
+                const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + aq_off;
+                const int row_off = CR == 32 ? 0 : (hc & 1) * 16;
+                int32_t* mine = s_part + (pb * 4 + j) * (kDW * kPartOut);
+#pragma unroll
+                for (int rb = 0; rb < NRB; ++rb) {
+                    int32_t c[4][4];
+#pragma unroll
+                    for (int T = 0; T < 4; ++T)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) c[T][i] = 0;
+#pragma unroll
+                    for (int k = 0; k < NKN; ++k) {
+                        if (k < nkq) {
+                            uint32_t a0[4];
+                            ldmatrix_x4(a0, a_addr + k * 32 + rb * 16 * pitch_bytes);
+#pragma unroll
+                            for (int T = 0; T < 4; ++T) mma_u8s8(c[T], a0, nreg[k][T]);
+                        }
+                    }
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int row = rb * 16 + hf * 8 + g;
+#pragma unroll
+                        for (int T = 0; T < 4; ++T) {
+                            const int32_t xa = __shfl_sync(0xffffffffu, c[T][2 * hf], src);
+                            const int32_t xb = __shfl_sync(0xffffffffu, c[T][2 * hf + 1], src);
+                            const int32_t v = c[T][2 * hf] + (c[T][2 * hf + 1] << 8) + ((t == 0 ? xa : xb) << 16);
+                            if (t < 2) mine[(2 * T + t) * kPartOut + row] = v;
+                        }
+                        if (t == 3) mine[8 * kPartOut + row] = c[0][2 * hf] + (c[0][2 * hf + 1] << 8) + (c[1][2 * hf] << 16);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // the four quarter sums of this chunk are written
+                {
+                    const int32_t* all = s_part + pb * 4 * (kDW * kPartOut);
+                    // CR == 32: lane = row, one output after the other; CR == 16: lanes 0..15 / 16..31 = first / second output
+                    const int row = CR == 32 ? lane : (lane & 15);
+#pragma unroll
+                    for (int pass = 0; pass < (CR == 32 ? 3 : 2); ++pass) {
+                        const int oi = CR == 32 ? pass : 2 * pass + (lane >> 4);
+                        if (oi < n_own) {
+                            const int32_t* p = all + (2 * j + oi) * kPartOut + row;
+                            const int32_t v = p[0] + p[kDW * kPartOut] + p[2 * kDW * kPartOut] + p[3 * kDW * kPartOut] + (1 << (kPrec - 1));
+                            scr[(scr_col + oi) * kHP + row_off + row] = (uint8_t)pack_sat_u8(0, v >> kPrec);
+                        }
+                    }
+                }
+                __syncwarp();  // the pair's columns are written
+                const bool vstep = CR == 32 || (hc & 1) || r0 + CR >= a.h;
+                const int ci = CR == 32 ? hc : hc >> 1;
+                if (vstep && !(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
+                    const uint32_t b0 = col[t], b1 = col[4 + t];
+                    const uint4* af = a.vmma + ((size_t)(ci * 3 + 2) * 3) * 32 + lane;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) mma_s8u8(vc[d], __ldg(af + d * 32), b0, b1);
+                }
+                __syncwarp();  // every lane has read the columns before the next chunk overwrites them
+            }
+            {   // 8x9 plane: rows g; tile columns 0, 1 (warp 7: 0, 1, 2) are outputs 2 (warp - 4) + 0, 1 (, 2)
+                const int32_t v0 = vc[0][0] + (vc[1][0] << 8) + (vc[2][0] << 16);
+                const int32_t v1 = vc[0][1] + (vc[1][1] << 8) + (vc[2][1] << 16);
+                const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+                const int x = 2 * (warp - 4) + 2 * t;
+                if (t == 0) {
+                    s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+                    s_x98[g * kDW + x + 1] = (uint8_t)(pk >> 8);
+                } else if (t == 1 && warp == 7) {
+                    s_x98[g * kDW + x] = (uint8_t)(pk & 0xFFu);
+                }
+            }
+            compute_sync<NW>();
+            dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
+        }
+        return;
+    }
+    // NKW == 8 (two CTAs per SM: 72 registers) and NKW == 0 (rows beyond ~2200 pixels): warps 4..7 own output pairs of the 9-wide target (warp 7: outputs 6, 7 and 8) END
+    // TO END, fragments behind a pointer: the pair's columns go into a private 8-column scratch (plane 1 of the row plane)
+    // and come straight back as the B fragment of the 8x9 plane's vertical pass — six of the tile's eight columns are
+    // padding, three MMAs per chunk are cheap, and no tap warp waits for another before the image is finished.
+    const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
+    if (cfg.narrow_b == kBGmem) bw = a.mma_b + a.mma_boff[warp] + lane;
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -1439,7 +1593,9 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     cfg.dbg = 0;
     const int wide_words = a.mma_boff[4], narrow_words = a.mma_words - a.mma_boff[4];
     // wide-target bands of <= 8 k-steps stay in registers at two CTAs per SM, of <= 32 at one CTA per SM
-    const int nkw_reg = nk_wide <= kNKP ? kNKP : nk_wide <= 16 ? 16 : nk_wide <= 32 ? 32 : 0;
+    // (and the narrow warps a quarter of the row each: <= 4 / 9 / 18 k-steps)
+    const int kq = a.mmaq_kq;
+    const int nkw_reg = nk_wide <= kNKP ? kNKP : nk_wide <= 16 && kq <= 9 ? 16 : nk_wide <= 32 && kq <= 18 ? 32 : 0;
     auto fits = [&](int budget, int wide, int narrow, int bufs, int sub, int shift, int cr) -> bool {
         if (sub < 1 || sub > cr || (cr % sub) || sub * row_bytes > (1 << 20) || shift < 1 || shift > 3 || bufs < 1 ||
             bufs > kMaxLumaBufs)
@@ -1452,8 +1608,9 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
         // unaligned rows: room for the aligned superset (<= 15 B in front, <= 15 B behind) and for the luma loads that
         // run a few words past the last pixel
         const int slot = cfg.aligned ? (int)(sub * row_bytes) : (int)((sub * row_bytes + 64 + 127) / 128 * 128);
+        if (nkw > kNKP) narrow = kBReg;  // one CTA per SM: the K-split narrow warps hold their fragments too, nothing in shared memory
         const int words = (wide == kBSmem ? wide_words : 0) + (narrow == kBSmem ? narrow_words : 0);
-        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs, cr);
+        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs, cr, nkw > kNKP);
         if (L.total > budget) return false;
         cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot, cfg.cr = cr;
         cfg.wide_b = wide, cfg.narrow_b = narrow, cfg.smem_words = words, cfg.L = L, cfg.nkw = nkw;
@@ -1485,10 +1642,11 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     // narrow-target fragments moved out to L2 where that is what it takes.
     const int wide_chip = nkw_reg ? kBReg : kBSmem, wide_l2 = nkw_reg ? kBReg : kBGmem;
     const Place places[] = {{227 * 1024, wide_chip, kBSmem}, {227 * 1024, wide_l2, kBSmem}, {227 * 1024, wide_l2, kBGmem}};
-    // register-resident bands: 32-row buffers while two of them fit beside >= 12 KB sub-chunks (1024 pixels: 0.855 of HBM
-    // against 0.787 with 16-row buffers), else 16-row buffers (2048 pixels: 0.862)
+    // register-resident bands: 32-row buffers while two of them fit beside sub-chunks of >= 8 rows (1024 pixels: 0.85 of
+    // HBM against 0.82-0.84 with 16-row buffers), else 16-row buffers (2048 pixels: 0.887 with 8-row sub-chunks; 4-row
+    // sub-chunks, whatever the buffers, stay at 0.63)
     if (nkw_reg > kNKP)
-        for (int sub : {16, 8, 4, 2, 1})
+        for (int sub : {16, 8})
             if (sub * row_bytes >= min_slot && fits(227 * 1024, kBReg, kBSmem, 2, sub, 1, 32)) return true;
     if (nk_wide > kNKP)
         for (int sub : {16, 8, 4, 2, 1})
@@ -1634,6 +1792,8 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     a.mma_b = ht->d_mma_b;
     a.mma_words = ht->mma_words;
     for (int i = 0; i < 8; ++i) a.mma_k0[i] = ht->mma_k0[i], a.mma_nk[i] = ht->mma_nk[i], a.mma_boff[i] = ht->mma_boff[i];
+    for (int i = 0; i < 4; ++i) a.mmaq_k0[i] = ht->mmaq_k0[i], a.mmaq_nk[i] = ht->mmaq_nk[i], a.mmaq_boff[i] = ht->mmaq_boff[i];
+    a.mmaq_kq = ht->mmaq_kq;
     a.vmma = vt->vmma_ok ? vt->d_vmma : nullptr;
     for (int i = 0; i < 3; ++i) a.v_lo[i] = vt->v_lo[i], a.v_hi[i] = vt->v_hi[i];
     a.meta = ht->d_meta;

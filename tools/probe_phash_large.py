@@ -1,6 +1,6 @@
 """K1 on larger photographs: time the streaming kernel under pinned staging configurations (KE_OPT_PHASH_CFG).
 
-    python tools/probe_phash_large.py            # 1024x1024 and 2048x1536 RGB, automatic + a sweep
+    python tools/probe_phash_large.py [--auto]   # 512 ... 4000-pixel rows, the automatic configuration (+ a sweep)
 """
 import json
 import sys
@@ -41,7 +41,7 @@ for (h, w, c) in ((512, 512, 3), (1024, 1024, 3), (1536, 2048, 3), (3000, 4000, 
         ops.synth_images_device(lo, k, h, w, c, n_set=n, out=bank[lo:lo + k])
     res = {}
     cfgs = [("auto", 0)]
-    for cr16 in (0, 1):
+    for cr16 in (() if "--auto" in sys.argv else (0, 1)):
         for place in (0, 1, 2, 3):
             for bufs in (4, 3, 2, 1):
                 for sub in (16, 8, 4, 2, 1):
