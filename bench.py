@@ -340,7 +340,7 @@ def run_cuda(args) -> dict:
     k1_ms = stage["phash"] / args.steps  # live, inside the timed region: one launch per step
     k1_bytes = n * (IMG_BYTES + 16)
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
-    roof_k1 = {"kernel": "ke_phash_v5_kernel<3,0,1> (512x512x3; TMA ring + dp2a luma + mma.sync u8xs8 resample)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roof_k1 = {"kernel": "ke_phash_v5_kernel<3,8,1,32> (512x512x3; TMA ring + dp2a luma + mma.sync u8xs8 resample, fragments in registers)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
                "frac": k1_gbs / hbm_peak,
                # dram read+write per launch: 787 184 B/image measured by `ncu --set full` on an 8192-image launch of
                # the same kernel (profiles/r2_ncu_k1_512_summary.txt: 6 448 615 352 B), scaled to this launch's image count
@@ -350,7 +350,7 @@ def run_cuda(args) -> dict:
                "images_per_s": n / (k1_ms * 1e-3)}
 
     # K1 on larger photographs (the reference feeds images up to 4096 px, src/utils/image_io.py:60-138): the same
-    # kernel with its resample fragments in shared memory (1024 px) / L2 (2048 px); banks of 6 GB >> L2
+    # kernel, one CTA per SM with every resample fragment in registers (ke_phash_v5_kernel<3,16|32,1,*>); banks of 6 GB >> L2
     roof_k1_large = {}
     for (hh, ww) in ((1024, 1024), (1536, 2048)):
         # ~6 GB banks, a whole number of images per persistent CTA (296 = 2 x 148 covers one and two CTAs per SM)
@@ -362,7 +362,8 @@ def run_cuda(args) -> dict:
         ms_l = timed(lambda: ops.phash_dhash_batch(big))
         gbs_l = cnt_l * (hh * ww * C + 16) / (ms_l * 1e-3) / 1e9
         roof_k1_large[f"{ww}x{hh}x{C}"] = {"images": cnt_l, "ms": ms_l, "images_per_s": cnt_l / (ms_l * 1e-3), "achieved": gbs_l,
-                                           "unit": "GB/s", "frac": gbs_l / hbm_peak}
+                                           "unit": "GB/s", "frac": gbs_l / hbm_peak,
+                                           "kernel": f"ke_phash_v5_kernel<3,{16 if ww <= 1100 else 32},1,{32 if ww <= 1100 else 16}>"}
         del big
 
     # K2 at config C3: 1 M synthetic hashes, T=8, tiles split over the ranks (strong scaling)

@@ -1595,7 +1595,8 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     // wide-target bands of <= 8 k-steps stay in registers at two CTAs per SM, of <= 32 at one CTA per SM
     // (and the narrow warps a quarter of the row each: <= 4 / 9 / 18 k-steps)
     const int kq = a.mmaq_kq;
-    const int nkw_reg = nk_wide <= kNKP ? kNKP : nk_wide <= 16 && kq <= 9 ? 16 : nk_wide <= 32 && kq <= 18 ? 32 : 0;
+    const bool force_one = forced && ((forced >> 21) & 1);  // tuning: the one-CTA kernel on short rows too
+    const int nkw_reg = nk_wide <= kNKP && !force_one ? kNKP : nk_wide <= 16 && kq <= 9 ? 16 : nk_wide <= 32 && kq <= 18 ? 32 : 0;
     auto fits = [&](int budget, int wide, int narrow, int bufs, int sub, int shift, int cr) -> bool {
         if (sub < 1 || sub > cr || (cr % sub) || sub * row_bytes > (1 << 20) || shift < 1 || shift > 3 || bufs < 1 ||
             bufs > kMaxLumaBufs)
