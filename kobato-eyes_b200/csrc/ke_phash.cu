@@ -442,7 +442,6 @@ struct PhashArgs {
     const uint2* mma_b;
     int mma_words;
     int mma_k0[8], mma_nk[8], mma_boff[8];
-    int mmaq_k0[4], mmaq_nk[4], mmaq_boff[4], mmaq_kq;
     const uint4* vmma;
     int v_lo[3], v_hi[3];
     const int* kk32;
@@ -456,6 +455,8 @@ struct PhashArgs {
     float* min_margin;
     uint8_t* plane32;
     uint8_t* plane98;
+    // K-split narrow-target tables (one-CTA kernels); kept behind the fields the two-CTA kernel reads
+    int mmaq_k0[4], mmaq_nk[4], mmaq_boff[4], mmaq_kq;
 };
 
 struct SmemLayout {
@@ -963,12 +964,14 @@ __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, i
     L.luma = take(nlb * L.luma_bytes, 128);
     L.bfrag = take(mma_words * 8, 16);
     L.hrow = take(2 * kHCols * kHP, 16);
-    L.part = take(ksplit ? kPartWords * 4 : 0, 16);
     L.x32 = take(1024, 16);
     L.x98 = take(80, 16);
     L.tmat = take(8 * 32 * 8, 16);
     L.ymat = take(64 * 8, 16);
     L.bar = take((2 * kMaxSlots + 2 * kMaxLumaBufs) * 8 + kMaxSlots * 4, 8);
+    // last: with this region in the middle of the layout the two-CTA kernel lost 2.5 % (9.25 -> 9.46 ms per 70 000 images,
+    // A/B on one box) although it never touches it
+    L.part = take(ksplit ? kPartWords * 4 : 0, 16);
     L.total = off;
     return L;
 }
@@ -1171,7 +1174,6 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
                    const int dbg, const V5Config cfg) {
     constexpr int NW = kV5Tap, NRB = CR / 16;
     constexpr bool BMEM = NKW != kNKP;  // narrow-target (and, NKW == 0, wide-target) fragments behind a pointer
-    constexpr bool ONE = NKW > kNKP;    // one CTA per SM
     static_assert(NKW == 0 || NKW == kNKP || NKW == 16 || NKW == 32, "register-resident bands of 8, 16 or 32 k-steps");
     static_assert(CR == 32 || (CR == 16 && BMEM), "16-row buffers come with the pointer-fed narrow tap loops only");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1183,7 +1185,9 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
     // B fragments in shared memory: [wide-target warps 0..3 when cfg.wide_b == kBSmem][narrow-target warps 4..7 when
     // cfg.narrow_b == kBSmem], in table order
     const int b_first = (NKW == 0 && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
-    const int b_last = NKW > kNKP ? b_first : (cfg.narrow_b != kBSmem ? a.mma_boff[4] : a.mma_words);
+    // (NKW == 8 must not read cfg here: a value selected through the parameter struct leaves the uniform datapath and
+    // every shared-memory address derived from the layout with it — measured 9.20 -> 9.44 ms per 70 000 images)
+    const int b_last = NKW > kNKP ? b_first : NKW == kNKP ? a.mma_words : (cfg.narrow_b != kBSmem ? a.mma_boff[4] : a.mma_words);
     const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR, NKW > kNKP);
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
@@ -1343,7 +1347,11 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
     }
 
     // ===== tap warps =====
-    const int nk = ((dbg & 2) || ((dbg & 32) && warp < 4) || ((dbg & 64) && warp >= 4)) ? 0 : a.mma_nk[warp];  // probes
+#ifdef KE_TUNING_PROBES
+    const int nk = ((dbg & 2) || ((dbg & 32) && warp < 4) || ((dbg & 64) && warp >= 4)) ? 0 : a.mma_nk[warp];
+#else
+    const int nk = (dbg & 2) ? 0 : a.mma_nk[warp];
+#endif
     const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mma_k0[warp] * 32);
     const uint32_t poll_ns = (uint32_t)dbg >> 8;
     const int g = lane >> 2, t = lane & 3;
@@ -1539,7 +1547,7 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
     // and come straight back as the B fragment of the 8x9 plane's vertical pass — six of the tile's eight columns are
     // padding, three MMAs per chunk are cheap, and no tap warp waits for another before the image is finished.
     const uint2* bw = s_b + (a.mma_boff[warp] - b_first) + lane;
-    if (cfg.narrow_b == kBGmem) bw = a.mma_b + a.mma_boff[warp] + lane;
+    if (NKW == 0 && cfg.narrow_b == kBGmem) bw = a.mma_b + a.mma_boff[warp] + lane;  // (NKW == 8: always shared memory, LDS)
     for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
 #pragma unroll
         for (int d = 0; d < 3; ++d)

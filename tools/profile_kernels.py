@@ -48,7 +48,7 @@ def main():
         gbs = args.images * 786448 / (min(t) * 1e-3) / 1e9
         print(f"phash: {args.images} images 512x512x3: ms={t} -> {args.images / (min(t) * 1e-3):.3e} img/s, {gbs:.1f} GB/s")
         del bank
-    if "phash_large" in only:  # the streaming kernel with its fragments in shared memory (1024 px) / L2 (2048 px)
+    if "phash_large" in only:  # the streaming kernel at one CTA per SM, resample fragments in registers (1024 / 2048 px)
         for (h, w) in ((1024, 1024), (1536, 2048)):
             n = max(64, int(3e9) // (h * w * 3))
             bank = ops.synth_images_device(0, n, h, w, 3, n_set=n)
