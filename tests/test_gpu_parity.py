@@ -366,8 +366,8 @@ def test_ssim_both_kernels_agree_with_the_oracle():
 def test_phash_streaming_and_generic_kernels_agree():
     """K1 has two kernels (v5: the streaming tensor-pipe kernel, every batch of contiguous rows; generic: strided rows
     and the reference inside the library): identical planes, hashes and margins on every geometry — widths that are not a
-    multiple of 16 or 4, rows / images off the 16-byte grid, bands whose fragments live in registers (<= ~512 px), in
-    shared memory (~1024 px) and in L2 (2048, 4096 px), upscales, one-row and one-column-block images."""
+    multiple of 16 or 4, rows / images off the 16-byte grid, bands whose fragments live in registers (two CTAs per SM
+    up to ~512 px, one up to ~2200 px) and behind pointers (3000, 4096 px), upscales, one-row and one-column-block images."""
     torch = _torch()
     from kobato_b200 import _native as nat
 
@@ -402,6 +402,37 @@ def test_phash_streaming_and_generic_kernels_agree():
                 off = ops.phash_dhash_batch(view, want_planes=True)
                 assert torch.equal(off[0], gen[0]) and torch.equal(off[1], gen[1]), (h, w, c, shift)
                 assert torch.equal(off[2][0], gen[3][0]) and torch.equal(off[2][1], gen[3][1]), (h, w, c, shift)
+
+
+def test_phash_widths_around_the_kernel_class_boundaries():
+    """K1 picks its kernel by the width: resample bands of <= 8 k-steps (two CTAs per SM), <= 16 and <= 32 (one CTA per SM,
+    wide-target fragments in registers, narrow-target warps split by K with <= 9 / 18 k-steps each), beyond (pointer-fed).
+    Widths on both sides of every boundary — aligned and not, heights that end in the middle of a ring buffer — must give
+    the generic kernel's (w <= 2048) or the CPU oracle's planes and hashes."""
+    torch = _torch()
+    from kobato_b200 import _native as nat
+
+    ctx = nat.context(torch.cuda.current_device())
+    widths = (513, 520, 528, 544, 576, 600, 1039, 1040, 1056, 1088, 1104, 1119, 1120, 1136, 1152, 1153, 1168, 1200,
+              2047, 2049, 2175, 2176, 2208, 2239, 2240, 2272, 2303, 2304, 2305, 2336, 2400)
+    for i, w in enumerate(widths):
+        h, c, n = (41, 70, 97, 130)[i % 4], (3, 1, 4)[i % 3] if w <= 1200 else 3, 3
+        imgs = ops.synth_images_device(0, n, h, w, c, n_set=n, seed=100 + i)
+        got = ops.phash_dhash_batch(imgs, want_planes=True)
+        if w > 2048:
+            host = imgs.cpu().numpy()
+            for k in range(n):
+                wp, wd, _, p32, p98 = oracle.signature(host[k])
+                assert np.array_equal(got[2][0][k].cpu().numpy(), p32) and np.array_equal(got[2][1][k].cpu().numpy(), p98), (h, w, c)
+                assert int(got[0][k].item()) & U64 == wp and int(got[1][k].item()) & U64 == wd, (h, w, c)
+            continue
+        ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 1)
+        try:
+            gen = ops.phash_dhash_batch(imgs, want_planes=True)
+        finally:
+            ctx.set_option(nat.KE_OPT_PHASH_GENERIC, 0)
+        assert torch.equal(got[2][0], gen[2][0]) and torch.equal(got[2][1], gen[2][1]), (h, w, c)
+        assert torch.equal(got[0], gen[0]) and torch.equal(got[1], gen[1]), (h, w, c)
 
 
 def test_phash_every_staging_configuration_gives_the_same_hashes():
