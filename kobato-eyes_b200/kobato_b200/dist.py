@@ -150,6 +150,36 @@ def plan_cross_pairs(ci: np.ndarray, cj: np.ndarray, offsets: np.ndarray, rank: 
             "send": send, "recv": recv, "own_i": own_i, "own_j": own_j, "scorer": scorer}
 
 
+def plan_cross_pairs_t(ci, cj, offsets, rank: int, size: int) -> dict:
+    """``plan_cross_pairs`` on torch tensors of any device (the candidate list never leaves the GPU in ``pipeline.scan``;
+    the numpy version costs 2.5-3.5 ms of host time on the 8-GPU step's 28 778 candidates).  ``ci``/``cj``: int64 tensors,
+    ``offsets``: int64 tensor ``[size + 1]`` on the same device.  Returns tensors on that device — ``local`` / ``cross``
+    (positions this rank scores), ``send_rows`` (my rows that travel, grouped by destination, sorted inside a group),
+    ``recv_rows`` (the rows I receive: sorted, hence grouped by source), ``own_i`` — and the two count lists the
+    all_to_all needs on the host (``send_counts``, ``recv_counts``: ONE device->host copy)."""
+    import torch
+
+    total = int(offsets[-1])
+    own_i = torch.searchsorted(offsets, ci, right=True) - 1
+    own_j = torch.searchsorted(offsets, cj, right=True) - 1
+    is_cross = own_i != own_j
+    scorer = torch.where(is_cross & (((ci + cj) & 1) == 1), own_j, own_i)
+    i_scores = scorer == own_i
+    trav = torch.where(i_scores, cj, ci)              # the image NOT owned by the scorer (meaningless for local pairs)
+    trav_owner = torch.where(i_scores, own_j, own_i)
+    mine_cross = is_cross & (scorer == rank)
+    out_mask = is_cross & (trav_owner == rank)
+    key = torch.unique(scorer[out_mask] * (total + 1) + trav[out_mask])   # sorted distinct (destination, row)
+    dest = torch.div(key, total + 1, rounding_mode="floor")
+    send_rows = key - dest * (total + 1)
+    recv_rows = torch.unique(trav[mine_cross])
+    counts = torch.stack([torch.bincount(dest, minlength=size)[:size],
+                          torch.bincount(torch.searchsorted(offsets, recv_rows, right=True) - 1, minlength=size)[:size]]).cpu()
+    return {"local": torch.nonzero(~is_cross & (own_i == rank)).flatten(), "cross": torch.nonzero(mine_cross).flatten(),
+            "send_rows": send_rows, "recv_rows": recv_rows, "own_i": own_i,
+            "send_counts": counts[0].tolist(), "recv_counts": counts[1].tolist()}
+
+
 def exchange_rows(rows, send_counts, recv_counts, async_op: bool = False, out=None):
     """ONE ``all_to_all_single``: ``rows`` = [sum(send_counts), k] with the rows for rank 0 first, then rank 1, ...;
     returns [sum(recv_counts), k] ordered by source rank (received straight into ``out`` when given) — or

@@ -204,12 +204,13 @@ def hamming_join_device(hashes, threshold: int, *, require_band: bool = False, b
 # ----------------------------------------------------------------------------- K3
 
 
-def ssim_batch(bank, ia, ib, *, gaussian: bool = False):
+def ssim_batch(bank, ia, ib, *, gaussian: bool = False, check: bool = True):
     """SSIM of pairs (bank[ia[p]], bank[ib[p]]) — reference src/dup/refine.py:52 semantics.
 
     bank: CUDA uint8 tensor ``[m,h,w]`` ('L' planes) or ``[m,h,w,c]`` (RGB/RGBA, Pillow luma applied
     on the fly); ia/ib: index sequences.  Returns a float64 CUDA tensor ``[n_pairs]``.
-    ``gaussian=True`` is skimage's ``gaussian_weights=True`` window (not the reference's path)."""
+    ``gaussian=True`` is skimage's ``gaussian_weights=True`` window (not the reference's path).  ``check=False`` skips the
+    range check of DEVICE index tensors (two reductions and a synchronisation; for indices the caller derived itself)."""
     torch = _torch()
     lib = nat.load()
     if not (_is_tensor(bank) and bank.is_cuda and bank.dtype == torch.uint8):
@@ -219,7 +220,7 @@ def ssim_batch(bank, ia, ib, *, gaussian: bool = False):
     if x.stride(3) != 1 or x.stride(2) != c:
         x = x.contiguous()
     dev = x.device.index
-    ia_t, ib_t, n = _pair_index(ia, ib, m, x.device)
+    ia_t, ib_t, n = _pair_index(ia, ib, m, x.device, check)
     out = torch.empty(n, dtype=torch.float64, device=x.device)
     if n:
         ctx = nat.context(dev)
@@ -334,7 +335,7 @@ def bits_to_ints(bits) -> list[int]:
     return [int.from_bytes(row.tobytes(), "little") for row in raw]
 
 
-def _pair_index(ia, ib, m: int, device):
+def _pair_index(ia, ib, m: int, device, check: bool = True):
     """Pair index sequences -> int64 device tensors, range-checked.  Host sequences (lists, numpy arrays) are checked on
     the host before they are uploaded; only device tensors cost a device reduction and a synchronisation."""
     torch = _torch()
@@ -352,7 +353,7 @@ def _pair_index(ia, ib, m: int, device):
     if ia_t.shape != ib_t.shape or ia_t.dim() != 1:
         raise ValueError("ia and ib must be 1-D and of equal length")
     n = ia_t.numel()
-    if n and (int(torch.max(torch.maximum(ia_t, ib_t))) >= m or int(torch.min(torch.minimum(ia_t, ib_t))) < 0):
+    if check and n and (int(torch.max(torch.maximum(ia_t, ib_t))) >= m or int(torch.min(torch.minimum(ia_t, ib_t))) < 0):
         raise ValueError("pair index out of range")
     return ia_t, ib_t, n
 
@@ -498,7 +499,7 @@ def orb_match_pairs(desc_a: list, desc_b: list, *, want_matches: bool = False):
     return counts
 
 
-def luma_planes(bank, idx, out=None):
+def luma_planes(bank, idx, out=None, check: bool = True):
     """``convert("L")`` planes of ``bank[idx]`` (Pillow rgb2l; reference src/dup/refine.py:48-49) -> uint8 CUDA tensor
     ``[len(idx), h, w]`` (written into ``out`` — contiguous, ``len(idx) * h * w`` bytes — when given)."""
     torch = _torch()
@@ -507,7 +508,7 @@ def luma_planes(bank, idx, out=None):
     m, h, w, c = x.shape
     idx_t = torch.as_tensor(idx, dtype=torch.int64).to(x.device).contiguous()
     n = idx_t.numel()
-    if n and (int(idx_t.max()) >= m or int(idx_t.min()) < 0):
+    if check and n and (int(idx_t.max()) >= m or int(idx_t.min()) < 0):
         raise ValueError("image index out of range")
     if out is None:
         out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)

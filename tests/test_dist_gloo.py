@@ -135,6 +135,16 @@ def test_cross_pair_plan_is_consistent_across_ranks():
             own = np.searchsorted(offsets, ci[p["local"]], side="right") - 1
             assert np.all(own == r)
         assert np.all(scored == 1)
+        # the tensor version (what pipeline.scan runs, on the GPU) is the same plan
+        import torch
+
+        for r, p in enumerate(plans):
+            t = kdist.plan_cross_pairs_t(torch.from_numpy(ci), torch.from_numpy(cj), torch.from_numpy(offsets.astype(np.int64)), r, size)
+            assert np.array_equal(t["local"].numpy(), p["local"]) and np.array_equal(t["cross"].numpy(), p["cross"])
+            assert t["send_counts"] == [len(x) for x in p["send"]] and t["recv_counts"] == [len(x) for x in p["recv"]]
+            assert np.array_equal(t["send_rows"].numpy(), np.concatenate(p["send"]).astype(np.int64))
+            assert np.array_equal(t["recv_rows"].numpy(), np.concatenate(p["recv"]).astype(np.int64))
+            assert np.array_equal(t["own_i"].numpy(), p["own_i"])
         if size == 8:  # balance: no rank scores more than twice its fair share of the cross pairs
             cross = [len(p["cross"]) for p in plans]
             assert max(cross) <= 2 * sum(cross) / size

@@ -366,3 +366,20 @@ def test_pipeline_scan_world_size_2_matches_the_oracle_with_cross_shard_duplicat
     res = _spawn_multigpu(2, ["--images", "260", "--uneven"])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "multigpu check ok" in res.stdout
+
+
+def test_pipeline_scan_clusters_on_the_device_equal_the_host_union_find():
+    """pipeline.scan keeps the candidate list on the GPU; long lists are unioned there (device union-find + sort),
+    short ones by the library's host union-find: the two must give the same components in the same order."""
+    import torch
+
+    from kobato_b200 import pipeline
+
+    n = 600
+    bank = ops.synth_images_device(0, n, 64, 64, 3, n_set=n, planted=0.5)
+    a = pipeline.scan(bank, cluster_on_device=False)
+    b = pipeline.scan(bank, cluster_on_device=True)
+    assert len(a.cand_i) > 50 and a.counts["accepted"] > 10
+    assert np.array_equal(a.cand_i, b.cand_i) and np.array_equal(a.cand_j, b.cand_j) and np.array_equal(a.ssim, b.ssim)
+    assert a.clusters.as_list() == b.clusters.as_list() and len(a.clusters) > 3
+    assert np.array_equal(a.clusters.members, b.clusters.members) and np.array_equal(a.clusters.offsets, b.clusters.offsets)
