@@ -59,8 +59,10 @@ ke_ctx* ke_ctx_child(ke_ctx* ctx, int k); /* k in [0, device_count): child 0 is 
 /* KE_OPT_JOIN_MODE: 0 auto (hybrid for large tables with threshold <= 15), 1 POPC kernel only,
  * 2 hybrid (POPC role + bit-sliced LOP3 role in one kernel), 3 bit-sliced kernel only. */
 #define KE_OPT_JOIN_MODE 2
-/* KE_OPT_PHASH_CFG: pin the streaming K1 kernel's staging (0 = automatic): sub_rows | slot_shift << 8 | luma_buffers << 12
- * | placement << 16 (0 resample fragments on chip, 1 wide-target fragments in L2, 2 both in L2) | 16-row ring buffers << 20. */
+/* KE_OPT_PHASH_CFG: pin the streaming K1 kernel's staging (0 = automatic; tests and tuning): sub_rows | slot_shift << 8 |
+ * luma_buffers << 12 | placement << 16 (0 resample fragments in registers where the band allows, else shared memory;
+ * 1 wide-target fragments in L2; 2 both in L2; 3 both in shared memory) | 16-row ring buffers << 20 | the one-CTA-per-SM
+ * kernel also on short rows << 21.  A configuration that does not fit the geometry makes the call return KE_E_UNSUPPORTED. */
 #define KE_OPT_PHASH_CFG 5
 /* KE_OPT_SSIM_V1=1: K3 on the one-column-per-thread kernel (the one that takes unaligned banks). */
 #define KE_OPT_SSIM_V1 3
