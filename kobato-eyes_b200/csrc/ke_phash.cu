@@ -66,6 +66,8 @@ struct HTable {           // horizontal pass, one per input width
     int mma_k0[8] = {}, mma_nk[8] = {}, mma_boff[8] = {};
     // narrow target split by k range: warp 4 + j owns k-steps [mmaq_k0[j], + mmaq_nk[j]) of ALL nine outputs (four tiles)
     int mmaq_k0[4] = {}, mmaq_nk[4] = {}, mmaq_boff[4] = {}, mmaq_kq = 0;
+    // narrow target in two output groups x two halves of the group's band (the two-CTA kernel): warp 4 + 2 grp + half
+    int mmah_k0[4] = {}, mmah_nk[4] = {}, mmah_boff[4] = {}, mmah_end = 0;
 };
 struct VTable {           // vertical pass, one per input height
     int* d_kk32 = nullptr;
@@ -182,6 +184,7 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
     std::vector<uint2> mma_b;
     int mma_k0[8], mma_nk[8], mma_boff[8];
     int mmaq_k0[4] = {}, mmaq_nk[4] = {}, mmaq_boff[4] = {}, mmaq_kq = 0;
+    int mmah_k0[4] = {}, mmah_nk[4] = {}, mmah_boff[4] = {}, mmah_end = 0;
     int mma_words_ptr = 0;  // words of the per-output-band tables above (what the pointer-fed kernel may copy to shared memory)
     bool mma_ok = true;  // any width: taps are zero outside an output's support, so the padding of the last k-step adds nothing
     if (mma_ok) {
@@ -279,6 +282,40 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
                         mma_b.push_back(make_uint2(wd[0], wd[1]));
                     }
             }
+            // Two-CTA kernel (72 registers in the narrow warps: no room for the K-split): outputs in two groups,
+            // (0..3) and (4..8), each group's band cut in two halves -> warp 4 + 2 grp + half multiplies half of the band
+            // into the group's two tiles {a.d0, a.d1, b.d0, b.d1, a.d2, b.d2, e0, e1}, (a, b) = (g0 + 2 tile, + 1); the
+            // ninth output rides in the spare columns of group 1: e = (8.d0, 8.d1) in tile 0, (8.d2, -) in tile 1.  Each
+            // luma byte is read by at most two narrow warps instead of four; the upper half hands its sums to the lower
+            // one through shared memory.
+            for (int jw = 0; jw < 4; ++jw) {
+                const int grp = jw >> 1, half = jw & 1, g0 = kOutW + 4 * grp;
+                int k0g, nkg;
+                range(g0, grp ? kOutW + 8 : g0 + 3, k0g, nkg);
+                const int n_lo = (nkg + 1) / 2;
+                mmah_k0[jw] = half ? k0g + n_lo : k0g;
+                mmah_nk[jw] = half ? nkg - n_lo : n_lo;
+                mmah_boff[jw] = (int)mma_b.size();
+                for (int k = 0; k < mmah_nk[jw]; ++k)
+                    for (int T = 0; T < 2; ++T)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int n = lane >> 2, t4 = lane & 3;
+                            static const int sel_out[6] = {0, 0, 1, 1, 0, 1}, sel_d[6] = {0, 1, 0, 1, 2, 2};
+                            int out = -1, dg = 0;
+                            if (n < 6) out = g0 + 2 * T + sel_out[n], dg = sel_d[n];
+                            else if (grp == 1 && T == 0) out = kOutW + 8, dg = n - 6;
+                            else if (grp == 1 && T == 1 && n == 6) out = kOutW + 8, dg = 2;
+                            uint32_t wd[2] = {0, 0};
+                            for (int hf = 0; hf < 2; ++hf)
+                                for (int i = 0; i < 4; ++i) {
+                                    const int x = (mmah_k0[jw] + k) * 32 + hf * 16 + 4 * t4 + i;
+                                    const int dv = out < 0 ? 0 : digit(tap(out, x), dg);
+                                    wd[hf] |= ((uint32_t)dv & 0xFFu) << (8 * i);
+                                }
+                            mma_b.push_back(make_uint2(wd[0], wd[1]));
+                        }
+            }
+            mmah_end = (int)mma_b.size();
         }
     }
     HTable t;
@@ -294,6 +331,8 @@ int get_htable(ke_ctx* ctx, int w, const HTable** out) {
         for (int i = 0; i < 8; ++i) t.mma_k0[i] = mma_k0[i], t.mma_nk[i] = mma_nk[i], t.mma_boff[i] = mma_boff[i];
         for (int i = 0; i < 4; ++i) t.mmaq_k0[i] = mmaq_k0[i], t.mmaq_nk[i] = mmaq_nk[i], t.mmaq_boff[i] = mmaq_boff[i];
         t.mmaq_kq = mmaq_kq;
+        for (int i = 0; i < 4; ++i) t.mmah_k0[i] = mmah_k0[i], t.mmah_nk[i] = mmah_nk[i], t.mmah_boff[i] = mmah_boff[i];
+        t.mmah_end = mmah_end;
     }
     auto ins = ctx->tables->h.emplace(w, t);
     *out = &ins.first->second;
@@ -457,6 +496,7 @@ struct PhashArgs {
     uint8_t* plane98;
     // K-split narrow-target tables (one-CTA kernels); kept behind the fields the two-CTA kernel reads
     int mmaq_k0[4], mmaq_nk[4], mmaq_boff[4], mmaq_kq;
+    int mmah_k0[4], mmah_nk[4], mmah_boff[4], mmah_end;
 };
 
 struct SmemLayout {
@@ -943,6 +983,10 @@ constexpr int kHCols = 48;
 constexpr int kMaxLumaBufs = 4;
 // narrow-target partial sums: [2 buffers][4 source warps][9 outputs][32 rows (stride 40: outputs 8 banks apart)] int32
 constexpr int kPartOut = 40, kPartWords = 2 * 4 * kDW * kPartOut;
+// two-CTA kernel: the upper half-band warp of a group hands 12 accumulator slots per lane to the lower one:
+// [2 groups][2 buffers][12 slots][32 lanes] int32
+constexpr int kHalfSlots = 12, kHalfWords = 2 * 2 * kHalfSlots * 32;
+__host__ __device__ constexpr int v5_part_bytes(int nkw) { return nkw > 8 ? kPartWords * 4 : nkw == 8 ? kHalfWords * 4 : 0; }
 
 struct V5Layout {
     int raw, luma, bfrag, hrow, part, x32, x98, tmat, ymat, bar, luma_bytes, total;
@@ -950,7 +994,7 @@ struct V5Layout {
 
 __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, int n_slots, int mma_words /* in shared memory */,
                                                   int nlb /* luma chunk buffers */, int chunk_rows = 32,
-                                                  bool ksplit = false /* narrow-target partial sums */) {
+                                                  int part_bytes = 0 /* narrow-target partial sums */) {
     V5Layout L;
     int off = 0;
     auto take = [&](int bytes, int align) {
@@ -971,7 +1015,7 @@ __host__ __device__ inline V5Layout v5_layout(int slot_bytes, int pitch_bytes, i
     L.bar = take((2 * kMaxSlots + 2 * kMaxLumaBufs) * 8 + kMaxSlots * 4, 8);
     // last: with this region in the middle of the layout the two-CTA kernel lost 2.5 % (9.25 -> 9.46 ms per 70 000 images,
     // A/B on one box) although it never touches it
-    L.part = take(ksplit ? kPartWords * 4 : 0, 16);
+    L.part = take(part_bytes, 16);
     L.total = off;
     return L;
 }
@@ -1184,11 +1228,11 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
     const uint32_t slot_mask = (uint32_t)n_slots - 1u;
     // B fragments in shared memory: [wide-target warps 0..3 when cfg.wide_b == kBSmem][narrow-target warps 4..7 when
     // cfg.narrow_b == kBSmem], in table order
-    const int b_first = (NKW == 0 && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
+    const int b_first = NKW == kNKP ? a.mmah_boff[0] : (NKW == 0 && cfg.wide_b == kBSmem) ? 0 : a.mma_boff[4];
     // (NKW == 8 must not read cfg here: a value selected through the parameter struct leaves the uniform datapath and
     // every shared-memory address derived from the layout with it — measured 9.20 -> 9.44 ms per 70 000 images)
-    const int b_last = NKW > kNKP ? b_first : NKW == kNKP ? a.mma_words : (cfg.narrow_b != kBSmem ? a.mma_boff[4] : a.mma_words);
-    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR, NKW > kNKP);
+    const int b_last = NKW > kNKP ? b_first : NKW == kNKP ? a.mmah_end : (cfg.narrow_b != kBSmem ? a.mma_boff[4] : a.mma_words);
+    const V5Layout L = v5_layout(slot_bytes, pitch_bytes, n_slots, b_last - b_first, nlb, CR, v5_part_bytes(NKW));
     uint8_t* s_raw = smem + L.raw;
     uint8_t* s_luma = smem + L.luma;
     uint2* s_b = reinterpret_cast<uint2*>(smem + L.bfrag);
@@ -1542,7 +1586,127 @@ ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, 
         }
         return;
     }
-    // NKW == 8 (two CTAs per SM: 72 registers) and NKW == 0 (rows beyond ~2200 pixels): warps 4..7 own output pairs of the 9-wide target (warp 7: outputs 6, 7 and 8) END
+    if constexpr (NKW == kNKP) {
+        // Two CTAs per SM (72 registers here): outputs in two groups, (0..3) -> warps 4, 5 and (4..8) -> warps 6, 7; the two
+        // warps of a group split the group's band in halves (fragments in shared memory, two tiles per k-step), so each
+        // luma byte is read by at most two narrow warps instead of four.  The upper half hands its twelve accumulator
+        // words per lane to the lower one through shared memory (same lane mapping on both sides: conflict free, double
+        // buffered, one 64-thread named barrier per chunk); the lower warp rounds, writes the group's columns and runs
+        // their vertical pass.
+        const int j = warp - 4, grp = j >> 1;
+        const bool upper = j & 1;
+#ifdef KE_TUNING_PROBES
+        const int nkh = ((dbg & 2) || (dbg & 64)) ? 0 : a.mmah_nk[j];
+#else
+        const int nkh = (dbg & 2) ? 0 : a.mmah_nk[j];
+#endif
+        const uint2* bh = s_b + (a.mmah_boff[j] - b_first) + lane;
+        const uint32_t ah_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * pitch_bytes + (lane >> 4) * 16 + a.mmah_k0[j] * 32);
+        const int src = (lane & ~3) | 2;  // the quad's lane holding the third digits {a.d2, b.d2}
+        int32_t* xch = s_part + grp * (2 * kHalfSlots * 32) + lane;
+        const int gcol = 8 * j;  // the lower warp's private columns of plane 1 (j = 0 or 2)
+        const uint32_t* colh = reinterpret_cast<const uint32_t*>(scr + (gcol + g) * kHP);
+        int pb = 0;
+        for (long long im = blockIdx.x; im < a.n; im += gridDim.x) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vc[d][i] = d == 0 ? (1 << (kPrec - 1)) : 0;
+            int hc = 0;
+            for (int r0 = 0; r0 < a.h; r0 += CR, ++hc, lph ^= (lb + 1 == nlb), lb = lb + 1 == nlb ? 0 : lb + 1, pb ^= 1) {
+                mbar_wait_sleep(&l_full[lb], lph, poll_ns);
+                const uint32_t a_addr = smem_u32(s_luma + lb * L.luma_bytes) + ah_off;
+                int32_t c[NRB][2][4];
+#pragma unroll
+                for (int rb = 0; rb < NRB; ++rb)
+#pragma unroll
+                    for (int T = 0; T < 2; ++T)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) c[rb][T][i] = 0;
+#pragma unroll 2
+                for (int k = 0; k < nkh; ++k) {
+                    uint32_t a0[4], a1[4];
+                    ldmatrix_x4(a0, a_addr + k * 32);
+                    if (NRB == 2) ldmatrix_x4(a1, a_addr + k * 32 + 16 * pitch_bytes);
+#pragma unroll
+                    for (int T = 0; T < 2; ++T) {
+                        const uint2 b = bh[(k * 2 + T) * 32];
+                        mma_u8s8(c[0][T], a0, b);
+                        if (NRB == 2) mma_u8s8(c[NRB - 1][T], a1, b);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive1(&l_empty[lb]);  // this warp no longer reads the luma buffer
+                // digits -> values: lanes t < 2 hold output 2 T + t of the group, lanes t == 3 the ninth output (group 1)
+                int32_t v[NRB][3][2];
+#pragma unroll
+                for (int rb = 0; rb < NRB; ++rb)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                        for (int T = 0; T < 2; ++T) {
+                            const int32_t xa = __shfl_sync(0xffffffffu, c[rb][T][2 * hf], src);
+                            const int32_t xb = __shfl_sync(0xffffffffu, c[rb][T][2 * hf + 1], src);
+                            v[rb][T][hf] = c[rb][T][2 * hf] + (c[rb][T][2 * hf + 1] << 8) + ((t == 0 ? xa : xb) << 16);
+                        }
+                        v[rb][2][hf] = c[rb][0][2 * hf] + (c[rb][0][2 * hf + 1] << 8) + (c[rb][1][2 * hf] << 16);
+                    }
+                int32_t* x = xch + pb * (kHalfSlots * 32);
+                if (upper) {
+#pragma unroll
+                    for (int rb = 0; rb < NRB; ++rb)
+#pragma unroll
+                        for (int T = 0; T < 3; ++T)
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) x[((rb * 3 + T) * 2 + hf) * 32] = v[rb][T][hf];
+                }
+                if (grp == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+                else asm volatile("bar.sync 3, 64;" ::: "memory");
+                if (!upper) {
+                    const int row_off = CR == 32 ? 0 : (hc & 1) * 16;
+#pragma unroll
+                    for (int rb = 0; rb < NRB; ++rb)
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int row = row_off + rb * 16 + hf * 8 + g;
+#pragma unroll
+                            for (int T = 0; T < 2; ++T) {
+                                const int32_t sum = v[rb][T][hf] + x[((rb * 3 + T) * 2 + hf) * 32] + (1 << (kPrec - 1));
+                                if (t < 2) scr[(gcol + 2 * T + t) * kHP + row] = (uint8_t)pack_sat_u8(0, sum >> kPrec);
+                            }
+                            const int32_t s8 = v[rb][2][hf] + x[((rb * 3 + 2) * 2 + hf) * 32] + (1 << (kPrec - 1));
+                            if (t == 3 && grp == 1) scr[(gcol + 4) * kHP + row] = (uint8_t)pack_sat_u8(0, s8 >> kPrec);
+                        }
+                    __syncwarp();  // the group's columns are written
+                    const bool vstep = CR == 32 || (hc & 1) || r0 + CR >= a.h;
+                    const int ci = CR == 32 ? hc : hc >> 1;
+                    if (vstep && !(dbg & 4) && ci >= a.v_lo[2] && ci <= a.v_hi[2]) {
+                        const uint32_t b0 = colh[t], b1 = colh[4 + t];
+                        const uint4* af = a.vmma + ((size_t)(ci * 3 + 2) * 3) * 32 + lane;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) mma_s8u8(vc[d], __ldg(af + d * 32), b0, b1);
+                    }
+                    __syncwarp();  // every lane has read the columns before the next chunk overwrites them
+                }
+            }
+            if (!upper) {  // 8x9 plane: rows g; tile column 2 t + e is output 4 grp + 2 t + e (group 1: five outputs)
+                const int32_t v0 = vc[0][0] + (vc[1][0] << 8) + (vc[2][0] << 16);
+                const int32_t v1 = vc[0][1] + (vc[1][1] << 8) + (vc[2][1] << 16);
+                const uint32_t pk = pack_sat_u8(v1 >> kPrec, v0 >> kPrec);
+                const int xo = 4 * grp + 2 * t;
+                if (t < 2) {
+                    s_x98[g * kDW + xo] = (uint8_t)(pk & 0xFFu);
+                    s_x98[g * kDW + xo + 1] = (uint8_t)(pk >> 8);
+                } else if (t == 2 && grp == 1) {
+                    s_x98[g * kDW + 8] = (uint8_t)(pk & 0xFFu);
+                }
+            }
+            compute_sync<NW>();
+            dct_and_bits<NW>(a, im, s_x32, s_x98, s_t, s_y, tid, lane, warp);
+        }
+        return;
+    }
+    // NKW == 0 (rows beyond ~2200 pixels): warps 4..7 own output pairs of the 9-wide target (warp 7: outputs 6, 7 and 8) END
     // TO END, fragments behind a pointer: the pair's columns go into a private 8-column scratch (plane 1 of the row plane)
     // and come straight back as the B fragment of the 8x9 plane's vertical pass — six of the tile's eight columns are
     // padding, three MMAs per chunk are cheap, and no tap warp waits for another before the image is finished.
@@ -1618,8 +1782,8 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
         // run a few words past the last pixel
         const int slot = cfg.aligned ? (int)(sub * row_bytes) : (int)((sub * row_bytes + 64 + 127) / 128 * 128);
         if (nkw > kNKP) narrow = kBReg;  // one CTA per SM: the K-split narrow warps hold their fragments too, nothing in shared memory
-        const int words = (wide == kBSmem ? wide_words : 0) + (narrow == kBSmem ? narrow_words : 0);
-        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs, cr, nkw > kNKP);
+        const int words = nkw == kNKP ? a.mmah_end - a.mmah_boff[0] : (wide == kBSmem ? wide_words : 0) + (narrow == kBSmem ? narrow_words : 0);
+        const V5Layout L = v5_layout(slot, cfg.pitch_bytes, 1 << shift, words, bufs, cr, v5_part_bytes(nkw));
         if (L.total > budget) return false;
         cfg.sub_rows = sub, cfg.slot_shift = shift, cfg.nlb = bufs, cfg.slot_bytes = slot, cfg.cr = cr;
         cfg.wide_b = wide, cfg.narrow_b = narrow, cfg.smem_words = words, cfg.L = L, cfg.nkw = nkw;
@@ -1803,6 +1967,8 @@ extern "C" int ke_phash_batch(ke_ctx* ctx, const uint8_t* d_img, int64_t n, int 
     for (int i = 0; i < 8; ++i) a.mma_k0[i] = ht->mma_k0[i], a.mma_nk[i] = ht->mma_nk[i], a.mma_boff[i] = ht->mma_boff[i];
     for (int i = 0; i < 4; ++i) a.mmaq_k0[i] = ht->mmaq_k0[i], a.mmaq_nk[i] = ht->mmaq_nk[i], a.mmaq_boff[i] = ht->mmaq_boff[i];
     a.mmaq_kq = ht->mmaq_kq;
+    for (int i = 0; i < 4; ++i) a.mmah_k0[i] = ht->mmah_k0[i], a.mmah_nk[i] = ht->mmah_nk[i], a.mmah_boff[i] = ht->mmah_boff[i];
+    a.mmah_end = ht->mmah_end;
     a.vmma = vt->vmma_ok ? vt->d_vmma : nullptr;
     for (int i = 0; i < 3; ++i) a.v_lo[i] = vt->v_lo[i], a.v_hi[i] = vt->v_hi[i];
     a.meta = ht->d_meta;
