@@ -10,9 +10,10 @@
 //   * ke_phash_v5_kernel (default; "tensor-core kernel (v5)" below): persistent CTAs, raw rows by 1-D TMA bulk copies into
 //     a ring of sub-chunks, luma warps (dp2a), and eight tap warps that run BOTH Lanczos resamples exactly on the
 //     tensor pipe (mma.sync u8 x s8 over balanced base-256 tap digits), then the FP64 DCT.  It takes every batch of
-//     contiguous rows: any width (the resample band's B fragments sit in registers up to ~512 pixels, in shared memory
-//     up to ~1100, in L2 beyond), any byte alignment (the copies move the 16-byte aligned superset of a sub-chunk and
-//     the luma warps funnel-shift), 'L' / RGB / RGBA.
+//     contiguous rows: any width (the resample bands' B fragments sit in registers up to ~2200 pixels — two CTAs per SM up
+//     to ~512 pixels, one CTA per SM with setmaxnreg-enlarged tap warps beyond — and behind pointers into shared memory /
+//     L2 for longer rows), any byte alignment (the copies move the 16-byte aligned superset of a sub-chunk and the luma
+//     warps funnel-shift), 'L' / RGB / RGBA.
 //   * ke_phash_kernel (generic): one CTA of 256 threads per image stream, dp4a taps on CUDA cores, plain loads when the
 //     rows are strided.  It takes everything else (row_stride != w * c) and is the in-library reference the parity
 //     tests compare v5 with (KE_OPT_PHASH_GENERIC).  Its steps:
@@ -1199,13 +1200,15 @@ __device__ __noinline__ void luma_rows_any(const uint8_t* __restrict__ slot, int
 }
 
 // NKW = k-steps of wide-target resample fragments each wide warp keeps in REGISTERS:
-//   8   bands of <= 8 k-steps (widths up to ~512: the benchmark geometry); narrow-target fragments in shared memory;
-//       80 registers per thread, two CTAs per SM.
+//   8   bands of <= 8 k-steps (widths up to ~512: the benchmark geometry); 80 registers per thread, two CTAs per SM;
+//       narrow-target fragments in shared memory, the narrow warps work in two output groups x two band halves.
 //   16 / 32   longer rows (up to ~1100 / ~2200 pixels): ONE CTA per SM with 168 registers per thread at launch, which
-//       setmaxnreg redistributes — the wide warps take 200 / 232 and hold their whole band.  Shared memory was the
-//       bound there (ncu: the LSU data pipe at 60 % + the bulk-copy writes at 0.70 of HBM, a third of it fragment
-//       reads); narrow-target fragments behind a pointer (shared memory or L2).
-//   0   bands beyond that: every fragment behind a pointer into shared or global memory (L2).
+//       setmaxnreg redistributes — the wide warps take 200 / 232 and hold their whole band, the narrow warps take
+//       144 / 200 and hold a quarter of the row's k-steps for all nine outputs (K-split).  Shared memory was the bound
+//       there (ncu: the LSU data pipe at 60 % + the bulk-copy writes at 0.70 of HBM, a third of it fragment reads, a
+//       quarter the four narrow warps each reading nearly the whole row); nothing is left in shared memory but the rings.
+//   0   bands beyond that: every fragment behind a pointer into shared or global memory (L2), narrow warps own output
+//       pairs end to end.
 // ALIGNED = true: base, images and rows on 16-byte boundaries and w % 16 == 0 (exact copies, vector luma path).
 // The staging geometry comes as SCALAR kernel parameters and the shared-memory layout is recomputed in the kernel: with
 // the same values read from a parameter struct the compiler kept them off the uniform datapath and the 512x512 RGB case
@@ -1217,9 +1220,8 @@ __global__ void __launch_bounds__(kV5Threads, NKW > kNKP ? 1 : 2)
 ke_phash_v5_kernel(const PhashArgs a, const int sub_rows, const int slot_shift, const int pitch_bytes, const int nlb,
                    const int dbg, const V5Config cfg) {
     constexpr int NW = kV5Tap, NRB = CR / 16;
-    constexpr bool BMEM = NKW != kNKP;  // narrow-target (and, NKW == 0, wide-target) fragments behind a pointer
     static_assert(NKW == 0 || NKW == kNKP || NKW == 16 || NKW == 32, "register-resident bands of 8, 16 or 32 k-steps");
-    static_assert(CR == 32 || (CR == 16 && BMEM), "16-row buffers come with the pointer-fed narrow tap loops only");
+    static_assert(CR == 32 || (CR == 16 && NKW != kNKP), "the two-CTA kernel runs 32-row luma buffers only");
     extern __shared__ __align__(128) uint8_t smem[];
     const int row_bytes = a.w * C;
     const int sub_bytes = sub_rows * row_bytes;
