@@ -47,7 +47,8 @@ def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+        # the file holds ONE HBM figure (a burst copy, best of 10); K1 is timed inside the sustained, power-capped step
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json: burst copy)"
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
