@@ -1,7 +1,7 @@
 """ke_phash_batch_host (the call behind core.fastsig.compute_signatures_mp) from PAGEABLE and from page-locked host memory:
 images/s and GB/s of the whole call (host->device copies, kernels, hashes back), next to the bare pinned copy.
 
-    python tools/probe_host_path.py [n_images=12288]      # KE_STAGE_THREADS=4 by default
+    python tools/probe_host_path.py [n_images=12288]      # KE_STAGE_THREADS: default max(2, min(8, cores / 2))
 """
 import os
 import sys
@@ -33,7 +33,7 @@ def run(arr, label):
         best = min(best, time.perf_counter() - t0)
     assert np.array_equal(ph, want)
     print(f"{label}: {n} images in {best * 1e3:.1f} ms -> {n / best:.0f} img/s, {gb / best:.1f} GB/s "
-          f"(KE_STAGE_THREADS={os.environ.get('KE_STAGE_THREADS', '4')})", flush=True)
+          f"(KE_STAGE_THREADS={os.environ.get('KE_STAGE_THREADS', 'default')})", flush=True)
 
 
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

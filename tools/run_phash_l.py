@@ -1,5 +1,7 @@
+"""One K1 launch on 8192 'L' images of 512x512 (an `ncu` target)."""
 import sys
-sys.path.insert(0, "/root/repo/kobato-eyes_b200")
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "kobato-eyes_b200"))
 import torch
 from kobato_b200 import ops
 bank = ops.synth_images_device(0, 8192, 512, 512, 1, n_set=8192)
