@@ -1817,6 +1817,13 @@ bool v5_config(const PhashArgs& a, V5Config& cfg, int forced) {
     // narrow-target fragments moved out to L2 where that is what it takes.
     const int wide_chip = nkw_reg ? kBReg : kBSmem, wide_l2 = nkw_reg ? kBReg : kBGmem;
     const Place places[] = {{227 * 1024, wide_chip, kBSmem}, {227 * 1024, wide_l2, kBSmem}, {227 * 1024, wide_l2, kBGmem}};
+    // Between the regimes (bands of 9+ k-steps on rows still short enough for TWO CTAs of the pointer-fed kernel, every
+    // fragment in L2): two CTAs hide each other's per-chunk chain, which a single CTA on short rows cannot — measured
+    // 0.71 against 0.58 at 640 pixels, 0.71 / 0.72 against 0.68 / 0.69 at 768 / 800; at 1024 the register kernel wins (0.84+)
+    if (nkw_reg > kNKP && a.w < 900)
+        for (int sub : {16, 8, 4})
+            for (int narrow : {kBSmem, kBGmem})
+                if (sub * row_bytes >= min_slot && fits(113 * 1024, kBGmem, narrow, 2, sub, 1, 32)) return true;
     // register-resident bands: 32-row buffers while two of them fit beside sub-chunks of >= 8 rows (1024 pixels: 0.85 of
     // HBM against 0.82-0.84 with 16-row buffers), else 16-row buffers (2048 pixels: 0.887 with 8-row sub-chunks; 4-row
     // sub-chunks, whatever the buffers, stay at 0.63)

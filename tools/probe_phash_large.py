@@ -1,6 +1,6 @@
 """K1 on larger photographs: time the streaming kernel under pinned staging configurations (KE_OPT_PHASH_CFG).
 
-    python tools/probe_phash_large.py [--auto]   # 512 ... 4000-pixel rows, the automatic configuration (+ a sweep)
+    python tools/probe_phash_large.py [--auto] [HxWxC ...]   # default: 512 ... 4000-pixel rows; the automatic configuration (+ a sweep)
 """
 import json
 import sys
@@ -33,8 +33,9 @@ def timed(fn, reps=3):
 
 
 out = {}
-for (h, w, c) in ((512, 512, 3), (1024, 1024, 3), (1536, 2048, 3), (3000, 4000, 3)):
-    n = max(16, int(4e9) // (h * w * c))
+shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:] if "x" in a]  # e.g. 768x768x3 (h x w x c)
+for (h, w, c) in (shapes or ((512, 512, 3), (1024, 1024, 3), (1536, 2048, 3), (3000, 4000, 3))):
+    n = max(16, int(4e9) // (h * w * c) // 296 * 296 or 16)
     bank = torch.empty((n, h, w, c), dtype=torch.uint8, device="cuda")
     for lo in range(0, n, 128):
         k = min(128, n - lo)
